@@ -1,0 +1,165 @@
+/*
+ * b200coord.h -- C ABI of the B200-native COORDINATION + neighbour-list engine (libb200coord.so).
+ *
+ * This is the drop-in boundary: a PLUMED action (plumed2_b200/csrc/plugin/CoordinationB200.cpp,
+ * registered with PLUMED_REGISTER_ACTION as "COORDINATION") or any other host (the ctypes mirror in
+ * plumed2_b200/coordination.py, an MD engine) calls only these functions.  Plain C types, caller-owned
+ * host arrays, library-owned device memory.  Every function returns 0 on success and a non-zero
+ * B200COORD_ERR_* code otherwise -- it never throws and never falls back to a CPU path: if no usable
+ * CUDA device / kernel image is present the call fails and b200coord_last_error() says why.
+ *
+ * Reference interfaces replaced (paths relative to plumed2 v2.11.0-dev, /root/reference):
+ *   b200coord_switch_parse / _rational   <- SwitchingFunction::set            src/tools/SwitchingFunction.cpp:1055-1159, :1176-1184
+ *   b200coord_create                     <- CoordinationBase ctor + NeighborList ctors
+ *                                           src/colvar/CoordinationBase.cpp:42-131, src/tools/NeighborList.cpp:43-141
+ *   b200coord_set_box                    <- Pbc::setBox                       src/tools/Pbc.cpp:165-212
+ *   b200coord_prepare                    <- CoordinationBase::prepare -> NeighborList::prepare
+ *                                           src/colvar/CoordinationBase.cpp:137-139, src/tools/NeighborList.cpp:433-456
+ *   b200coord_update_list                <- NeighborList::update              src/tools/NeighborList.cpp:168-315
+ *   b200coord_calculate                  <- CoordinationBase::calculate       src/colvar/CoordinationBase.cpp:142-232
+ *   b200coord_comm_*                     <- Communicator::Sum (MPI_Allreduce) src/tools/Communicator.cpp:194-201,
+ *                                           called at src/colvar/CoordinationBase.cpp:218-224
+ *   b200coord_nl_size / _nl_pairs        <- NeighborList::size / getClosePair src/tools/NeighborList.cpp:369-389
+ */
+#ifndef B200COORD_H
+#define B200COORD_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200COORD_ABI_VERSION 1
+
+/* error codes */
+enum {
+  B200COORD_OK = 0,
+  B200COORD_ERR_INVALID = 1,   /* bad argument / unsupported keyword combination */
+  B200COORD_ERR_CUDA = 2,      /* CUDA runtime error (no device, launch failure, OOM) */
+  B200COORD_ERR_PARSE = 3,     /* SWITCH string could not be parsed */
+  B200COORD_ERR_UNSUPPORTED = 4, /* valid in the reference but not available on the GPU (SWITCH=CUSTOM) */
+  B200COORD_ERR_NCCL = 5,
+  B200COORD_ERR_STATE = 6      /* call order violated (e.g. calculate before set_box with PBC) */
+};
+
+/* pair-list style, reference NeighborList::NNStyle (src/tools/NeighborList.h:44) */
+enum { B200COORD_STYLE_PAIR = 0, B200COORD_STYLE_TWOLIST = 1, B200COORD_STYLE_SINGLELIST = 2 };
+
+/* neighbour-list mode: none (all pairs, NL off), NLIST (distance filtered), NLISTCELLS (27-cell superset) */
+enum { B200COORD_NL_NONE = 0, B200COORD_NL_CLASSIC = 1, B200COORD_NL_CELLS = 2 };
+
+/* arithmetic of the pair sweep: FP64 (default, 1e-10 parity) or the opt-in FP32 mode (1e-5 parity;
+ * positions relative to the cell, FP32 pair math, FP64 accumulation) */
+enum { B200COORD_FP64 = 0, B200COORD_FP32 = 1 };
+
+/* switching-function kinds, same order as switchContainers::switchType (src/tools/SwitchingFunction.h:36-57) */
+enum {
+  B200COORD_SW_RATIONALFIX12 = 0, B200COORD_SW_RATIONALFIX10, B200COORD_SW_RATIONALFIX8,
+  B200COORD_SW_RATIONALFIX6, B200COORD_SW_RATIONALFIX4, B200COORD_SW_RATIONALFIX2,
+  B200COORD_SW_RATIONAL, B200COORD_SW_RATIONALFAST, B200COORD_SW_RATIONALSIMPLE, B200COORD_SW_RATIONALSIMPLEFAST,
+  B200COORD_SW_EXPONENTIAL, B200COORD_SW_GAUSSIAN, B200COORD_SW_FASTGAUSSIAN, B200COORD_SW_SMAP,
+  B200COORD_SW_CUBIC, B200COORD_SW_TANH, B200COORD_SW_COSINUS, B200COORD_SW_NATIVEQ,
+  B200COORD_SW_LEPTON, B200COORD_SW_NOT_INITIALIZED
+};
+
+/* mirrors switchContainers::Data (src/tools/SwitchingFunction.h:58-94) */
+typedef struct b200coord_switch {
+  int type;
+  double d0, dmax, dmax_2, invr0, invr0_2, stretch, shift;
+  int nn, mm;
+  double preRes, preDfunc, preSecDev;
+  int nnf, mmf;
+  double preDfuncF, preSecDevF;
+  int a, b;
+  double c, d;
+  double beta, lambda, ref;
+} b200coord_switch;
+
+typedef struct b200coord_config {
+  int abi_version;       /* must be B200COORD_ABI_VERSION */
+  int device;            /* CUDA device ordinal, -1 = the calling thread's current device */
+  int precision;         /* B200COORD_FP64 | B200COORD_FP32 */
+  int style;             /* B200COORD_STYLE_* ; SINGLELIST when GROUPB is empty, PAIR for the PAIR flag */
+  unsigned n_group_a;    /* atoms in GROUPA */
+  unsigned n_group_b;    /* atoms in GROUPB (0 for SINGLELIST) */
+  int pbc;               /* 1 unless NOPBC */
+  int nl_mode;           /* B200COORD_NL_* */
+  double nl_cutoff;      /* NL_CUTOFF (>0 when nl_mode != NONE) */
+  int nl_stride;         /* NL_STRIDE (>0 when nl_mode != NONE) */
+  int rank;              /* this context's share of the i-atoms, like the MPI stride split ... */
+  int nranks;            /* ... CoordinationBase.cpp:152-170 ; 0/1 = everything */
+} b200coord_config;
+
+typedef struct b200coord_stats {
+  unsigned long long nl_size;        /* list entries the reference would iterate (nl->size()), self-pairs included */
+  unsigned long long pair_evals;     /* pair evaluations this context executed in the last calculate (both directions) */
+  unsigned long long kernel_launches;/* kernels launched by this context since creation */
+  unsigned long long rebuilds;       /* neighbour-list rebuilds since creation */
+  float last_sweep_ms;               /* CUDA-event time of the last pair-sweep kernel */
+  float last_build_ms;               /* CUDA-event time of the last list rebuild (all its kernels) */
+  float last_h2d_ms, last_d2h_ms;    /* last host<->device copies inside calculate */
+  unsigned ncells[3];                /* cell grid in use */
+  int pbc_type;                      /* 0 unset, 1 orthorhombic, 2 generic (Pbc.h:52) */
+} b200coord_stats;
+
+typedef struct b200coord_ctx b200coord_ctx;
+
+int b200coord_abi_version(void);
+
+/* ---- switching function set-up (host only, no CUDA needed) */
+/* SWITCH={...} form; err (may be NULL) receives the reference's error text */
+int b200coord_switch_parse(const char* definition, b200coord_switch* out, char* err, size_t errlen);
+/* R_0= NN= MM= D_0= keyword form: automatic D_MAX and stretch (SwitchingFunction.cpp:1176-1184) */
+int b200coord_switch_rational(int nn, int mm, double r0, double d0, b200coord_switch* out);
+/* text like SwitchingFunction::description() for the action's log */
+int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen);
+
+/* ---- life cycle */
+/* abs_index: n_group_a+n_group_b absolute atom indices in GROUPA-then-GROUPB order (self-pair skip by
+ * absolute index, CoordinationBase.cpp:183) */
+int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, const unsigned* abs_index,
+                     b200coord_ctx** out);
+void b200coord_destroy(b200coord_ctx* ctx);
+/* last error text of this context (ctx==NULL: of the last failed create/parse in this thread) */
+const char* b200coord_last_error(const b200coord_ctx* ctx);
+
+/* ---- per step */
+/* box: 9 doubles row-major, box[3*i+j] = j-th component of lattice vector i; all zeros = no box */
+int b200coord_set_box(b200coord_ctx* ctx, const double box[9]);
+/* neighbour-list schedule; *will_rebuild = 1 when the next calculate rebuilds the list.
+ * Returns B200COORD_ERR_STATE for a non-rebuild exchange step (NeighborList.cpp:447-449) */
+int b200coord_prepare(b200coord_ctx* ctx, long step, int exchange_step, int* will_rebuild);
+/* force a rebuild from these host positions now (NeighborList::update) */
+int b200coord_update_list(b200coord_ctx* ctx, const double* pos);
+/* pos: n*3 host doubles (AoS, GROUPA then GROUPB).  Outputs (host): *value, deriv n*3, virial 9 (row-major).
+ * With a communicator attached the outputs are the sums over all ranks on every rank. */
+int b200coord_calculate(b200coord_ctx* ctx, const double* pos, double* value, double* deriv, double* virial);
+/* same with device-resident buffers: d_pos n*3 doubles, d_out 3n+10 doubles = [deriv | virial(9) | value] */
+int b200coord_calculate_device(b200coord_ctx* ctx, const double* d_pos, double* d_out);
+
+/* ---- inspection */
+int b200coord_get_stats(const b200coord_ctx* ctx, b200coord_stats* out);
+/* current list as (i0,i1) index pairs into the position array, sorted by (i0,i1); self-pairs included as the
+ * reference lists them.  *n receives the number of pairs; pairs may be NULL to query the size only. */
+int b200coord_nl_pairs(b200coord_ctx* ctx, unsigned* pairs, unsigned long long capacity, unsigned long long* n);
+
+/* ---- multi-GPU (one context per GPU/process; i-atoms sharded by cfg.rank/nranks) */
+#define B200COORD_UNIQUE_ID_BYTES 128
+int b200coord_comm_unique_id(char id[B200COORD_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */
+int b200coord_comm_init(b200coord_ctx* ctx, const char id[B200COORD_UNIQUE_ID_BYTES]); /* every rank */
+
+/* ---- pinned host memory for callers that want full-speed copies */
+int b200coord_host_alloc(size_t bytes, void** ptr);
+int b200coord_host_free(void* ptr);
+/* raw device scratch for benchmarks/tests that keep inputs resident in HBM */
+int b200coord_device_alloc(size_t bytes, void** dptr);
+int b200coord_device_free(void* dptr);
+int b200coord_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
+int b200coord_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
+int b200coord_device_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200COORD_H */

@@ -1,0 +1,857 @@
+// C ABI of libb200coord.so (include/b200coord.h): context, neighbour-list schedule, rebuild and sweep
+// orchestration on one CUDA stream, host<->device staging, optional NCCL combine across ranks.
+// There is no CPU fallback anywhere in this file: every numeric result comes from the kernels in
+// kernels_build.cu / kernels_sweep.cu, and a missing device or kernel image is an error.
+#include "../../include/b200coord.h"
+#include "host_setup.hpp"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// ---- NCCL resolved lazily with dlopen so that single-GPU users need no libnccl at all
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.handle || api.ok) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+#define B200_SYM(field, sym) *(void**)(&api.field) = dlsym(api.handle, sym)
+  B200_SYM(GetUniqueId, "ncclGetUniqueId");
+  B200_SYM(CommInitRank, "ncclCommInitRank");
+  B200_SYM(CommDestroy, "ncclCommDestroy");
+  B200_SYM(AllGather, "ncclAllGather");
+  B200_SYM(AllReduce, "ncclAllReduce");
+  B200_SYM(GroupStart, "ncclGroupStart");
+  B200_SYM(GroupEnd, "ncclGroupEnd");
+  B200_SYM(GetErrorString, "ncclGetErrorString");
+#undef B200_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce && api.GroupStart &&
+           api.GroupEnd && api.GetErrorString;
+  return api;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8 + 16;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct b200coord_ctx {
+  b200coord_config cfg;
+  b200coord_switch sw;
+  DevSwitch dsw;
+  unsigned n = 0, n_a = 0, n_b = 0;
+  int two_groups = 0, check_abs = 0;
+  unsigned long long n_self_pairs = 0;  // listed by the reference, skipped by the sweep
+  std::vector<unsigned> abs_host;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8] = {nullptr};  // 0/1 h2d, 2/3 sweep, 4/5 build, 6/7 d2h
+  bool ev_valid[4] = {false, false, false, false};
+
+  HostPbc hpbc;
+  DevPbc dpbc;
+  bool box_set = false;
+  double box_cached[9] = {0};
+  DevGrid grid;
+  bool sorted_valid = false;  // perm/scell/cstart/ccount describe the current grouping
+  bool list_valid = false;
+
+  // schedule (CoordinationBase members firsttime / invalidateList, CoordinationBase.cpp:46-47)
+  bool firsttime = true, invalidate = true;
+
+  // rows of this rank
+  unsigned row_begin = 0, row_end = 0, row_chunk = 0;
+
+  DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small;
+  DevBuf<uint32_t> d_abs, d_perm, d_scell, d_cell_of_slot, d_tmp, d_ccount, d_cstart, d_cursor, d_rowcount, d_nbr;
+  DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch
+  DevBuf<SPos> d_spos;
+  DevBuf<uint8_t> d_active;
+  unsigned long long nbr_total = 0;
+  int sweep_blocks = 0;
+
+  double* h_small = nullptr;  // pinned: [0..9] tail, [10..15] bbox
+  unsigned long long* h_u64 = nullptr;  // pinned: [0] grand total, [1] evals
+
+  ncclComm_t comm = nullptr;
+  b200coord_stats stats;
+  std::string err;
+};
+
+namespace {
+
+int fail(b200coord_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CU(c, expr)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(c, B200COORD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+#define CU_LAST(c, what)                                                                                \
+  do {                                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                                               \
+    if (e__ != cudaSuccess) return fail(c, B200COORD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+void to_dev_switch(const b200coord_switch& s, DevSwitch& d) {
+  d.type = s.type;
+  d.d0 = s.d0; d.dmax = s.dmax; d.dmax_2 = s.dmax_2; d.invr0 = s.invr0; d.invr0_2 = s.invr0_2;
+  d.stretch = s.stretch; d.shift = s.shift;
+  d.nn = s.nn; d.mm = s.mm; d.preRes = s.preRes; d.preDfunc = s.preDfunc; d.preSecDev = s.preSecDev;
+  d.nnf = s.nnf; d.mmf = s.mmf; d.preDfuncF = s.preDfuncF; d.preSecDevF = s.preSecDevF;
+  d.a = s.a; d.b = s.b; d.c = s.c; d.d = s.d; d.beta = s.beta; d.lambda = s.lambda; d.ref = s.ref;
+  // rationalfixN evaluates y^(N/2-1): keep N/2 in nnf for the device (the host struct leaves the default there)
+  switch (s.type) {
+    case B200COORD_SW_RATIONALFIX12: d.nnf = 6; break;
+    case B200COORD_SW_RATIONALFIX10: d.nnf = 5; break;
+    case B200COORD_SW_RATIONALFIX8: d.nnf = 4; break;
+    case B200COORD_SW_RATIONALFIX6: d.nnf = 3; break;
+    case B200COORD_SW_RATIONALFIX4: d.nnf = 2; break;
+    case B200COORD_SW_RATIONALFIX2: d.nnf = 1; break;
+    default: break;
+  }
+}
+
+void to_dev_pbc(const HostPbc& h, bool use_pbc, DevPbc& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.type = use_pbc ? h.type : 0;
+  std::memcpy(d.box, h.box, sizeof(d.box));
+  std::memcpy(d.inv_box, h.inv_box, sizeof(d.inv_box));
+  std::memcpy(d.reduced, h.reduced, sizeof(d.reduced));
+  std::memcpy(d.inv_reduced, h.inv_reduced, sizeof(d.inv_reduced));
+  std::memcpy(d.nshift, h.nshift, sizeof(d.nshift));
+  std::memcpy(d.shifts, h.shifts, sizeof(d.shifts));
+}
+
+bool box_is_zero(const double b[9]) {
+  for (int i = 0; i < 9; ++i)
+    if (b[i] != 0.0) return false;
+  return true;
+}
+
+void set_grid_from_box(DevGrid& g, const double inv_box[9], const unsigned nc[3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) g.inv_box_t[3 * i + j] = inv_box[3 * j + i];
+  for (int k = 0; k < 3; ++k) g.n[k] = (int)nc[k];
+  g.ncell = g.n[0] * g.n[1] * g.n[2];
+}
+
+// cell grid for the coming rebuild.  NLISTCELLS: exactly LinkCells::setupCells (LinkCells.cpp:49-122).
+// NLIST: our own grid, cell width >= cutoff*(1+1e-6), only used to FIND candidates (the kept set is decided
+// by the exact distance test, so the grid cannot change it).
+int setup_grid(b200coord_ctx* c, const double* d_pos) {
+  DevGrid& g = c->grid;
+  std::memset(&g, 0, sizeof(g));
+  const bool cells_mode = (c->cfg.nl_mode == B200COORD_NL_CELLS);
+  const double cut = cells_mode ? c->cfg.nl_cutoff : c->cfg.nl_cutoff * (1.0 + 1e-6);
+  bool use_bbox;
+  if (cells_mode) {
+    use_bbox = box_is_zero(c->hpbc.box);
+    if (!use_bbox && c->hpbc.type == 0)
+      return fail(c, B200COORD_ERR_INVALID, "Cell lists cannot be built when passing a box with null volume");
+    g.stencil_pbc = c->cfg.pbc ? 1 : 0;
+  } else {
+    use_bbox = !(c->cfg.pbc && c->hpbc.type != 0);
+    g.stencil_pbc = use_bbox ? 0 : 1;
+  }
+  g.bbox = use_bbox ? 1 : 0;
+  unsigned nc[3];
+  if (use_bbox) {
+    launch_bbox(d_pos, c->n, c->d_small.p + 16, c->d_u64.p + 2, c->st);
+    c->stats.kernel_launches += 2;
+    CU(c, cudaMemcpyAsync(c->h_small + 10, c->d_small.p + 16, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    double box[9] = {0};
+    for (int k = 0; k < 3; ++k) {
+      const double mn = c->h_small[10 + k], mx = c->h_small[13 + k];
+      box[4 * k] = (cut < std::sqrt(1.79769313486231570e308)) ? cut * (1 + std::ceil((mx - mn) / cut)) : (mx - mn + 1);
+      g.origin[k] = (mn + mx) / 2;
+    }
+    HostPbc bb;
+    setup_pbc(box, bb);
+    cell_grid(bb.inv_box, cut, nc);
+    set_grid_from_box(g, bb.inv_box, nc);
+  } else {
+    cell_grid(c->hpbc.inv_box, cut, nc);
+    set_grid_from_box(g, c->hpbc.inv_box, nc);
+  }
+  if ((unsigned long long)nc[0] * nc[1] * nc[2] > 400000000ull)
+    return fail(c, B200COORD_ERR_INVALID, "cell grid too large for the given NL_CUTOFF and box");
+  for (int k = 0; k < 3; ++k) c->stats.ncells[k] = nc[k];
+  return B200COORD_OK;
+}
+
+int ensure_cell_arrays(b200coord_ctx* c) {
+  const size_t m = (size_t)(c->two_groups ? 2 : 1) * (size_t)c->grid.ncell;
+  CU(c, c->d_ccount.reserve(m));
+  CU(c, c->d_cstart.reserve(m));
+  CU(c, c->d_cursor.reserve(m));
+  return B200COORD_OK;
+}
+
+// no neighbour list: one "cell" per group holding every atom in slot order (NeighborList.cpp:133-140 order)
+int setup_all_pairs(b200coord_ctx* c) {
+  DevGrid& g = c->grid;
+  std::memset(&g, 0, sizeof(g));
+  g.n[0] = g.n[1] = g.n[2] = 1;
+  g.ncell = 1;
+  g.stencil_pbc = 0;
+  int rc = ensure_cell_arrays(c);
+  if (rc) return rc;
+  const uint32_t starts[2] = {0u, c->n_a}, counts[2] = {c->n_a, c->n_b};
+  const size_t m = c->two_groups ? 2 : 1;
+  CU(c, cudaMemcpyAsync(c->d_cstart.p, starts, m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->d_ccount.p, counts, m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+  launch_identity(c->n, c->d_perm.p, c->d_scell.p, c->st);
+  c->stats.kernel_launches += 1;
+  CU(c, cudaStreamSynchronize(c->st));  // starts/counts live on this stack frame
+  CU_LAST(c, "identity perm");
+  c->sorted_valid = true;
+  for (int k = 0; k < 3; ++k) c->stats.ncells[k] = 1;
+  return B200COORD_OK;
+}
+
+// NeighborList::update (NeighborList.cpp:168-315) on the device
+int rebuild(b200coord_ctx* c, const double* d_pos) {
+  const int mode = c->cfg.nl_mode;
+  if (c->cfg.style == B200COORD_STYLE_PAIR) {
+    if (mode == B200COORD_NL_CLASSIC) {
+      CU(c, c->d_active.reserve(c->n_a));
+      CU(c, cudaEventRecord(c->ev[4], c->st));
+      launch_pair_mask(d_pos, c->n_a, c->dpbc, c->cfg.nl_cutoff * c->cfg.nl_cutoff, c->d_active.p, c->st);
+      CU(c, cudaEventRecord(c->ev[5], c->st));
+      c->ev_valid[2] = true;
+      c->stats.kernel_launches += 1;
+      c->stats.rebuilds++;
+    }
+    c->list_valid = true;
+    return B200COORD_OK;
+  }
+  if (mode == B200COORD_NL_NONE) {
+    if (!c->sorted_valid) {
+      int rc = setup_all_pairs(c);
+      if (rc) return rc;
+    }
+    c->list_valid = true;
+    return B200COORD_OK;
+  }
+  CU(c, cudaEventRecord(c->ev[4], c->st));
+  int rc = setup_grid(c, d_pos);
+  if (rc) return rc;
+  rc = ensure_cell_arrays(c);
+  if (rc) return rc;
+  launch_sort(d_pos, c->n, c->n_a, c->two_groups ? 2 : 1, c->grid, c->d_cell_of_slot.p, c->d_ccount.p, c->d_cstart.p,
+              c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->st);
+  c->stats.kernel_launches += 4;
+  c->sorted_valid = true;
+  if (mode == B200COORD_NL_CLASSIC) {
+    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+    const unsigned rows = c->row_end - c->row_begin;
+    CU(c, c->d_rowcount.reserve(rows + 1));
+    CU(c, c->d_rowstart.reserve(rows + 1));
+    CU(c, c->d_bsum.reserve(rows / 1024 + 2));
+    const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
+    launch_nl_rows(false, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
+                   c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, nullptr, nullptr, c->st);
+    launch_scan_rows(c->d_rowcount.p, rows, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
+    CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    CU_LAST(c, "neighbour list count");
+    c->nbr_total = c->h_u64[0];
+    CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 1));
+    launch_nl_rows(true, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
+                   c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p, c->d_nbr.p, c->st);
+    c->stats.kernel_launches += 6;
+  }
+  CU(c, cudaEventRecord(c->ev[5], c->st));
+  c->ev_valid[2] = true;
+  CU_LAST(c, "neighbour list rebuild");
+  c->stats.rebuilds++;
+  c->list_valid = true;
+  return B200COORD_OK;
+}
+
+int combine_ranks(b200coord_ctx* c) {
+  NcclApi& api = nccl_api();
+  ncclResult_t r;
+  if (c->cfg.style == B200COORD_STYLE_PAIR) {
+    r = api.AllReduce(c->d_out.p, c->d_out.p, (size_t)3 * c->n + 10, ncclDouble, ncclSum, c->comm, c->st);
+    if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
+    return B200COORD_OK;
+  }
+  // every rank owns complete derivatives for its rows: all-gather the row slices (sorted order), and
+  // all-reduce the 10 scalars (virial + value) -- the Comm::Sum of CoordinationBase.cpp:218-224
+  api.GroupStart();
+  r = api.AllGather(c->d_sderiv.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_sderiv.p, (size_t)3 * c->row_chunk,
+                    ncclDouble, c->comm, c->st);
+  ncclResult_t r2 = api.AllReduce(c->d_out.p + (size_t)3 * c->n, c->d_out.p + (size_t)3 * c->n, 10, ncclDouble, ncclSum,
+                                  c->comm, c->st);
+  ncclResult_t r3 = api.GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess || r3 != ncclSuccess)
+    return fail(c, B200COORD_ERR_NCCL, std::string("nccl combine: ") +
+                                           api.GetErrorString(r != ncclSuccess ? r : (r2 != ncclSuccess ? r2 : r3)));
+  return B200COORD_OK;
+}
+
+// the whole per-step device pipeline on c->st; d_pos device positions, result left in c->d_out
+int run_device(b200coord_ctx* c, const double* d_pos) {
+  if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
+  const bool need_rebuild = !c->list_valid || (c->cfg.nl_mode != B200COORD_NL_NONE && c->invalidate);
+  if (need_rebuild) {
+    int rc = rebuild(c, d_pos);
+    if (rc) return rc;
+    c->invalidate = false;
+  }
+  CU(c, cudaMemsetAsync(c->d_u64.p + 1, 0, sizeof(unsigned long long), c->st));
+  int nblocks;
+  double weight;
+  if (c->cfg.style == B200COORD_STYLE_PAIR) {
+    const unsigned chunk = (c->n_a + (unsigned)c->cfg.nranks - 1) / (unsigned)c->cfg.nranks;
+    const unsigned pb = std::min(c->n_a, chunk * (unsigned)c->cfg.rank), pe = std::min(c->n_a, pb + chunk);
+    if (c->cfg.nranks > 1) CU(c, cudaMemsetAsync(c->d_out.p, 0, sizeof(double) * 3 * (size_t)c->n, c->st));
+    CU(c, c->d_partials.reserve((size_t)kPartialStride * ((pe - pb) / 256 + 2)));
+    CU(c, cudaEventRecord(c->ev[2], c->st));
+    nblocks = launch_sweep_pairs(d_pos, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
+                                 c->n_a, pb, pe, c->dpbc, c->dsw, c->d_out.p, c->d_partials.p, c->d_u64.p + 1, c->st);
+    CU(c, cudaEventRecord(c->ev[3], c->st));
+    weight = 1.0;
+    c->stats.kernel_launches += 1;
+  } else {
+    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+    SweepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.spos = c->d_spos.p;
+    a.n_a = c->n_a;
+    a.two_groups = c->two_groups;
+    a.check_abs = c->check_abs;
+    a.row_begin = c->row_begin;
+    a.row_end = c->row_end;
+    a.row_start = c->d_rowstart.p;
+    a.row_count = c->d_rowcount.p;
+    a.nbr = c->d_nbr.p;
+    a.scell = c->d_scell.p;
+    a.cstart = c->d_cstart.p;
+    a.ccount = c->d_ccount.p;
+    a.grid = c->grid;
+    a.sderiv = c->d_sderiv.p;
+    a.evals = c->d_u64.p + 1;
+    CU(c, c->d_partials.reserve((size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 2)));
+    a.partials = c->d_partials.p;
+    CU(c, cudaEventRecord(c->ev[2], c->st));
+    nblocks = (c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? launch_sweep_list(a, c->dpbc, c->dsw, c->st)
+                                                        : launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
+    CU(c, cudaEventRecord(c->ev[3], c->st));
+    weight = c->two_groups ? 1.0 : 0.5;
+    c->stats.kernel_launches += 1 + (c->two_groups ? 2 : 1);
+  }
+  c->ev_valid[1] = true;
+  if (nblocks < 0) return fail(c, B200COORD_ERR_UNSUPPORTED, "switching function type has no GPU kernel");
+  CU_LAST(c, "pair sweep launch");
+  c->sweep_blocks = nblocks;
+  launch_finalize(c->d_partials.p, nblocks, weight, c->d_out.p + (size_t)3 * c->n, c->st);
+  c->stats.kernel_launches += 1;
+  if (c->comm) {
+    int rc = combine_ranks(c);
+    if (rc) return rc;
+  }
+  if (c->cfg.style != B200COORD_STYLE_PAIR) {
+    launch_unsort_derivs(c->d_sderiv.p, c->d_spos.p, c->n, c->d_out.p, c->st);
+    c->stats.kernel_launches += 1;
+  }
+  CU(c, cudaMemcpyAsync(c->h_u64 + 1, c->d_u64.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+  CU_LAST(c, "finalize");
+  return B200COORD_OK;
+}
+
+void refresh_stats(b200coord_ctx* c) {
+  c->stats.pair_evals = c->h_u64[1];
+  const unsigned long long n = c->n;
+  switch (c->cfg.nl_mode) {
+    case B200COORD_NL_CLASSIC:
+      c->stats.nl_size = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : c->nbr_total / 2 + (c->cfg.rank == 0 ? c->n_self_pairs : 0);
+      break;
+    case B200COORD_NL_CELLS:
+      c->stats.nl_size = c->two_groups ? c->h_u64[1] / 2 : (c->h_u64[1] - (c->row_end - c->row_begin)) / 2;
+      break;
+    default:
+      if (c->cfg.style == B200COORD_STYLE_PAIR) c->stats.nl_size = c->n_a;
+      else if (c->two_groups) c->stats.nl_size = (unsigned long long)c->n_a * c->n_b;
+      else c->stats.nl_size = n * (n - 1) / 2;
+  }
+  c->stats.pbc_type = c->hpbc.type;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int b200coord_abi_version(void) { return B200COORD_ABI_VERSION; }
+
+int b200coord_switch_parse(const char* definition, b200coord_switch* out, char* err, size_t errlen) {
+  if (!definition || !out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  std::string e;
+  const int rc = parse_switch(definition, *out, e);
+  if (err && errlen) std::snprintf(err, errlen, "%s", e.c_str());
+  if (rc) g_last_error = e;
+  return rc;
+}
+
+int b200coord_switch_rational(int nn, int mm, double r0, double d0, b200coord_switch* out) {
+  if (!out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  if (!(r0 > 0.0)) return fail(nullptr, B200COORD_ERR_INVALID, "R_0 should be explicitly specified and positive");
+  rational_switch(nn, mm, r0, d0, *out);
+  return B200COORD_OK;
+}
+
+int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen) {
+  if (!sw || !buf || !buflen) return B200COORD_ERR_INVALID;
+  std::snprintf(buf, buflen, "%s", describe_switch(*sw).c_str());
+  return B200COORD_OK;
+}
+
+const char* b200coord_last_error(const b200coord_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, const unsigned* abs_index,
+                     b200coord_ctx** out) {
+  if (!cfg || !sw || !out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != B200COORD_ABI_VERSION) return fail(nullptr, B200COORD_ERR_INVALID, "ABI version mismatch");
+  if (cfg->style < 0 || cfg->style > 2) return fail(nullptr, B200COORD_ERR_INVALID, "unknown list style");
+  // the keyword rules of CoordinationBase.cpp:69-83 and NeighborList.cpp:71-79
+  if (cfg->nl_mode == B200COORD_NL_CELLS && cfg->style == B200COORD_STYLE_PAIR)
+    return fail(nullptr, B200COORD_ERR_INVALID, "Pair is not compatible with the CELLS implementation of the NL");
+  if (cfg->nl_mode != B200COORD_NL_NONE) {
+    if (!(cfg->nl_cutoff > 0.0)) return fail(nullptr, B200COORD_ERR_INVALID, "NL_CUTOFF should be explicitly specified and positive");
+    if (cfg->nl_stride <= 0) return fail(nullptr, B200COORD_ERR_INVALID, "NL_STRIDE should be explicitly specified and positive");
+  }
+  if (cfg->style == B200COORD_STYLE_PAIR && cfg->n_group_a != cfg->n_group_b)
+    return fail(nullptr, B200COORD_ERR_INVALID,
+                "when using PAIR option, the two groups should have the same number of elements");
+  if (cfg->style == B200COORD_STYLE_SINGLELIST && cfg->n_group_b != 0)
+    return fail(nullptr, B200COORD_ERR_INVALID, "SINGLELIST style takes GROUPA only");
+  if (sw->type < 0 || sw->type >= B200COORD_SW_LEPTON)
+    return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "switching function is not available on the GPU");
+  if (cfg->precision != B200COORD_FP64)
+    return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "only the FP64 sweep is built in this version");
+  const unsigned long long ntot = (unsigned long long)cfg->n_group_a + cfg->n_group_b;
+  if (ntot == 0 || ntot > 0x7fffffffull) return fail(nullptr, B200COORD_ERR_INVALID, "atom count out of range");
+
+  b200coord_ctx* c = new b200coord_ctx();
+  c->cfg = *cfg;
+  if (c->cfg.nranks < 1) c->cfg.nranks = 1;
+  if (c->cfg.rank < 0 || c->cfg.rank >= c->cfg.nranks) {
+    delete c;
+    return fail(nullptr, B200COORD_ERR_INVALID, "rank out of range");
+  }
+  c->sw = *sw;
+  to_dev_switch(*sw, c->dsw);
+  c->n_a = cfg->n_group_a;
+  c->n_b = cfg->n_group_b;
+  c->n = (unsigned)ntot;
+  c->two_groups = (cfg->style == B200COORD_STYLE_TWOLIST) ? 1 : 0;
+  std::memset(&c->stats, 0, sizeof(c->stats));
+  c->abs_host.resize(c->n);
+  for (unsigned i = 0; i < c->n; ++i) c->abs_host[i] = abs_index ? abs_index[i] : i;
+  {  // do the two groups share atoms (TwoList) / does GROUPA repeat atoms (SingleList)?
+    if (c->two_groups) {
+      std::vector<unsigned> a(c->abs_host.begin(), c->abs_host.begin() + c->n_a);
+      std::vector<unsigned> b(c->abs_host.begin() + c->n_a, c->abs_host.end());
+      std::sort(a.begin(), a.end());
+      std::sort(b.begin(), b.end());
+      size_t i = 0, j = 0;
+      while (i < a.size() && j < b.size()) {
+        if (a[i] < b[j]) ++i;
+        else if (b[j] < a[i]) ++j;
+        else {
+          size_t i2 = i, j2 = j;
+          while (i2 < a.size() && a[i2] == a[i]) ++i2;
+          while (j2 < b.size() && b[j2] == b[j]) ++j2;
+          c->n_self_pairs += (unsigned long long)(i2 - i) * (j2 - j);
+          i = i2;
+          j = j2;
+        }
+      }
+    } else if (cfg->style == B200COORD_STYLE_SINGLELIST) {
+      std::vector<unsigned> a(c->abs_host);
+      std::sort(a.begin(), a.end());
+      for (size_t i = 0; i < a.size();) {
+        size_t i2 = i;
+        while (i2 < a.size() && a[i2] == a[i]) ++i2;
+        c->n_self_pairs += (unsigned long long)(i2 - i) * (i2 - i - 1) / 2;
+        i = i2;
+      }
+    }
+    c->check_abs = c->n_self_pairs ? 1 : 0;
+  }
+  c->row_chunk = (c->n + (unsigned)c->cfg.nranks - 1) / (unsigned)c->cfg.nranks;
+  c->row_begin = std::min(c->n, c->row_chunk * (unsigned)c->cfg.rank);
+  c->row_end = std::min(c->n, c->row_begin + c->row_chunk);
+
+#define CREATE_CU(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      std::string m__ = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+      b200coord_destroy(c);                                                                    \
+      return fail(nullptr, B200COORD_ERR_CUDA, m__);                                           \
+    }                                                                                          \
+  } while (0)
+
+  int ndev = 0;
+  CREATE_CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) {
+    b200coord_destroy(c);
+    return fail(nullptr, B200COORD_ERR_CUDA, "no CUDA device visible; libb200coord has no CPU path");
+  }
+  if (cfg->device >= 0) {
+    CREATE_CU(cudaSetDevice(cfg->device));
+    c->device = cfg->device;
+  } else {
+    CREATE_CU(cudaGetDevice(&c->device));
+  }
+  CREATE_CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CREATE_CU(cudaEventCreate(&c->ev[i]));
+  const size_t n = c->n;
+  const size_t padded_rows = (size_t)c->row_chunk * (size_t)c->cfg.nranks;
+  CREATE_CU(c->d_pos.reserve(3 * n));
+  CREATE_CU(c->d_out.reserve(3 * n + 10));
+  CREATE_CU(c->d_sderiv.reserve(3 * padded_rows));
+  CREATE_CU(c->d_small.reserve(32));
+  CREATE_CU(c->d_u64.reserve(16));
+  CREATE_CU(c->d_abs.reserve(n));
+  CREATE_CU(c->d_perm.reserve(n));
+  CREATE_CU(c->d_scell.reserve(n));
+  CREATE_CU(c->d_cell_of_slot.reserve(n));
+  CREATE_CU(c->d_tmp.reserve(n));
+  CREATE_CU(c->d_spos.reserve(n));
+  CREATE_CU(c->d_rowcount.reserve(1));
+  CREATE_CU(c->d_rowstart.reserve(1));
+  CREATE_CU(c->d_nbr.reserve(1));
+  CREATE_CU(cudaMemsetAsync(c->d_sderiv.p, 0, sizeof(double) * 3 * padded_rows, c->st));
+  CREATE_CU(cudaHostAlloc((void**)&c->h_small, 32 * sizeof(double), cudaHostAllocDefault));
+  CREATE_CU(cudaHostAlloc((void**)&c->h_u64, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+  c->h_u64[0] = c->h_u64[1] = 0;
+  CREATE_CU(cudaMemcpyAsync(c->d_abs.p, c->abs_host.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+  CREATE_CU(cudaStreamSynchronize(c->st));
+#undef CREATE_CU
+  std::memset(&c->hpbc, 0, sizeof(c->hpbc));
+  to_dev_pbc(c->hpbc, false, c->dpbc);
+  *out = c;
+  return B200COORD_OK;
+}
+
+void b200coord_destroy(b200coord_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+  c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
+  c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
+  c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release();
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_u64) cudaFreeHost(c->h_u64);
+  for (int i = 0; i < 8; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+int b200coord_set_box(b200coord_ctx* c, const double box[9]) {
+  if (!c || !box) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (c->box_set && std::memcmp(box, c->box_cached, sizeof(c->box_cached)) == 0) return B200COORD_OK;
+  std::memcpy(c->box_cached, box, sizeof(c->box_cached));
+  setup_pbc(box, c->hpbc);
+  to_dev_pbc(c->hpbc, c->cfg.pbc != 0, c->dpbc);
+  c->box_set = true;
+  return B200COORD_OK;
+}
+
+int b200coord_prepare(b200coord_ctx* c, long step, int exchange_step, int* will_rebuild) {
+  if (!c) return fail(c, B200COORD_ERR_INVALID, "null context");
+  int rc = B200COORD_OK;
+  const int stride = (c->cfg.nl_mode == B200COORD_NL_NONE) ? 0 : c->cfg.nl_stride;
+  if (stride > 0) {  // NeighborList::prepare, NeighborList.cpp:433-456
+    if (stride == 1) {
+      c->invalidate = true;
+      c->firsttime = false;
+    } else if (c->firsttime || (step % stride == 0)) {
+      c->invalidate = true;
+      c->firsttime = false;
+    } else {
+      c->invalidate = false;
+      if (exchange_step)
+        rc = fail(c, B200COORD_ERR_STATE,
+                  "Neighbor lists should be updated on exchange steps - choose a NL_STRIDE which divides the exchange stride!");
+    }
+    if (exchange_step) c->firsttime = true;
+  }
+  if (will_rebuild) *will_rebuild = (stride > 0 && c->invalidate) ? 1 : 0;
+  return rc;
+}
+
+int b200coord_update_list(b200coord_ctx* c, const double* pos) {
+  if (!c || !pos) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before update_list");
+  CU(c, cudaMemcpyAsync(c->d_pos.p, pos, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyHostToDevice, c->st));
+  int rc = rebuild(c, c->d_pos.p);
+  if (rc) return rc;
+  CU(c, cudaStreamSynchronize(c->st));
+  c->invalidate = false;
+  return B200COORD_OK;
+}
+
+int b200coord_calculate(b200coord_ctx* c, const double* pos, double* value, double* deriv, double* virial) {
+  if (!c || !pos || !value || !deriv || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  const size_t n3 = 3 * (size_t)c->n;
+  CU(c, cudaEventRecord(c->ev[0], c->st));
+  CU(c, cudaMemcpyAsync(c->d_pos.p, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaEventRecord(c->ev[1], c->st));
+  int rc = run_device(c, c->d_pos.p);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[6], c->st));
+  CU(c, cudaMemcpyAsync(deriv, c->d_out.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(c->h_small, c->d_out.p + n3, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaEventRecord(c->ev[7], c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->ev_valid[0] = c->ev_valid[3] = true;
+  for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
+  *value = c->h_small[9];
+  refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_calculate_device(b200coord_ctx* c, const double* d_pos, double* d_out) {
+  if (!c || !d_pos || !d_out) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  int rc = run_device(c, d_pos);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_get_stats(const b200coord_ctx* cc, b200coord_stats* out) {
+  if (!cc || !out) return B200COORD_ERR_INVALID;
+  b200coord_ctx* c = const_cast<b200coord_ctx*>(cc);
+  float ms;
+  if (c->ev_valid[0] && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->stats.last_h2d_ms = ms;
+  if (c->ev_valid[1] && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->stats.last_sweep_ms = ms;
+  if (c->ev_valid[2] && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->stats.last_build_ms = ms;
+  if (c->ev_valid[3] && cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->stats.last_d2h_ms = ms;
+  *out = c->stats;
+  return B200COORD_OK;
+}
+
+int b200coord_nl_pairs(b200coord_ctx* c, unsigned* pairs, unsigned long long capacity, unsigned long long* nout) {
+  if (!c || !nout) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->list_valid) return fail(c, B200COORD_ERR_STATE, "no neighbour list has been built yet");
+  if (c->cfg.nranks > 1) return fail(c, B200COORD_ERR_STATE, "nl_pairs is only available on a single-rank context");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->st));
+  std::vector<std::pair<unsigned, unsigned>> out;
+  const unsigned n = c->n, n_a = c->n_a;
+  if (c->cfg.style == B200COORD_STYLE_PAIR) {
+    std::vector<uint8_t> act;
+    if (c->cfg.nl_mode == B200COORD_NL_CLASSIC) {
+      act.resize(n_a);
+      CU(c, cudaMemcpy(act.data(), c->d_active.p, n_a, cudaMemcpyDeviceToHost));
+    }
+    for (unsigned k = 0; k < n_a; ++k)
+      if (act.empty() || act[k]) out.emplace_back(k, k + n_a);
+  } else {
+    std::vector<uint32_t> perm(n);
+    CU(c, cudaMemcpy(perm.data(), c->d_perm.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    auto emit = [&](unsigned si, unsigned sj) {  // slots -> reference (i0,i1)
+      if (c->two_groups) {
+        if (si < n_a) out.emplace_back(si, sj);
+      } else if (si < sj) {
+        out.emplace_back(si, sj);
+      }
+    };
+    if (c->cfg.nl_mode == B200COORD_NL_CLASSIC) {
+      std::vector<uint32_t> cnt(n), nbr((size_t)c->nbr_total);
+      std::vector<unsigned long long> st(n);
+      CU(c, cudaMemcpy(cnt.data(), c->d_rowcount.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(c, cudaMemcpy(st.data(), c->d_rowstart.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (c->nbr_total)
+        CU(c, cudaMemcpy(nbr.data(), c->d_nbr.p, (size_t)c->nbr_total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (unsigned k = 0; k < n; ++k)
+        for (uint32_t e = 0; e < cnt[k]; ++e) emit(perm[k], perm[nbr[st[k] + e]]);
+      // pairs of one and the same atom are at distance 0 <= cutoff: the reference lists them
+      if (c->n_self_pairs) {
+        for (unsigned i = 0; i < (c->two_groups ? n_a : n); ++i)
+          for (unsigned j = (c->two_groups ? n_a : i + 1); j < n; ++j)
+            if (c->abs_host[i] == c->abs_host[j]) out.emplace_back(i, j);
+      }
+    } else {
+      const size_t m = (size_t)(c->two_groups ? 2 : 1) * c->grid.ncell;
+      std::vector<uint32_t> cs(m), cn(m), sc(n);
+      CU(c, cudaMemcpy(cs.data(), c->d_cstart.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(c, cudaMemcpy(cn.data(), c->d_ccount.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(c, cudaMemcpy(sc.data(), c->d_scell.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      const DevGrid& g = c->grid;
+      for (unsigned k = 0; k < n; ++k) {
+        const unsigned grp = k < n_a ? 0 : 1, other = c->two_groups ? 1 - grp : 0;
+        if (c->two_groups && grp == 1) continue;
+        int cc[3], lo[3], hi[3];
+        const int cell = (int)sc[k];
+        cc[2] = cell / (g.n[0] * g.n[1]);
+        const int rem = cell - cc[2] * g.n[0] * g.n[1];
+        cc[1] = rem / g.n[0];
+        cc[0] = rem - cc[1] * g.n[0];
+        for (int a = 0; a < 3; ++a) {
+          const int nn = g.n[a];
+          int mn = cc[a] + ((nn < 2) ? 0 : -1), mx = cc[a] + ((nn < 3 && g.stencil_pbc) ? 1 : 2);
+          if (!g.stencil_pbc) {
+            mn = std::max(mn, 0);
+            mx = std::min(mx, nn);
+          }
+          lo[a] = mn;
+          hi[a] = mx;
+        }
+        auto wrap = [](int v, int nn) { return v < 0 ? nn - 1 : v % nn; };
+        for (int x = lo[0]; x < hi[0]; ++x)
+          for (int y = lo[1]; y < hi[1]; ++y)
+            for (int z = lo[2]; z < hi[2]; ++z) {
+              const size_t ci = (size_t)other * g.ncell + wrap(x, g.n[0]) + wrap(y, g.n[1]) * g.n[0] +
+                                (size_t)wrap(z, g.n[2]) * g.n[0] * g.n[1];
+              for (uint32_t e = 0; e < cn[ci]; ++e) {
+                const unsigned j = cs[ci] + e;
+                if (j != k) emit(perm[k], perm[j]);
+              }
+            }
+      }
+    }
+  }
+  std::sort(out.begin(), out.end());
+  *nout = out.size();
+  if (pairs) {
+    const unsigned long long m = std::min<unsigned long long>(capacity, out.size());
+    for (unsigned long long i = 0; i < m; ++i) {
+      pairs[2 * i] = out[i].first;
+      pairs[2 * i + 1] = out[i].second;
+    }
+  }
+  return B200COORD_OK;
+}
+
+int b200coord_comm_unique_id(char id[B200COORD_UNIQUE_ID_BYTES]) {
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(nullptr, B200COORD_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == B200COORD_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  ncclResult_t r = api.GetUniqueId(&u);
+  if (r != ncclSuccess) return fail(nullptr, B200COORD_ERR_NCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+  std::memcpy(id, &u, sizeof(u));
+  return B200COORD_OK;
+}
+
+int b200coord_comm_init(b200coord_ctx* c, const char id[B200COORD_UNIQUE_ID_BYTES]) {
+  if (!c || !id) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(c, B200COORD_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  if (c->cfg.nranks <= 1) return B200COORD_OK;
+  CU(c, cudaSetDevice(c->device));
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclResult_t r = api.CommInitRank(&c->comm, c->cfg.nranks, u, c->cfg.rank);
+  if (r != ncclSuccess) {
+    c->comm = nullptr;
+    return fail(c, B200COORD_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+  }
+  return B200COORD_OK;
+}
+
+int b200coord_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return B200COORD_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, B200COORD_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return B200COORD_OK;
+}
+int b200coord_host_free(void* ptr) {
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) return B200COORD_ERR_CUDA;
+  return B200COORD_OK;
+}
+int b200coord_device_alloc(size_t bytes, void** dptr) {
+  if (!dptr) return B200COORD_ERR_INVALID;
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(nullptr, B200COORD_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  return B200COORD_OK;
+}
+int b200coord_device_free(void* dptr) {
+  if (dptr && cudaFree(dptr) != cudaSuccess) return B200COORD_ERR_CUDA;
+  return B200COORD_OK;
+}
+int b200coord_memcpy_h2d(void* dptr, const void* hptr, size_t bytes) {
+  cudaError_t e = cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice);
+  return e == cudaSuccess ? B200COORD_OK : fail(nullptr, B200COORD_ERR_CUDA, cudaGetErrorString(e));
+}
+int b200coord_memcpy_d2h(void* hptr, const void* dptr, size_t bytes) {
+  cudaError_t e = cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? B200COORD_OK : fail(nullptr, B200COORD_ERR_CUDA, cudaGetErrorString(e));
+}
+int b200coord_device_synchronize(void) {
+  cudaError_t e = cudaDeviceSynchronize();
+  return e == cudaSuccess ? B200COORD_OK : fail(nullptr, B200COORD_ERR_CUDA, cudaGetErrorString(e));
+}
+
+}  // extern "C"

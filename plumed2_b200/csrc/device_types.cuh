@@ -1,0 +1,201 @@
+// Device-side parameter blocks and small math helpers shared by the build and sweep kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// ---- periodic box, passed by value to kernels (lives in the constant bank as a kernel parameter)
+struct DevPbc {
+  int type;          // 0 none (plain delta), 1 orthorhombic, 2 generic  (Pbc.h:52)
+  double box[9];     // ortho path uses box[4k] and inv_box[4k]   (Pbc.cpp:377-379)
+  double inv_box[9];
+  double reduced[9]; // generic path (Pbc.cpp:381-411)
+  double inv_reduced[9];
+  int nshift[8];
+  double shifts[8][6][3];
+};
+
+// ---- cell grid used for binning (either the reference's LinkCells grid or our own margin grid)
+struct DevGrid {
+  int bbox;            // 1: no box -> bounding box around the atoms, origin subtracted (LinkCells.cpp:49-73, :279-281)
+  int stencil_pbc;     // 1: neighbour stencil wraps, 0: clamps (the usePbc argument of addRequiredCells, :195-239)
+  int n[3];            // cells per direction
+  int ncell;           // n0*n1*n2
+  double inv_box_t[9]; // transpose(invBox): fpos = inv_box_t * pos   (Pbc::realToScaled, Pbc.cpp:472-474)
+  double origin[3];
+};
+
+// ---- switching function (mirrors b200coord_switch / switchContainers::Data)
+struct DevSwitch {
+  int type;
+  double d0, dmax, dmax_2, invr0, invr0_2, stretch, shift;
+  int nn, mm;
+  double preRes, preDfunc, preSecDev;
+  int nnf, mmf;
+  double preDfuncF, preSecDevF;
+  int a, b;
+  double c, d;
+  double beta, lambda, ref;
+};
+
+// sorted atom record: position + slot bookkeeping in one 32-byte sector
+struct __align__(32) SPos {
+  double x, y, z;
+  uint32_t abs_index;  // absolute atom index (self-pair skip, CoordinationBase.cpp:183)
+  uint32_t slot;       // index in the caller's position array
+};
+
+// ------------------------------------------------------------------ exact (never contracted) arithmetic
+// Used wherever the result feeds a comparison that must reproduce the reference's x86-64 non-FMA build
+// bit for bit: cell assignment and the r^2 <= cutoff^2 neighbour test.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+
+// Tools::pbc (Tools.h:557-564): x+=100; x - int(x +/- 0.5)  with C truncation
+__device__ __forceinline__ double tools_pbc_exact(double x) {
+  x = xadd(x, 100.0);
+  const double h = (x >= 0.0) ? xadd(x, 0.5) : xsub(x, 0.5);
+  return xsub(x, (double)__double2int_rz(h));
+}
+
+// modulo2 (LoopUnroller.h:146-152): (x*x + y*y) + z*z
+__device__ __forceinline__ double norm2_exact(double x, double y, double z) {
+  return xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));
+}
+
+// row-vector x matrix with accumulation from 0 in j order (Tensor.h:451-458)
+__device__ __forceinline__ void vecmat_exact(const double a[3], const double* __restrict__ m, double out[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t = xadd(0.0, xmul(a[0], m[i]));  // the reference accumulates from 0 (matters for -0.0)
+    t = xadd(t, xmul(a[1], m[3 + i]));
+    t = xadd(t, xmul(a[2], m[6 + i]));
+    out[i] = t;
+  }
+}
+
+// Pbc::distance (Pbc.cpp:362-415) reproduced operation by operation; d = p1 - p0 on entry
+__device__ __forceinline__ void min_image_exact(const DevPbc& pbc, double d[3]) {
+  if (pbc.type == 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = xmul(tools_pbc_exact(xmul(d[k], pbc.inv_box[4 * k])), pbc.box[4 * k]);
+  } else if (pbc.type == 2) {
+    double s[3];
+    vecmat_exact(d, pbc.inv_reduced, s);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] = tools_pbc_exact(s[k]);
+    vecmat_exact(s, pbc.reduced, d);
+    if (xadd(xadd(fabs(s[0]), fabs(s[1])), fabs(s[2])) > 0.5) {
+      const int o = 4 * (s[0] > 0 ? 1 : 0) + 2 * (s[1] > 0 ? 1 : 0) + (s[2] > 0 ? 1 : 0);
+      double best[3] = {d[0], d[1], d[2]};
+      double lbest = norm2_exact(d[0], d[1], d[2]);
+      const int ns = pbc.nshift[o];
+      for (int i = 0; i < ns; ++i) {
+        const double t0 = xadd(d[0], pbc.shifts[o][i][0]);
+        const double t1 = xadd(d[1], pbc.shifts[o][i][1]);
+        const double t2 = xadd(d[2], pbc.shifts[o][i][2]);
+        const double lt = norm2_exact(t0, t1, t2);
+        if (lt < lbest) {
+          lbest = lt;
+          best[0] = t0;
+          best[1] = t1;
+          best[2] = t2;
+        }
+      }
+      d[0] = best[0];
+      d[1] = best[1];
+      d[2] = best[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fast arithmetic for the sweep
+// round to nearest integer with two FP64 adds (valid for |x| < 2^51)
+__device__ __forceinline__ double fast_rint(double x) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  return __dsub_rn(__dadd_rn(x, magic), magic);
+}
+
+// 1/a: hardware seed (MUFU.RCP64H) + two Newton steps -> ~1 ulp, no slow path, no division by zero care
+__device__ __forceinline__ double fast_rcp(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// 1/sqrt(a) for a>0: MUFU.RSQ64H seed + two Newton steps
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  double x;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  const double ha = 0.5 * a;
+  double e = fma(-ha * x, x, 0.5);
+  x = fma(x, e, x);
+  e = fma(-ha * x, x, 0.5);
+  x = fma(x, e, x);
+  return x;
+}
+
+__device__ __forceinline__ double ipow_dev(double base, int e) {  // Tools::fastpow (Tools.h:581-595)
+  if (e < 0) {
+    e = -e;
+    base = fast_rcp(base);
+  }
+  double r = 1.0;
+  while (e) {
+    if (e & 1) r *= base;
+    e >>= 1;
+    base *= base;
+  }
+  return r;
+}
+
+// minimum image for the sweep (1e-10 parity, not bit parity): same algorithm, fused arithmetic
+template <int PBC>
+__device__ __forceinline__ void min_image_fast(const DevPbc& pbc, double& dx, double& dy, double& dz) {
+  if (PBC == 1) {
+    dx = fma(-fast_rint(dx * pbc.inv_box[0]), pbc.box[0], dx);
+    dy = fma(-fast_rint(dy * pbc.inv_box[4]), pbc.box[4], dy);
+    dz = fma(-fast_rint(dz * pbc.inv_box[8]), pbc.box[8], dz);
+  } else if (PBC == 2) {
+    const double* ir = pbc.inv_reduced;
+    const double* rd = pbc.reduced;
+    double s0 = fma(dz, ir[6], fma(dy, ir[3], dx * ir[0]));
+    double s1 = fma(dz, ir[7], fma(dy, ir[4], dx * ir[1]));
+    double s2 = fma(dz, ir[8], fma(dy, ir[5], dx * ir[2]));
+    s0 -= fast_rint(s0);
+    s1 -= fast_rint(s1);
+    s2 -= fast_rint(s2);
+    dx = fma(s2, rd[6], fma(s1, rd[3], s0 * rd[0]));
+    dy = fma(s2, rd[7], fma(s1, rd[4], s0 * rd[1]));
+    dz = fma(s2, rd[8], fma(s1, rd[5], s0 * rd[2]));
+    if (fabs(s0) + fabs(s1) + fabs(s2) > 0.5) {
+      const int o = 4 * (s0 > 0 ? 1 : 0) + 2 * (s1 > 0 ? 1 : 0) + (s2 > 0 ? 1 : 0);
+      double bx = dx, by = dy, bz = dz;
+      double lbest = fma(dz, dz, fma(dy, dy, dx * dx));
+      const int ns = pbc.nshift[o];
+      for (int i = 0; i < ns; ++i) {
+        const double tx = dx + pbc.shifts[o][i][0];
+        const double ty = dy + pbc.shifts[o][i][1];
+        const double tz = dz + pbc.shifts[o][i][2];
+        const double lt = fma(tz, tz, fma(ty, ty, tx * tx));
+        if (lt < lbest) {
+          lbest = lt;
+          bx = tx;
+          by = ty;
+          bz = tz;
+        }
+      }
+      dx = bx;
+      dy = by;
+      dz = bz;
+    }
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,400 @@
+// Neighbour-list rebuild on the device: cell binning, deterministic counting sort, and the
+// stream-compacted classic (distance-filtered) pair list.
+//
+//   reference                                            here
+//   LinkCells::findMyCell/findCell  LinkCells.cpp:277-315   k_bin_atoms        (bit-exact cell of every atom)
+//   LinkCells::resetCollection      LinkCells.cpp:138-181   k_bin_atoms + k_scan_cells + k_place_atoms + k_order_cells
+//   LinkCells::addRequiredCells     LinkCells.cpp:183-239   stencil_bounds / wrap_cell (device_types + here)
+//   NeighborList::update (classic)  NeighborList.cpp:237-308 k_nl_rows<false> (count) + scan + k_nl_rows<true> (fill)
+//
+// All of this is HBM-bound integer/byte work except the distance test in k_nl_rows, which repeats the
+// reference's arithmetic exactly (no FMA contraction) so that the pair SET is identical bit for bit.
+#include "kernels.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// bounding box of the positions (only when there is no periodic box): min/max per axis
+__global__ void k_bbox(const double* __restrict__ pos, unsigned n, double* __restrict__ out /*[6]: min xyz, max xyz*/,
+                       unsigned long long* __restrict__ scratch /*[6] ordered-int encodings*/) {
+  // encode doubles so that unsigned comparison == floating comparison
+  auto enc = [](double v) -> unsigned long long {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  };
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = pos[3 * (size_t)i + k];
+      mn[k] = fmin(mn[k], v);
+      mx[k] = fmax(mx[k], v);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(&scratch[k], enc(mn[k]));
+      atomicMax(&scratch[3 + k], enc(mx[k]));
+    }
+  }
+  (void)out;
+}
+
+__global__ void k_bbox_decode(const unsigned long long* __restrict__ scratch, double* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k < 6) {
+    unsigned long long e = scratch[k];
+    unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
+    out[k] = __longlong_as_double((long long)b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LinkCells::findCell : f = invBox^T * (pos - origin); c_k = floor((Tools::pbc(f_k)+0.5)*n_k)
+__device__ __forceinline__ int cell_of(const DevGrid& g, double px, double py, double pz) {
+  double p[3] = {px, py, pz};
+  if (g.bbox) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = xsub(p[k], g.origin[k]);
+  }
+  int c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f = xadd(0.0, xmul(g.inv_box_t[3 * i], p[0]));  // Tensor.h:440-447, accumulation from 0
+    f = xadd(f, xmul(g.inv_box_t[3 * i + 1], p[1]));
+    f = xadd(f, xmul(g.inv_box_t[3 * i + 2], p[2]));
+    const double w = xmul(xadd(tools_pbc_exact(f), 0.5), (double)g.n[i]);
+    int ci = (int)floor(w);
+    ci = max(0, min(g.n[i] - 1, ci));  // the reference asserts this range (LinkCells.cpp:286-290)
+    c[i] = ci;
+  }
+  return c[0] + c[1] * g.n[0] + c[2] * g.n[0] * g.n[1];
+}
+
+// one thread per atom slot: cell id + histogram per (group, cell)
+__global__ void k_bin_atoms(const double* __restrict__ pos, unsigned n, unsigned n_a, DevGrid g,
+                            uint32_t* __restrict__ cell_of_slot, uint32_t* __restrict__ cell_count /*[ngroups*ncell]*/) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cell_of(g, pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2]);
+  cell_of_slot[i] = (uint32_t)c;
+  const unsigned grp = (i < n_a) ? 0u : 1u;
+  atomicAdd(&cell_count[grp * (unsigned)g.ncell + (unsigned)c], 1u);
+}
+
+// single-block exclusive scan over `m` counters (m = ngroups*ncell; group 1 simply continues after group 0,
+// which is exactly the [A sorted | B sorted] layout).  Also zeroes the placement cursors.
+__global__ void k_scan_cells(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                             unsigned m) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (unsigned base = 0; base < m; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const uint32_t v = (i < m) ? cnt[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t t = (lane < nw) ? warp_tot[lane] : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= (unsigned)o) t += y;
+      }
+      warp_tot[lane] = t;  // inclusive totals of warps
+    }
+    __syncthreads();
+    const uint32_t before = carry + (wid ? warp_tot[wid - 1] : 0u) + (x - v);
+    if (i < m) {
+      start[i] = before;
+      cursor[i] = 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = before + v;
+    __syncthreads();
+  }
+}
+
+// scatter slots into their cell segment (order inside a segment is arbitrary here, fixed by k_order_cells)
+__global__ void k_place_atoms(unsigned n, unsigned n_a, int ncell, const uint32_t* __restrict__ cell_of_slot,
+                              const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                              uint32_t* __restrict__ tmp) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned grp = (i < n_a) ? 0u : 1u;
+  const unsigned cc = grp * (unsigned)ncell + cell_of_slot[i];
+  const uint32_t k = start[cc] + atomicAdd(&cursor[cc], 1u);
+  tmp[k] = i;
+}
+
+// one warp per (group,cell) segment: order its slots ascending (what the reference's serial counting sort
+// produces, LinkCells.cpp:175-180) by rank counting.  O(m^2/32) per segment, m = atoms in the cell -- the
+// pair work on the same cell is O(27 m^2), so this never dominates.
+__global__ void k_order_cells(unsigned nseg, int ncell, const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                              const uint32_t* __restrict__ tmp, uint32_t* __restrict__ perm, uint32_t* __restrict__ scell) {
+  const unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (seg >= nseg) return;
+  const uint32_t s = start[seg], m = cnt[seg];
+  const uint32_t cell = seg % (unsigned)ncell;
+  for (uint32_t e = lane; e < m; e += 32) {
+    const uint32_t mine = tmp[s + e];
+    uint32_t rank = 0;
+    for (uint32_t q = 0; q < m; ++q) rank += (tmp[s + q] < mine) ? 1u : 0u;
+    perm[s + rank] = mine;
+    scell[s + rank] = cell;
+  }
+}
+
+// per step: sorted, 32-byte records from the caller's AoS positions
+__global__ void k_gather_sorted(const double* __restrict__ pos, const uint32_t* __restrict__ perm,
+                                const uint32_t* __restrict__ abs_index, unsigned n, SPos* __restrict__ spos) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t slot = perm[k];
+  SPos r;
+  r.x = pos[3 * (size_t)slot];
+  r.y = pos[3 * (size_t)slot + 1];
+  r.z = pos[3 * (size_t)slot + 2];
+  r.abs_index = abs_index[slot];
+  r.slot = slot;
+  spos[k] = r;
+}
+
+__global__ void k_identity_perm(unsigned n, uint32_t* __restrict__ perm, uint32_t* __restrict__ scell) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    perm[k] = k;
+    scell[k] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classic list rows.  One warp per row (sorted atom k in [row_begin,row_end)); candidates = atoms of the
+// partner group in the stencil cells; a candidate is kept iff modulo2(Pbc::distance) <= cutoff^2 evaluated
+// exactly as NeighborList.cpp:246-259 does.  FILL=false counts, FILL=true writes the sorted indices j in
+// stencil order (deterministic).  Self-pairs (same absolute index) are not stored: the sweep would skip
+// them anyway (CoordinationBase.cpp:183); they are accounted for in the reported list size on the host.
+template <bool FILL>
+__global__ void k_nl_rows(const SPos* __restrict__ spos, const uint32_t* __restrict__ scell,
+                          const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
+                          double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
+                          uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
+                          uint32_t* __restrict__ nbr) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned k = row_begin + warp;
+  if (k >= row_end) return;
+  const SPos pi = spos[k];
+  const unsigned my_grp = (k < n_a) ? 0u : 1u;
+  const unsigned other = two_groups ? (1u - my_grp) : 0u;
+  int c[3];
+  {
+    const int cell = (int)scell[k];
+    c[2] = cell / (g.n[0] * g.n[1]);
+    const int rem = cell - c[2] * g.n[0] * g.n[1];
+    c[1] = rem / g.n[0];
+    c[0] = rem - c[1] * g.n[0];
+  }
+  int lo[3], hi[3];
+  stencil_bounds(g, c, lo, hi);
+  unsigned total = 0;
+  unsigned long long base = FILL ? row_start[k - row_begin] : 0ull;
+  for (int nx = lo[0]; nx < hi[0]; ++nx) {
+    const int xv = wrap_cell(nx, g.n[0]);
+    for (int ny = lo[1]; ny < hi[1]; ++ny) {
+      const int yv = wrap_cell(ny, g.n[1]) * g.n[0];
+      for (int nz = lo[2]; nz < hi[2]; ++nz) {
+        const int zv = wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1];
+        const unsigned cc = other * (unsigned)g.ncell + (unsigned)(xv + yv + zv);
+        const uint32_t s = cstart[cc], m = ccount[cc];
+        for (uint32_t e0 = 0; e0 < m; e0 += 32) {
+          const uint32_t e = e0 + lane;
+          bool keep = false;
+          uint32_t j = 0;
+          if (e < m) {
+            j = s + e;
+            const SPos pj = spos[j];
+            if (j != k && pj.abs_index != pi.abs_index) {
+              // the reference always evaluates the pair as (index0,index1) = (lower slot, higher slot)
+              // resp. (A atom, B atom): distance = pos[index1]-pos[index0]   (NeighborList.cpp:247-254)
+              const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
+              double d[3];
+              if (i_first) {
+                d[0] = xsub(pj.x, pi.x);
+                d[1] = xsub(pj.y, pi.y);
+                d[2] = xsub(pj.z, pi.z);
+              } else {
+                d[0] = xsub(pi.x, pj.x);
+                d[1] = xsub(pi.y, pj.y);
+                d[2] = xsub(pi.z, pj.z);
+              }
+              min_image_exact(pbc, d);
+              keep = norm2_exact(d[0], d[1], d[2]) <= cutoff2;
+            }
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, keep);
+          if (FILL && keep) nbr[base + total + __popc(mask & ((1u << lane) - 1u))] = j;
+          total += __popc(mask);
+        }
+      }
+    }
+  }
+  if (!FILL && lane == 0) row_count[k - row_begin] = total;
+}
+
+template __global__ void k_nl_rows<false>(const SPos*, const uint32_t*, const uint32_t*, const uint32_t*, DevGrid, DevPbc,
+                                          double, unsigned, int, unsigned, unsigned, uint32_t*, const unsigned long long*,
+                                          uint32_t*);
+template __global__ void k_nl_rows<true>(const SPos*, const uint32_t*, const uint32_t*, const uint32_t*, DevGrid, DevPbc,
+                                         double, unsigned, int, unsigned, unsigned, uint32_t*, const unsigned long long*,
+                                         uint32_t*);
+
+// PAIR style with NLIST: pair k=(k, k+nA) is kept iff within the cutoff at build time (NeighborList.cpp:246-259)
+__global__ void k_pair_mask(const double* __restrict__ pos, unsigned n_a, DevPbc pbc, double cutoff2,
+                            uint8_t* __restrict__ active) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_a) return;
+  const size_t a = 3 * (size_t)k, b = 3 * (size_t)(k + n_a);
+  double d[3] = {xsub(pos[b], pos[a]), xsub(pos[b + 1], pos[a + 1]), xsub(pos[b + 2], pos[a + 2])};
+  min_image_exact(pbc, d);
+  active[k] = norm2_exact(d[0], d[1], d[2]) <= cutoff2 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan uint32 -> uint64 over n elements, three kernels (block sums, scan of sums, apply)
+constexpr int kScanBlock = 1024;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total_out) {
+  __shared__ unsigned long long wsum[32];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (unsigned)o) x += y;
+  }
+  if (lane == 31) wsum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long t = (lane < nw) ? wsum[lane] : 0ull;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= (unsigned)o) t += y;
+    }
+    wsum[lane] = t;
+  }
+  __syncthreads();
+  const unsigned long long excl = (wid ? wsum[wid - 1] : 0ull) + (x - v);
+  if (total_out) *total_out = wsum[nw - 1];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void k_scan_block_sums(const uint32_t* __restrict__ in, unsigned n, unsigned long long* __restrict__ bsum) {
+  const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
+  unsigned long long tot;
+  block_exclusive_scan(i < n ? in[i] : 0u, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_sums(unsigned long long* __restrict__ bsum, unsigned nb, unsigned long long* __restrict__ grand_total) {
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (unsigned base = 0; base < nb; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const unsigned long long v = (i < nb) ? bsum[i] : 0ull;
+    unsigned long long tot;
+    const unsigned long long ex = block_exclusive_scan(v, &tot);
+    if (i < nb) bsum[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void k_scan_apply(const uint32_t* __restrict__ in, unsigned n, const unsigned long long* __restrict__ bsum,
+                             unsigned long long* __restrict__ out) {
+  const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
+  const unsigned long long ex = block_exclusive_scan(i < n ? in[i] : 0u, nullptr);
+  if (i < n) out[i] = bsum[blockIdx.x] + ex;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch wrappers
+void launch_bbox(const double* pos, unsigned n, double* out6, unsigned long long* scratch6, cudaStream_t st) {
+  static const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+  cudaMemcpyAsync(scratch6, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  const int blocks = (int)min((n + 255u) / 256u, 148u * 8u);
+  k_bbox<<<blocks ? blocks : 1, 256, 0, st>>>(pos, n, out6, scratch6);
+  k_bbox_decode<<<1, 32, 0, st>>>(scratch6, out6);
+}
+
+void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const DevGrid& g, uint32_t* cell_of_slot,
+                 uint32_t* ccount, uint32_t* cstart, uint32_t* cursor, uint32_t* tmp, uint32_t* perm, uint32_t* scell,
+                 cudaStream_t st) {
+  const unsigned m = (unsigned)ngroups * (unsigned)g.ncell;
+  cudaMemsetAsync(ccount, 0, sizeof(uint32_t) * m, st);
+  k_bin_atoms<<<(n + 255) / 256, 256, 0, st>>>(pos, n, n_a, g, cell_of_slot, ccount);
+  k_scan_cells<<<1, 1024, 0, st>>>(ccount, cstart, cursor, m);
+  k_place_atoms<<<(n + 255) / 256, 256, 0, st>>>(n, n_a, g.ncell, cell_of_slot, cstart, cursor, tmp);
+  const unsigned long long threads = (unsigned long long)m * 32ull;
+  k_order_cells<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(m, g.ncell, cstart, ccount, tmp, perm, scell);
+}
+
+void launch_identity(unsigned n, uint32_t* perm, uint32_t* scell, cudaStream_t st) {
+  k_identity_perm<<<(n + 255) / 256, 256, 0, st>>>(n, perm, scell);
+}
+
+void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, SPos* spos,
+                   cudaStream_t st) {
+  k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, spos);
+}
+
+void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
+                    const DevGrid& g, const DevPbc& pbc, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
+                    unsigned row_end, uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr,
+                    cudaStream_t st) {
+  const unsigned rows = row_end - row_begin;
+  if (!rows) return;
+  const unsigned blocks = (rows * 32u + 255u) / 256u;
+  if (fill)
+    k_nl_rows<true><<<blocks, 256, 0, st>>>(spos, scell, cstart, ccount, g, pbc, cutoff2, n_a, two_groups, row_begin,
+                                            row_end, row_count, row_start, nbr);
+  else
+    k_nl_rows<false><<<blocks, 256, 0, st>>>(spos, scell, cstart, ccount, g, pbc, cutoff2, n_a, two_groups, row_begin,
+                                             row_end, row_count, row_start, nbr);
+}
+
+void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st) {
+  if (n_a) k_pair_mask<<<(n_a + 255) / 256, 256, 0, st>>>(pos, n_a, pbc, cutoff2, active);
+}
+
+void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long long* bsum, unsigned long long* row_start,
+                      unsigned long long* grand_total, cudaStream_t st) {
+  if (!rows) {
+    cudaMemsetAsync(grand_total, 0, sizeof(unsigned long long), st);
+    return;
+  }
+  const unsigned nb = (rows + kScanBlock - 1) / kScanBlock;
+  k_scan_block_sums<<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum);
+  k_scan_sums<<<1, kScanBlock, 0, st>>>(bsum, nb, grand_total);
+  k_scan_apply<<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum, row_start);
+}
+
+}  // namespace b200
