@@ -21,7 +21,19 @@ static std::string env_or(const char* key, const std::string& fallback) {
 
 std::string getSoExt() { return "so"; }
 bool isInstalled() { return false; }
-std::string getPlumedRoot() { return env_or("PLUMED_ROOT", B200_REF_ROOT); }
+// The CLI lists <root>/scripts and <root>/patches at start-up (core/CLToolMain.cpp:205-223).  The mini build
+// ships no scripts; oracle/Makefile creates an empty <_ref>/root/{scripts,patches} next to lib/ so that the
+// executable also starts on machines where the reference tree is not mounted (the GPU box).
+std::string getPlumedRoot() {
+  const char* v = std::getenv("PLUMED_ROOT");
+  if (v) return std::string(v);
+  std::string lib = getLibraryPath();              // .../_ref/lib/libplumedKernel.so
+  const size_t a = lib.rfind('/');
+  if (a == std::string::npos) return B200_REF_ROOT;
+  const size_t b = lib.rfind('/', a - 1);
+  if (b == std::string::npos) return B200_REF_ROOT;
+  return lib.substr(0, b) + "/root";
+}
 std::string getPlumedHtmldir() { return getPlumedRoot(); }
 std::string getPlumedIncludedir() { return getPlumedRoot() + "/src/include"; }
 std::string getPlumedProgramName() { return "plumed"; }

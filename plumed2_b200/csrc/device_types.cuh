@@ -112,10 +112,12 @@ __device__ __forceinline__ void min_image_exact(const DevPbc& pbc, double d[3]) 
 }
 
 // ------------------------------------------------------------------ fast arithmetic for the sweep
-// round to nearest integer with two FP64 adds (valid for |x| < 2^51)
-__device__ __forceinline__ double fast_rint(double x) {
+// floor(x) with two FP64 adds: the first add rounds toward -inf onto the integer grid of the magic constant
+// (valid for |x| < 2^51).  Callers pass x = t + 0.5 (folded into an FMA) to get the round-half-up of
+// Tools::pbc (Tools.h:557-564: x - int(x+0.5) after the +100 shift), including its behaviour at exact ties.
+__device__ __forceinline__ double fast_floor(double x) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52
-  return __dsub_rn(__dadd_rn(x, magic), magic);
+  return __dsub_rn(__dadd_rd(x, magic), magic);
 }
 
 // 1/a: hardware seed (MUFU.RCP64H) + two Newton steps -> ~1 ulp, no slow path, no division by zero care
@@ -159,18 +161,18 @@ __device__ __forceinline__ double ipow_dev(double base, int e) {  // Tools::fast
 template <int PBC>
 __device__ __forceinline__ void min_image_fast(const DevPbc& pbc, double& dx, double& dy, double& dz) {
   if (PBC == 1) {
-    dx = fma(-fast_rint(dx * pbc.inv_box[0]), pbc.box[0], dx);
-    dy = fma(-fast_rint(dy * pbc.inv_box[4]), pbc.box[4], dy);
-    dz = fma(-fast_rint(dz * pbc.inv_box[8]), pbc.box[8], dz);
+    dx = fma(-fast_floor(fma(dx, pbc.inv_box[0], 0.5)), pbc.box[0], dx);
+    dy = fma(-fast_floor(fma(dy, pbc.inv_box[4], 0.5)), pbc.box[4], dy);
+    dz = fma(-fast_floor(fma(dz, pbc.inv_box[8], 0.5)), pbc.box[8], dz);
   } else if (PBC == 2) {
     const double* ir = pbc.inv_reduced;
     const double* rd = pbc.reduced;
     double s0 = fma(dz, ir[6], fma(dy, ir[3], dx * ir[0]));
     double s1 = fma(dz, ir[7], fma(dy, ir[4], dx * ir[1]));
     double s2 = fma(dz, ir[8], fma(dy, ir[5], dx * ir[2]));
-    s0 -= fast_rint(s0);
-    s1 -= fast_rint(s1);
-    s2 -= fast_rint(s2);
+    s0 -= fast_floor(s0 + 0.5);
+    s1 -= fast_floor(s1 + 0.5);
+    s2 -= fast_floor(s2 + 0.5);
     dx = fma(s2, rd[6], fma(s1, rd[3], s0 * rd[0]));
     dy = fma(s2, rd[7], fma(s1, rd[4], s0 * rd[1]));
     dz = fma(s2, rd[8], fma(s1, rd[5], s0 * rd[2]));

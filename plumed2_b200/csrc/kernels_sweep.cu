@@ -173,20 +173,31 @@ struct LaneAcc {
   double val, vxx, vxy, vxz, vyy, vyz, vzz;
 };
 
-// one pair seen from atom i: d = min_image(r_j - r_i); f_i -= df*d; (ACC) value += s, virial -= df d(x)d
+// one pair seen from atom i.  The reference evaluates every pair once, as distance = pos[i1]-pos[i0] with
+// (i0,i1) = (GROUPA atom, GROUPB atom) resp. (lower, higher index) (NeighborList.cpp:147-166), and gives
+// -dd to i0 and +dd to i1.  When two periodic images are equally close (perfect crystals: regtest rt42) the
+// minimum image of -x is not minus the minimum image of x, so both ends of a pair must use the SAME vector:
+// `flip` says atom i is the i1 end; the difference is then taken as r_i - r_j, the image is chosen on that
+// canonical vector, and the sign goes into the derivative instead.
 template <int K, int PBC, bool ACC>
 __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw, double xi, double yi, double zi,
-                                          const SPos& pj, double& fx, double& fy, double& fz, LaneAcc& acc) {
+                                          const SPos& pj, bool flip, double& fx, double& fy, double& fz, LaneAcc& acc) {
   double dx = pj.x - xi, dy = pj.y - yi, dz = pj.z - zi;
+  if (flip) {
+    dx = -dx;
+    dy = -dy;
+    dz = -dz;
+  }
   min_image_fast<PBC>(pbc, dx, dy, dz);
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
   double s, df;
   eval_switch<K>(sw, r2, s, df);
-  const double gx = df * dx, gy = df * dy, gz = df * dz;
-  fx -= gx;
-  fy -= gy;
-  fz -= gz;
+  const double dfs = flip ? -df : df;  // deriv[i0] -= df*d ; deriv[i1] += df*d
+  fx = fma(-dfs, dx, fx);
+  fy = fma(-dfs, dy, fy);
+  fz = fma(-dfs, dz, fz);
   if (ACC) {
+    const double gx = df * dx, gy = df * dy, gz = df * dz;
     acc.val += s;
     acc.vxx = fma(gx, dx, acc.vxx);
     acc.vxy = fma(gx, dy, acc.vxy);
@@ -253,13 +264,15 @@ __global__ void __launch_bounds__(kSweepThreads)
     const SPos pi = a.spos[k];
     const unsigned long long base = a.row_start[k - a.row_begin];
     const unsigned cnt = a.row_count[k - a.row_begin];
+    const bool row_is_b = (k >= a.n_a);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const uint32_t* __restrict__ row = a.nbr + base;
 #pragma unroll 2
     for (unsigned e = lane; e < cnt; e += 32) {
       const uint32_t j = __ldg(row + e);
       const SPos pj = a.spos[j];
-      pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, fx, fy, fz, acc);
+      const bool flip = a.two_groups ? row_is_b : (pi.slot > pj.slot);
+      pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
     }
     fx = warp_sum(fx);
     fy = warp_sum(fy);
@@ -317,7 +330,8 @@ __global__ void __launch_bounds__(kSweepThreads)
             const uint32_t j = s0 + e;
             const SPos pj = a.spos[j];
             const bool valid = (j != k) && (!a.check_abs || pj.abs_index != pi.abs_index);
-            if (valid) pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, fx, fy, fz, acc);
+            const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
+            if (valid) pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
           }
         }
       }
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(kSweepThreads)
       pj.x = pos[ib];
       pj.y = pos[ib + 1];
       pj.z = pos[ib + 2];
-      pair_term<K, PBC, true>(pbc, sw, pos[ia], pos[ia + 1], pos[ia + 2], pj, fx, fy, fz, acc);
+      pair_term<K, PBC, true>(pbc, sw, pos[ia], pos[ia + 1], pos[ia + 2], pj, false, fx, fy, fz, acc);
       evals = 1;
     }
     out[ia] = fx;  // deriv[i0] -= dd

@@ -1,0 +1,226 @@
+// The PLUMED-facing side of the drop-in: a Colvar registered under the key "COORDINATION".
+//
+// Loaded with `LOAD FILE=libb200coord_plumed.so` at the top of plumed.dat it overrides the built-in
+// COORDINATION for every later input line (src/core/RegisterBase.h:236-252, src/setup/Load.cpp:86-135),
+// for `plumed driver`, `plumed benchmark` and any MD engine talking plumed_cmd.  It keeps the keyword set
+// of src/colvar/CoordinationBase.cpp:30-40 and src/colvar/Coordination.cpp:115-126 (plus the additive
+// top-level D_MAX of plugins/cudaCoord), the prepare()/calculate() life cycle and the error texts, and does
+// every computation through the C ABI of libb200coord.so (include/b200coord.h).  No pair is ever evaluated
+// on the host; if the CUDA library reports an error the action calls error().
+#include "b200coord.h"
+#include "core/ActionRegister.h"
+#include "core/Colvar.h"
+#include "tools/Communicator.h"
+#include "tools/Pbc.h"
+
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace PLMD {
+namespace colvar {
+
+class CoordinationB200 : public Colvar {
+  b200coord_ctx* ctx = nullptr;
+  bool pbc = true;
+  bool serial = false;
+  bool combineWithMpi = false;
+  std::vector<double> derivBuffer;
+  void check(int rc, const char* what);
+
+public:
+  explicit CoordinationB200(const ActionOptions&);
+  ~CoordinationB200() override;
+  static void registerKeywords(Keywords& keys);
+  void prepare() override;
+  void calculate() override;
+};
+
+PLUMED_REGISTER_ACTION(CoordinationB200, "COORDINATION")
+
+void CoordinationB200::registerKeywords(Keywords& keys) {
+  Colvar::registerKeywords(keys);
+  keys.addFlag("SERIAL", false, "Perform the calculation in serial - for debug purpose");
+  keys.addFlag("PAIR", false, "Pair only 1st element of the 1st group with 1st element in the second, etc");
+  keys.addFlag("NLIST", false, "Use a neighbor list to speed up the calculation");
+  keys.addFlag("NLISTCELLS", false, "Use a neighbor list to speed up the calculation - cell list flavour (27-cell superset)");
+  keys.add("optional", "NL_CUTOFF", "The cutoff for the neighbor list");
+  keys.add("optional", "NL_STRIDE", "The frequency with which we are updating the atoms in the neighbor list");
+  keys.add("atoms", "GROUPA", "First list of atoms");
+  keys.add("atoms", "GROUPB", "Second list of atoms (if empty, N*(N-1)/2 pairs in GROUPA are counted)");
+  keys.add("compulsory", "NN", "6", "The n parameter of the switching function ");
+  keys.add("compulsory", "MM", "0", "The m parameter of the switching function; 0 implies 2*NN");
+  keys.add("compulsory", "D_0", "0.0", "The d_0 parameter of the switching function");
+  keys.add("compulsory", "R_0", "The r_0 parameter of the switching function");
+  keys.add("optional", "D_MAX", "cut the rational switching function built from R_0/NN/MM/D_0 at this distance (stretched to zero)");
+  keys.add("optional", "SWITCH", "This keyword is used if you want to employ an alternative to the continuous switching function defined above. "
+           "When this keyword is present you no longer need the NN, MM, D_0 and R_0 keywords.");
+  keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
+  keys.setValueDescription("scalar", "the value of the coordination");
+}
+
+void CoordinationB200::check(int rc, const char* what) {
+  if (rc != B200COORD_OK) {
+    error(std::string(what) + " failed on the GPU: " + b200coord_last_error(ctx));
+  }
+}
+
+CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT(ao) {
+  parseFlag("SERIAL", serial);
+  std::vector<AtomNumber> ga, gb;
+  parseAtomList("GROUPA", ga);
+  parseAtomList("GROUPB", gb);
+  bool nopbc = !pbc;
+  parseFlag("NOPBC", nopbc);
+  pbc = !nopbc;
+  bool dopair = false;
+  parseFlag("PAIR", dopair);
+  bool classic = false, cells = false;
+  parseFlag("NLIST", classic);
+  parseFlag("NLISTCELLS", cells);
+  plumed_assert(!(cells && classic)) << "Please activate only one of the two version of the NL";
+  plumed_assert(!(cells && dopair)) << "Pair is not compatible with the CELLS implementation of the NL";
+  double nlCut = 0.0;
+  int nlStride = 0;
+  if (classic || cells) {
+    parse("NL_CUTOFF", nlCut);
+    if (nlCut <= 0.0) {
+      error("NL_CUTOFF should be explicitly specified and positive");
+    }
+    parse("NL_STRIDE", nlStride);
+    if (nlStride <= 0) {
+      error("NL_STRIDE should be explicitly specified and positive");
+    }
+  }
+  if (dopair && ga.size() != gb.size()) {
+    error("when using PAIR option, the two groups should have the same number of elements");
+  }
+
+  b200coord_switch sw;
+  std::string swDef;
+  parse("SWITCH", swDef);
+  if (!swDef.empty()) {
+    char err[1024];
+    const int rc = b200coord_switch_parse(swDef.c_str(), &sw, err, sizeof(err));
+    if (rc != B200COORD_OK) {
+      error("problem reading SWITCH keyword : " + std::string(err));
+    }
+  } else {
+    int nn = 6, mm = 0;
+    double d0 = 0.0, r0 = 0.0, dmax = -1.0;
+    parse("R_0", r0);
+    if (r0 <= 0.0) {
+      error("R_0 should be explicitly specified and positive");
+    }
+    parse("D_0", d0);
+    parse("NN", nn);
+    parse("MM", mm);
+    parse("D_MAX", dmax);
+    if (dmax > 0.0) {
+      const std::string def = "RATIONAL R_0=" + std::to_string(r0) + " D_0=" + std::to_string(d0) + " NN=" + std::to_string(nn) +
+                              " MM=" + std::to_string(mm) + " D_MAX=" + std::to_string(dmax);
+      char err[1024];
+      if (b200coord_switch_parse(def.c_str(), &sw, err, sizeof(err)) != B200COORD_OK) {
+        error("problem building the switching function : " + std::string(err));
+      }
+    } else {
+      b200coord_switch_rational(nn, mm, r0, d0, &sw);
+    }
+  }
+  int device = -1;
+  if (const char* env = std::getenv("B200COORD_DEVICE")) {
+    device = std::atoi(env);
+  }
+  parse("GPU_DEVICE", device);
+  checkRead();
+
+  addValueWithDerivatives();
+  setNotPeriodic();
+
+  std::vector<AtomNumber> all(ga);
+  all.insert(all.end(), gb.begin(), gb.end());
+  std::vector<unsigned> absIndex(all.size());
+  for (unsigned i = 0; i < all.size(); ++i) {
+    absIndex[i] = all[i].index();
+  }
+
+  b200coord_config cfg;
+  cfg.abi_version = B200COORD_ABI_VERSION;
+  cfg.device = device;
+  cfg.precision = B200COORD_FP64;
+  cfg.style = gb.empty() ? B200COORD_STYLE_SINGLELIST : (dopair ? B200COORD_STYLE_PAIR : B200COORD_STYLE_TWOLIST);
+  cfg.n_group_a = ga.size();
+  cfg.n_group_b = gb.size();
+  cfg.pbc = pbc ? 1 : 0;
+  cfg.nl_mode = cells ? B200COORD_NL_CELLS : (classic ? B200COORD_NL_CLASSIC : B200COORD_NL_NONE);
+  cfg.nl_cutoff = nlCut;
+  cfg.nl_stride = nlStride;
+  // the reference splits the pair range over MPI ranks and sums with Comm::Sum (CoordinationBase.cpp:152-170,
+  // :218-224); here every rank's context takes the same share of the i-atoms and the partial results are
+  // summed over the PLUMED communicator in exactly the same way.
+  combineWithMpi = !serial && comm.Get_size() > 1;
+  cfg.rank = combineWithMpi ? comm.Get_rank() : 0;
+  cfg.nranks = combineWithMpi ? comm.Get_size() : 1;
+  const int rc = b200coord_create(&cfg, &sw, absIndex.data(), &ctx);
+  if (rc != B200COORD_OK) {
+    error(std::string("cannot set up the B200 COORDINATION engine: ") + b200coord_last_error(nullptr));
+  }
+  derivBuffer.resize(3 * all.size());
+  requestAtoms(all);
+
+  char desc[512];
+  b200coord_switch_describe(&sw, desc, sizeof(desc));
+  log.printf("  B200-native COORDINATION (libb200coord, sm_100a kernels)\n");
+  log.printf("  between two groups of %u and %u atoms\n", static_cast<unsigned>(ga.size()), static_cast<unsigned>(gb.size()));
+  log.printf(pbc ? "  using periodic boundary conditions\n" : "  without periodic boundary conditions\n");
+  if (dopair) {
+    log.printf("  with PAIR option\n");
+  }
+  if (classic || cells) {
+    log.printf("  using neighbor lists (%s) with\n", cells ? "cell superset" : "distance filtered");
+    log.printf("  update every %d steps and cutoff %f\n", nlStride, nlCut);
+  }
+  log << "  contacts are counted with cutoff " << desc << "\n";
+}
+
+CoordinationB200::~CoordinationB200() {
+  b200coord_destroy(ctx);
+}
+
+void CoordinationB200::prepare() {
+  // NeighborList::prepare (src/tools/NeighborList.cpp:433-456); the full atom list stays requested on
+  // every step (legal: the reduced list is only a communication optimisation of the CPU code)
+  int willRebuild = 0;
+  const int rc = b200coord_prepare(ctx, static_cast<long>(getStep()), getExchangeStep() ? 1 : 0, &willRebuild);
+  if (rc != B200COORD_OK) {
+    error(b200coord_last_error(ctx));
+  }
+}
+
+void CoordinationB200::calculate() {
+  const unsigned n = getNumberOfAtoms();
+  double box[9];
+  const Tensor& b = getBox();
+  for (unsigned i = 0; i < 3; ++i)
+    for (unsigned j = 0; j < 3; ++j) {
+      box[3 * i + j] = b[i][j];
+    }
+  check(b200coord_set_box(ctx, box), "set_box");
+  double value = 0.0;
+  double virial[9];
+  const double* pos = n ? &getPositions()[0][0] : nullptr;
+  check(b200coord_calculate(ctx, pos, &value, derivBuffer.data(), virial), "calculate");
+  if (combineWithMpi) {
+    comm.Sum(value);
+    comm.Sum(derivBuffer);
+    comm.Sum(&virial[0], 9);
+  }
+  for (unsigned i = 0; i < n; ++i) {
+    setAtomsDerivatives(i, Vector(derivBuffer[3 * i], derivBuffer[3 * i + 1], derivBuffer[3 * i + 2]));
+  }
+  setValue(value);
+  setBoxDerivatives(Tensor(virial[0], virial[1], virial[2], virial[3], virial[4], virial[5], virial[6], virial[7], virial[8]));
+}
+
+}  // namespace colvar
+}  // namespace PLMD

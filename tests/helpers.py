@@ -42,3 +42,48 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-300)
     return np.abs(a - b).max() / scale
+
+
+def oracle_switch_from_kv(kv):
+    """the switching function a COORDINATION input line selects (Coordination.cpp:128-157)"""
+    if "SWITCH" in kv:
+        return O.make_switch(kv["SWITCH"])
+    if "D_MAX" in kv:  # additive top-level D_MAX (cudaCoord semantics)
+        return O.make_switch("RATIONAL R_0=%s D_0=%s NN=%s MM=%s D_MAX=%s" %
+                             (kv["R_0"], kv.get("D_0", "0.0"), kv.get("NN", "6"), kv.get("MM", "0"), kv["D_MAX"]))
+    return O.make_switch(nn=int(kv.get("NN", 6)), mm=int(kv.get("MM", 0)), r0=float(kv["R_0"]), d0=float(kv.get("D_0", 0.0)))
+
+
+def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast_list=False):
+    """evaluate a `c: COORDINATION ...` input line with the C oracle on full-system positions.
+    Returns dict(value, deriv (n,3) per requested atom, virial, pairs, atoms)"""
+    from plumed2_b200.coordination import parse_atom_list, split_input_line
+    _, action, kv, flags = split_input_line(line)
+    assert action == "COORDINATION"
+    ga = parse_atom_list(kv["GROUPA"])
+    gb = parse_atom_list(kv.get("GROUPB"))
+    atoms = np.concatenate([ga, gb]).astype(np.uint32)
+    style = "single" if gb.size == 0 else ("pair" if "PAIR" in flags else "two")
+    mode = "classic" if "NLIST" in flags else ("cells" if "NLISTCELLS" in flags else "none")
+    sw = oracle_switch_from_kv(kv)
+    pos = np.ascontiguousarray(np.asarray(positions, dtype=np.float64)[atoms])
+    lpos = None if list_positions is None else np.ascontiguousarray(np.asarray(list_positions, dtype=np.float64)[atoms])
+    v, d, vir, pairs, npairs = oracle_eval(pos, box, style, int(ga.size), int(gb.size), sw, do_pbc="NOPBC" not in flags,
+                                           nl_mode=mode, cutoff=float(kv.get("NL_CUTOFF", 1e30)),
+                                           stride=int(kv.get("NL_STRIDE", 0)), abs_index=atoms, nthreads=nthreads,
+                                           list_pos=lpos, fast_list=fast_list)
+    return dict(value=v, deriv=d, virial=vir, pairs=pairs, atoms=atoms, npairs=npairs)
+
+
+def sort_pairs(p):
+    p = np.asarray(p)
+    if p.shape[0] == 0:
+        return p.reshape(0, 2)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+def scatter_to_system(natoms, atoms, deriv):
+    """sum per-slot derivatives onto system atoms (what Colvar::apply does with a unit force)"""
+    out = np.zeros((natoms, 3))
+    np.add.at(out, atoms, deriv)
+    return out

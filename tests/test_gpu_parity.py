@@ -1,0 +1,362 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every test goes through the C ABI of
+libb200coord.so (via the ctypes mirror of the action) and compares with the CPU oracle on the same seeded
+inputs, with the committed golden outputs of the real reference, and -- at BASELINE.json sizes -- with
+size-independent properties.
+
+Tolerances (BASELINE.json north_star): neighbour-list pair sets bit-exact; value, derivatives and virial
+within 1e-10 relative in FP64."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import plumed2_b200 as P
+from helpers import oracle_from_line, rel_err, scatter_to_system, sort_pairs, water_box
+from oracle import oracle as O
+from plumed2_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NCPU = os.cpu_count() or 4
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "ref_outputs.npz"))
+
+
+def gpu_eval(line, pos, box, step=0, **kw):
+    c = P.Coordination.from_input(line, **kw)
+    c.prepare(step)
+    c.calculate(pos, box)
+    return c
+
+
+def assert_parity(c, ref, tag="", tol=TOL):
+    v = c.value
+    assert abs(v - ref["value"]) <= tol * max(abs(ref["value"]), 1e-300), (tag, v, ref["value"])
+    assert rel_err(c.derivatives, ref["deriv"]) <= tol, (tag, "derivatives", rel_err(c.derivatives, ref["deriv"]))
+    assert rel_err(c.virial, ref["virial"]) <= tol, (tag, "virial", rel_err(c.virial, ref["virial"]))
+
+
+SWITCHES = ["R_0=0.3", "R_0=0.3 NN=8 MM=16", "R_0=0.25 NN=6 MM=12 D_0=0.05", "R_0=0.3 D_MAX=0.7",
+            "SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8}", "SWITCH={RATIONAL R_0=0.3 NN=12 D_MAX=0.8}",
+            "SWITCH={RATIONAL R_0=0.3 NN=2 D_MAX=0.8}", "SWITCH={RATIONAL R_0=0.3 NN=4 MM=10 D_MAX=0.8}",
+            "SWITCH={RATIONAL R_0=0.3 NN=5 MM=11 D_MAX=0.8}", "SWITCH={RATIONAL R_0=0.3 NN=5 D_MAX=0.8}",
+            "SWITCH={RATIONAL R_0=0.3 NN=14 MM=28 D_MAX=0.8}", "SWITCH={RATIONAL R_0=0.3 D_MAX=0.8 NOSTRETCH}",
+            "SWITCH={EXP R_0=0.2 D_MAX=0.9}", "SWITCH={EXP R_0=0.2 D_0=0.1 D_MAX=0.8}",
+            "SWITCH={GAUSSIAN R_0=0.2 D_MAX=0.8}", "SWITCH={GAUSSIAN R_0=1.0 D_MAX=0.8}",
+            "SWITCH={SMAP R_0=0.3 A=4 B=3 D_MAX=0.8}", "SWITCH={CUBIC D_0=0.1 D_MAX=0.8}",
+            "SWITCH={TANH R_0=0.3 D_MAX=0.8}", "SWITCH={COSINUS R_0=0.5 D_0=0.2}",
+            "SWITCH={Q R_0=1.0 D_0=0.1 BETA=30.0 LAMBDA=1.5 REF=0.3 D_MAX=0.8}"]
+
+
+@pytest.mark.parametrize("sw", SWITCHES)
+@pytest.mark.parametrize("tri", [False, True])
+def test_every_switch_no_list(sw, tri):
+    """all GPU-capable switching functions, orthorhombic and triclinic minimum image, all pairs (config 1 style)"""
+    n = 400
+    pos, box = water_box(n, 100.0, seed=7 + tri, triclinic=tri, jitter=2.0)
+    line = "c: COORDINATION GROUPA=1-%d %s" % (n, sw)
+    c = gpu_eval(line, pos, box)
+    assert_parity(c, oracle_from_line(line, pos, box), line)
+    c.close()
+
+
+NL_LINES = [
+    ("single", "GROUPA=1-900 SWITCH={RATIONAL R_0=0.3 D_MAX=0.7} %s NL_CUTOFF=0.8 NL_STRIDE=5"),
+    ("two", "GROUPA=1-150 GROUPB=151-900 SWITCH={EXP R_0=0.2 D_MAX=0.7} %s NL_CUTOFF=0.8 NL_STRIDE=5"),
+    ("two_overlap", "GROUPA=1-500 GROUPB=300-900 SWITCH={GAUSSIAN R_0=0.2 D_MAX=0.7} %s NL_CUTOFF=0.8 NL_STRIDE=5"),
+    ("beyond_cutoff", "GROUPA=1-900 SWITCH={RATIONAL R_0=0.3 D_MAX=1.2} %s NL_CUTOFF=0.6 NL_STRIDE=5"),
+]
+
+
+@pytest.mark.parametrize("name,tmpl", NL_LINES)
+@pytest.mark.parametrize("mode", ["NLIST", "NLISTCELLS"])
+@pytest.mark.parametrize("boxkind", ["ortho", "tri", "nobox", "nopbc"])
+def test_neighbour_list_modes(name, tmpl, mode, boxkind):
+    """classic and cell lists, single/two lists, the three Pbc types; pair sets must be identical"""
+    n = 900
+    pos, box = water_box(n, 100.0, seed=11, triclinic=(boxkind == "tri"), jitter=1.5)
+    line = "c: COORDINATION " + (tmpl % mode)
+    if boxkind == "nopbc":
+        line += " NOPBC"
+    if boxkind == "nobox":
+        box = None
+    c = gpu_eval(line, pos, box)
+    ref = oracle_from_line(line, pos, box)
+    assert_parity(c, ref, line)
+    np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]), err_msg=line)
+    assert c.stats()["nl_size"] == ref["pairs"].shape[0]
+    c.close()
+
+
+def test_pair_style():
+    n = 800
+    pos, box = water_box(n, 100.0, seed=5, triclinic=True)
+    for extra in ("", " NLIST NL_CUTOFF=0.9 NL_STRIDE=3", " NOPBC"):
+        line = "c: COORDINATION GROUPA=1-400 GROUPB=401-800 SWITCH={RATIONAL R_0=0.6 D_MAX=1.5} PAIR" + extra
+        c = gpu_eval(line, pos, box)
+        ref = oracle_from_line(line, pos, box)
+        assert_parity(c, ref, line)
+        if "NLIST" in extra:
+            np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+        c.close()
+
+
+def test_golden_reference_outputs(gold):
+    """the CUDA path against numbers produced by the real reference (tests/golden/ref_outputs.npz)"""
+    for case in json.loads(str(gold["cases_json"])):
+        tag, line = case["tag"], case["line"]
+        key = "rt42" if tag.startswith("rt42") else ("ortho" if tag.startswith("ortho") else "tri")
+        pos = gold[key + "_pos"]
+        box = None if tag.startswith("nobox") else gold[key + "_box"]
+        c = gpu_eval(line, pos, box)
+        want_v = float(gold[tag + "_value"])
+        assert abs(c.value - want_v) <= TOL * abs(want_v), (tag, c.value, want_v)
+        got = scatter_to_system(pos.shape[0], c.atoms, c.derivatives)
+        want_d = gold[tag + "_deriv"]
+        # in the perfect rt42 crystal the derivatives cancel to ~1e-16: measure against the size of the terms
+        scale = max(np.abs(want_d).max(), abs(want_v) / pos.shape[0])
+        assert np.abs(got - want_d).max() <= TOL * scale, (tag, np.abs(got - want_d).max(), scale)
+        assert rel_err(c.virial, gold[tag + "_virial"]) <= TOL, tag
+        c.close()
+
+
+def test_golden_pair_sets(gold):
+    """neighbour-list pair sets of the reference's NeighborList class, bit-exact"""
+    for case in json.loads(str(gold["nl_cases_json"])):
+        pos = gold[case["pos"]]
+        box = None if case["box"] == "zero" else gold[case["box"]]
+        n0, n1 = case["n0"], case["n1"]
+        groups = "GROUPA=1-%d" % n0 + (" GROUPB=%d-%d" % (n0 + 1, n0 + n1) if n1 else "")
+        line = "c: COORDINATION %s R_0=0.3 %s NL_CUTOFF=%r NL_STRIDE=2%s%s" % (
+            groups, "NLISTCELLS" if case["cells"] else "NLIST", case["cutoff"], " PAIR" if case["style"] == 0 else "",
+            "" if case["do_pbc"] else " NOPBC")
+        c = P.Coordination.from_input(line)
+        c.update_list(pos, box)
+        np.testing.assert_array_equal(c.neighbor_pairs(), gold[case["tag"] + "_pairs"], err_msg=case["tag"])
+        c.close()
+
+
+def test_regtest_rt42_values(gold):
+    """regtest/basic/rt42, rt42c: 171.1815 (two identical groups) and half of it (single list)"""
+    pos, box = gold["rt42_pos"], gold["rt42_box"]
+    c = gpu_eval("c: COORDINATION GROUPA=1-108 GROUPB=1-108 R_0=1", pos, box)
+    assert abs(c.value - 171.1815) < 5.1e-5
+    c2 = gpu_eval("c: COORDINATION GROUPA=1-108 R_0=1", pos, box)
+    assert abs(c2.value - 171.1815 / 2) < 5.1e-5 and abs(2 * c2.value - c.value) < 1e-9
+    # rt42-cells: NLIST and NLISTCELLS agree
+    a = gpu_eval("c: COORDINATION GROUPA=1-108 SWITCH={RATIONAL R_0=1 D_MAX=1.5} NLIST NL_CUTOFF=2.0 NL_STRIDE=4", pos, box)
+    b = gpu_eval("c: COORDINATION GROUPA=1-108 SWITCH={RATIONAL R_0=1 D_MAX=1.5} NLISTCELLS NL_CUTOFF=2.0 NL_STRIDE=4", pos, box)
+    assert abs(a.value - b.value) < 1e-10 * abs(a.value)
+    for x in (c, c2, a, b):
+        x.close()
+
+
+@pytest.mark.parametrize("mode", ["NLIST", "NLISTCELLS"])
+@pytest.mark.parametrize("tri", [False, True])
+def test_frozen_list_between_rebuilds(mode, tri):
+    """NL_STRIDE=4: the pair set is frozen at the rebuild step while atoms move far enough that pairs cross
+    the cutoff -- value/derivatives must follow the reference's frozen-list semantics at every step"""
+    n = 700
+    pos0, box = water_box(n, 100.0, seed=21, triclinic=tri)
+    rng = np.random.default_rng(3)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.75} %s NL_CUTOFF=0.8 NL_STRIDE=4" % (n, mode)
+    c = P.Coordination.from_input(line)
+    onl = O.NeighborList(O.NL_SINGLELIST, n, 0, cutoff=0.8, stride=4, use_cells=(mode == "NLISTCELLS"))
+    pos, list_pos = pos0.copy(), None
+    for step in range(3, 14):
+        pos = pos + 0.03 * rng.standard_normal(pos.shape)
+        rebuild = c.prepare(step)
+        assert rebuild == onl.prepare(step)
+        if rebuild:
+            list_pos = pos.copy()
+        c.calculate(pos, box)
+        ref = oracle_from_line(line, pos, box, list_positions=list_pos)
+        assert_parity(c, ref, "%s step %d" % (mode, step))
+        if mode == "NLIST":
+            np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+    assert c.stats()["rebuilds"] == 4  # steps 3 (first), 4, 8, 12
+    c.close()
+
+
+def test_exchange_step_rules():
+    c = P.Coordination.from_input("c: COORDINATION GROUPA=1-50 R_0=0.3 NLIST NL_CUTOFF=1.0 NL_STRIDE=5")
+    assert c.prepare(0) is True
+    with pytest.raises(capi.B200CoordError) as e:  # NeighborList.cpp:447-449
+        c.prepare(1, exchange_step=True)
+    assert "exchange" in str(e.value)
+    assert c.prepare(2) is True  # firsttime was re-armed by the exchange step (:451-453)
+    c.close()
+
+
+EDGE = [
+    ("two atoms", 2, "GROUPA=1-2 R_0=0.5"),
+    ("two atoms nlist", 2, "GROUPA=1-2 R_0=0.5 NLIST NL_CUTOFF=3.0 NL_STRIDE=1"),
+    ("one vs many", 64, "GROUPA=1 GROUPB=2-64 SWITCH={EXP R_0=0.3 D_MAX=1.0} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=1"),
+    ("33 atoms", 33, "GROUPA=1-33 R_0=0.3 NLIST NL_CUTOFF=0.5 NL_STRIDE=1"),
+    ("one cell", 50, "GROUPA=1-50 R_0=0.3 NLISTCELLS NL_CUTOFF=5.0 NL_STRIDE=1"),
+    ("two cells per axis", 300, "GROUPA=1-300 SWITCH={RATIONAL R_0=0.3 D_MAX=0.6} NLIST NL_CUTOFF=0.65 NL_STRIDE=1"),
+    ("two cells per axis, cells", 300, "GROUPA=1-300 SWITCH={RATIONAL R_0=0.3 D_MAX=0.6} NLISTCELLS NL_CUTOFF=0.65 NL_STRIDE=1"),
+    ("duplicate atoms", 40, "GROUPA=1-40,5,6,7 R_0=0.3"),
+    ("duplicate atoms nlist", 40, "GROUPA=1-40,5,6,7 R_0=0.3 NLIST NL_CUTOFF=0.6 NL_STRIDE=1"),
+    ("identical groups", 60, "GROUPA=1-60 GROUPB=1-60 R_0=0.3 NLIST NL_CUTOFF=0.9 NL_STRIDE=1"),
+    ("identical groups cells", 60, "GROUPA=1-60 GROUPB=1-60 R_0=0.3 NLISTCELLS NL_CUTOFF=0.9 NL_STRIDE=1"),
+    ("empty rows", 30, "GROUPA=1-30 SWITCH={RATIONAL R_0=0.05 D_MAX=0.1} NLIST NL_CUTOFF=0.1 NL_STRIDE=1"),
+    ("reversed ranges", 100, "GROUPA=100-1:-1 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=0.9 NL_STRIDE=1"),
+]
+
+
+@pytest.mark.parametrize("name,n,body", EDGE)
+def test_edge_cases(name, n, body):
+    pos, box = water_box(n, 100.0 if n > 10 else 5.0, seed=n, jitter=0.5)
+    if "per axis" in name:
+        box = np.diag([1.35, 1.4, 1.45])
+    line = "c: COORDINATION " + body
+    c = gpu_eval(line, pos, box)
+    ref = oracle_from_line(line, pos, box)
+    assert_parity(c, ref, name)
+    if ref["pairs"] is not None:
+        np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]), err_msg=name)
+    c.close()
+
+
+def test_far_away_and_unwrapped_coordinates():
+    """positions many box lengths outside the cell (an MD engine that never wraps)"""
+    n = 500
+    pos, box = water_box(n, 100.0, seed=9, triclinic=True)
+    shifts = np.random.default_rng(1).integers(-7, 8, size=(n, 3)).astype(np.float64) @ box
+    for mode in ("NLIST", "NLISTCELLS"):
+        line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.7} %s NL_CUTOFF=0.8 NL_STRIDE=1" % (n, mode)
+        c = gpu_eval(line, pos + shifts, box)
+        ref = oracle_from_line(line, pos + shifts, box)
+        assert_parity(c, ref, mode)
+        np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+        c.close()
+
+
+def test_run_to_run_determinism_and_device_entry_point():
+    n = 3000
+    pos, box = water_box(n, 100.0, seed=2)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=2" % n
+    a = gpu_eval(line, pos, box)
+    b = gpu_eval(line, pos, box)
+    assert a.value == b.value and np.array_equal(a.derivatives, b.derivatives) and np.array_equal(a.virial, b.virial)
+    # device-resident entry point gives the same bits as the host one
+    L = capi.lib()
+    dpos, dout = C.c_void_p(), C.c_void_p()
+    capi.check(L.b200coord_device_alloc(pos.nbytes, C.byref(dpos)))
+    capi.check(L.b200coord_device_alloc((3 * n + 10) * 8, C.byref(dout)))
+    hp = np.ascontiguousarray(pos)
+    capi.check(L.b200coord_memcpy_h2d(dpos, hp.ctypes.data_as(C.c_void_p), hp.nbytes))
+    b.prepare(1)
+    capi.check(L.b200coord_calculate_device(b._ctx, dpos, dout), b._ctx)
+    out = np.zeros(3 * n + 10)
+    capi.check(L.b200coord_memcpy_d2h(out.ctypes.data_as(C.c_void_p), dout, out.nbytes))
+    assert out[3 * n + 9] == a.value and np.array_equal(out[:3 * n].reshape(n, 3), a.derivatives)
+    assert np.array_equal(out[3 * n:3 * n + 9].reshape(3, 3), a.virial)
+    L.b200coord_device_free(dpos)
+    L.b200coord_device_free(dout)
+    a.close()
+    b.close()
+
+
+def test_rank_sharding_partials_sum_to_full():
+    """i-atom sharding (cfg.rank/nranks) without a communicator: partial outputs add up to the full result,
+    which is what the plugin feeds to PLUMED's Comm::Sum under MPI"""
+    n = 2500
+    pos, box = water_box(n, 100.0, seed=4, triclinic=True)
+    for body in ("GROUPA=1-2500 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=1",
+                 "GROUPA=1-400 GROUPB=401-2500 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=1",
+                 "GROUPA=1-1250 GROUPB=1251-2500 R_0=0.5 PAIR"):
+        line = "c: COORDINATION " + body
+        full = gpu_eval(line, pos, box)
+        v, d, w = 0.0, 0.0, 0.0
+        for r in range(3):
+            part = gpu_eval(line, pos, box, rank=r, nranks=3)
+            v, d, w = v + part.value, d + part.derivatives, w + part.virial
+            part.close()
+        assert abs(v - full.value) <= TOL * abs(full.value)
+        assert rel_err(d, full.derivatives) <= TOL and rel_err(w, full.virial) <= TOL
+        full.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes
+def test_config2_100k_atoms_full_parity():
+    """configs[1]: 100k atoms, orthorhombic, NLIST 1.0/10, D_MAX=0.8 -- full comparison with the oracle"""
+    n = 100000
+    pos, box = water_box(n, 100.0)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=10" % n
+    c = gpu_eval(line, pos, box)
+    ref = oracle_from_line(line, pos, box, nthreads=NCPU, fast_list=True)
+    assert_parity(c, ref, "config2")
+    np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+    # second frame on the frozen list
+    pos2 = pos + 0.005 * np.random.default_rng(0).standard_normal(pos.shape)
+    assert c.prepare(1) is False
+    c.calculate(pos2, box)
+    assert_parity(c, oracle_from_line(line, pos2, box, list_positions=pos, nthreads=NCPU, fast_list=True), "config2 frame 2")
+    c.close()
+
+
+def test_config3_solute_solvent_triclinic_exp():
+    """configs[2] scaled to what the O(N) oracle finishes quickly: 2k solute vs 200k solvent, triclinic, EXP,
+    rebuild every step; NLISTCELLS and NLIST must agree with the oracle and with each other"""
+    na, nb = 2000, 200000
+    pos, box = water_box(na + nb, 100.0, seed=33, triclinic=True)
+    base = "c: COORDINATION GROUPA=1-%d GROUPB=%d-%d SWITCH={EXP R_0=0.2 D_MAX=0.9} %%s NL_CUTOFF=1.0 NL_STRIDE=1" % (na, na + 1, na + nb)
+    a = gpu_eval(base % "NLIST", pos, box)
+    b = gpu_eval(base % "NLISTCELLS", pos, box)
+    ref = oracle_from_line(base % "NLIST", pos, box, nthreads=NCPU, fast_list=True)
+    assert_parity(a, ref, "config3 NLIST")
+    assert_parity(b, ref, "config3 NLISTCELLS")
+    np.testing.assert_array_equal(a.neighbor_pairs(), sort_pairs(ref["pairs"]))
+    a.close()
+    b.close()
+
+
+def test_one_million_atoms_properties():
+    """headline size (1M atoms, NLIST): properties that need no O(N) oracle run"""
+    n = 1000000
+    pos, box = water_box(n, 100.0, seed=99)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=10" % n
+    c = gpu_eval(line, pos, box)
+    v, d, w = c.value, c.derivatives.copy(), c.virial.copy()
+    scale = np.abs(d).max()
+    assert np.abs(d.sum(axis=0)).max() <= 1e-9 * scale * np.sqrt(n)          # Newton's third law
+    assert np.abs(w - w.T).max() <= 1e-12 * np.abs(w).max()                   # symmetric virial
+    nl = c.stats()["nl_size"]
+    expect = 0.5 * n * (4.0 / 3.0 * np.pi) * 100.0                            # pairs within 1.0 nm at 100/nm^3
+    assert abs(nl - expect) < 0.01 * expect
+    # rigid translation by an arbitrary vector + re-wrapping by whole box vectors changes nothing
+    c2 = gpu_eval(line, pos + np.array([0.123, -4.56, 7.89]) + box[0] - 2 * box[2], box)
+    assert abs(c2.value - v) <= TOL * abs(v) and rel_err(c2.derivatives, d) <= 1e-9
+    assert c2.stats()["nl_size"] == nl
+    # permutation of the atom order permutes the derivatives
+    perm = np.random.default_rng(5).permutation(n)
+    c3 = gpu_eval(line, pos[perm], box)
+    assert abs(c3.value - v) <= TOL * abs(v) and rel_err(c3.derivatives, d[perm]) <= TOL
+    assert rel_err(c3.virial, w) <= TOL
+    # the cell-list flavour agrees
+    c4 = gpu_eval(line.replace("NLIST", "NLISTCELLS"), pos, box)
+    assert abs(c4.value - v) <= TOL * abs(v) and rel_err(c4.derivatives, d) <= TOL
+    # 300 randomly chosen atoms against a brute-force numpy evaluation of their rows
+    sw = O.make_switch("RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8")
+    L = box[0, 0]
+    for i in np.random.default_rng(6).choice(n, 300, replace=False):
+        dd = pos - pos[i]
+        dd -= L * np.round(dd / L)
+        r2 = (dd * dd).sum(axis=1)
+        idx = np.nonzero((r2 <= 0.64) & (r2 > 0))[0]
+        g = np.zeros(3)
+        for j in idx:
+            s, df = O.switch_calculate_sqr(sw, r2[j])
+            g -= df * dd[j]
+        assert np.abs(g - d[i]).max() <= 1e-9 * scale
+    for x in (c, c2, c3, c4):
+        x.close()

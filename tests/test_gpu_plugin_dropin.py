@@ -1,0 +1,135 @@
+"""Drop-in test on the GPU box: the UNMODIFIED reference PlumedMain (oracle/_ref, driven through plumed_cmd
+like an MD engine) runs the same plumed.dat twice -- once with the built-in CPU COORDINATION, once with
+`LOAD FILE=libb200coord_plumed.so` in front, which makes our action answer to the key COORDINATION -- and the
+bias, the forces on all atoms and the virial coming back through setForces/setVirial must agree.
+Pattern follows plugins/cudaCoord/regtest (CPU and GPU action in one comparison)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import rel_err, water_box
+from oracle import refplumed as R
+from plumed2_b200 import capi
+
+pytestmark = [pytest.mark.gpu, pytest.mark.ref]
+
+PLUGIN = os.path.join(os.path.dirname(capi.LIB_PATH), "libb200coord_plumed.so")
+
+
+def _need():
+    if not R.available():
+        pytest.skip("oracle/_ref (the reference build) is not present on this box")
+    if not os.path.exists(PLUGIN):
+        pytest.skip("plugin .so not built")
+
+
+def run_both(natoms, lines, frames, box, watch=("c",)):
+    os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
+    outs = []
+    for load in (False, True):
+        pre = ["LOAD FILE=" + PLUGIN] if load else []
+        p = R.Plumed(natoms, pre + lines, watch=watch, log="/tmp/plumed_%s.log" % ("gpu" if load else "cpu"))
+        res = []
+        for step, pos in enumerate(frames):
+            r = p.calc(step, pos, box)
+            r["values"] = {w: p.value(w) for w in watch}
+            res.append(r)
+        p.close()
+        outs.append(res)
+    if "B200-native COORDINATION" not in open("/tmp/plumed_gpu.log").read():
+        raise AssertionError("the loaded plugin did not take over the COORDINATION key")
+    assert "B200-native COORDINATION" not in open("/tmp/plumed_cpu.log").read()
+    return outs
+
+
+def compare(cpu, gpu, tol=1e-10):
+    for step, (a, b) in enumerate(zip(cpu, gpu)):
+        for k in a["values"]:
+            assert abs(a["values"][k] - b["values"][k]) <= tol * max(abs(a["values"][k]), 1e-300), (step, k)
+        assert abs(a["bias"] - b["bias"]) <= tol * max(abs(a["bias"]), 1e-300), step
+        assert rel_err(b["forces"], a["forces"]) <= tol, (step, rel_err(b["forces"], a["forces"]))
+        assert rel_err(b["virial"], a["virial"]) <= tol, step
+
+
+def trajectory(n, nframes, seed, triclinic=False, step=0.01):
+    pos, box = water_box(n, 100.0, seed=seed, triclinic=triclinic)
+    rng = np.random.default_rng(seed)
+    frames = []
+    for _ in range(nframes):
+        pos = pos + step * rng.standard_normal(pos.shape)
+        frames.append(pos.copy())
+    return frames, box
+
+
+@pytest.mark.parametrize("body", [
+    "GROUPA=1-2000 R_0=0.3",
+    "GROUPA=1-2000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+    "GROUPA=1-2000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=3",
+    "GROUPA=1-300 GROUPB=301-2000 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=1",
+    "GROUPA=1-1000 GROUPB=1001-2000 R_0=0.4 PAIR",
+    "GROUPA=1-2000 SWITCH={GAUSSIAN R_0=0.25 D_MAX=0.9} NOPBC",
+])
+@pytest.mark.parametrize("tri", [False, True])
+def test_driver_style_runs_match(body, tri):
+    _need()
+    frames, box = trajectory(2000, 7, seed=12, triclinic=tri)
+    lines = ["c: COORDINATION " + body, "RESTRAINT ARG=c AT=100 KAPPA=0.01 SLOPE=0.5"]
+    cpu, gpu = run_both(2000, lines, frames, box)
+    compare(cpu, gpu)
+
+
+def test_metad_with_grid_bias():
+    """configs[3] in miniature: COORDINATION driving METAD with a GRID bias through plumed_cmd; forces and
+    virial returned every step (hills are deposited, so the bias history must stay identical too)"""
+    _need()
+    n = 3000
+    frames, box = trajectory(n, 12, seed=44, step=0.02)
+    outs = []
+    for load in (False, True):
+        hills = "/tmp/HILLS_%s" % ("gpu" if load else "cpu")
+        if os.path.exists(hills):
+            os.remove(hills)
+        lines = ["c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=4" % n,
+                 "md: METAD ARG=c SIGMA=20 HEIGHT=1.2 PACE=2 GRID_MIN=0 GRID_MAX=60000 GRID_BIN=3000 FILE=" + hills]
+        pre = ["LOAD FILE=" + PLUGIN] if load else []
+        p = R.Plumed(n, pre + lines, watch=("c",))
+        res = []
+        for step, pos in enumerate(frames):
+            r = p.calc(step, pos, box)
+            r["values"] = {"c": p.value("c")}
+            res.append(r)
+        p.close()
+        outs.append(res)
+    compare(outs[0], outs[1], tol=1e-9)
+    assert abs(outs[0][-1]["bias"]) > 0.0
+
+
+def test_plumed_driver_cli(tmp_path):
+    """the same through the `plumed driver` executable and an xyz trajectory (configs[0] workflow)"""
+    _need()
+    import subprocess
+    n = 1000
+    frames, box = trajectory(n, 3, seed=8)
+    xyz = tmp_path / "traj.xyz"
+    with open(xyz, "w") as f:
+        for pos in frames:
+            f.write("%d\n%.10f %.10f %.10f\n" % (n, box[0, 0], box[1, 1], box[2, 2]))
+            for p in pos:
+                f.write("Ar %.12f %.12f %.12f\n" % tuple(p))
+    dat = tmp_path / "plumed.dat"
+    dat.write_text("cpu: COORDINATION GROUPA=1-1000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12}\n"
+                   "LOAD FILE=%s\n"
+                   "gpu: COORDINATION GROUPA=1-1000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12}\n"
+                   "diff: CUSTOM ARG=cpu,gpu FUNC=y-x PERIODIC=NO\n"
+                   "PRINT ARG=cpu,gpu,diff FILE=%s FMT=%%.14g\n"
+                   "DUMPDERIVATIVES ARG=cpu,gpu FILE=%s FMT=%%.14g\n" % (PLUGIN, tmp_path / "COLVAR", tmp_path / "DERIV"))
+    env = dict(os.environ, PLUMED_NUM_THREADS="1")
+    r = subprocess.run([R.PLUMED_BIN, "driver", "--plumed", str(dat), "--ixyz", str(xyz), "--length-units", "nm"],
+                       cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    rows = np.loadtxt(tmp_path / "COLVAR", comments="#")
+    assert rows.shape == (3, 4)
+    assert np.all(np.abs(rows[:, 3]) <= 1e-10 * np.abs(rows[:, 1]))
+    der = np.loadtxt(tmp_path / "DERIV", comments="#")
+    assert rel_err(der[:, 3], der[:, 2]) <= 1e-10
