@@ -101,6 +101,10 @@ typedef struct b200coord_stats {
   float last_h2d_ms, last_d2h_ms;    /* last host<->device copies inside calculate */
   unsigned ncells[3];                /* cell grid in use */
   int pbc_type;                      /* 0 unset, 1 orthorhombic, 2 generic (Pbc.h:52) */
+  float sweep_ms_sum;                /* CUDA-event time of all pair sweeps since the last b200coord_stream_mark(ctx,0) ... */
+  unsigned sweep_count;              /* ... and how many sweeps that covers (at most the last 64 are kept) */
+  float build_ms_sum;                /* same for list rebuilds */
+  unsigned build_count;
 } b200coord_stats;
 
 typedef struct b200coord_ctx b200coord_ctx;
@@ -137,6 +141,24 @@ int b200coord_update_list(b200coord_ctx* ctx, const double* pos);
 int b200coord_calculate(b200coord_ctx* ctx, const double* pos, double* value, double* deriv, double* virial);
 /* same with device-resident buffers: d_pos n*3 doubles, d_out 3n+10 doubles = [deriv | virial(9) | value] */
 int b200coord_calculate_device(b200coord_ctx* ctx, const double* d_pos, double* d_out);
+
+/* enqueue-only variant for callers that live on the GPU (GPU-resident MD engines, the HBM-resident leg of
+ * bench.py): same work on the context's stream, no host synchronisation at the end unless a list rebuild needs
+ * to size its buffers.  Results are valid after b200coord_stream_elapsed_ms / b200coord_device_synchronize. */
+int b200coord_enqueue_device(b200coord_ctx* ctx, const double* d_pos, double* d_out);
+/* CUDA-event stopwatch on the context's own stream (where all its kernels are launched) */
+int b200coord_stream_mark(b200coord_ctx* ctx, int which /*0 = start, 1 = stop*/);
+int b200coord_stream_elapsed_ms(b200coord_ctx* ctx, float* ms);   /* waits for the stop mark */
+/* Distributed step (needs b200coord_comm_init): this rank uploads only its slice of the positions
+ * [slot_begin, slot_begin+slot_count) (equal chunks of ceil(n/nranks) slots, rank-ordered), positions are
+ * all-gathered over NVLink, every rank sweeps its own i-atoms, derivative rows are all-gathered and
+ * value/virial all-reduced (the Comm::Sum of CoordinationBase.cpp:218-224), and only this rank's slice of
+ * the derivatives is copied back to deriv_slice (slot_count*3 doubles). */
+int b200coord_calculate_distributed(b200coord_ctx* ctx, const double* pos_slice, double* value, double* deriv_slice,
+                                    double* virial);
+int b200coord_my_slice(const b200coord_ctx* ctx, unsigned* slot_begin, unsigned* slot_count);
+/* FP64 FMA peak of the device measured with a register-resident DFMA kernel (roofline denominator) */
+int b200coord_measure_fp64_peak(int device, double* tflops);
 
 /* ---- inspection */
 int b200coord_get_stats(const b200coord_ctx* ctx, b200coord_stats* out);

@@ -27,7 +27,9 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_calculate_device", "b200coord_get_stats", "b200coord_nl_pairs",
             "b200coord_comm_unique_id", "b200coord_comm_init", "b200coord_host_alloc", "b200coord_host_free",
             "b200coord_device_alloc", "b200coord_device_free", "b200coord_memcpy_h2d", "b200coord_memcpy_d2h",
-            "b200coord_device_synchronize"]
+            "b200coord_device_synchronize", "b200coord_enqueue_device", "b200coord_stream_mark",
+            "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
+            "b200coord_measure_fp64_peak"]
 
 
 class B200CoordError(RuntimeError):
@@ -56,7 +58,8 @@ class Stats(C.Structure):
     _fields_ = [("nl_size", C.c_ulonglong), ("pair_evals", C.c_ulonglong), ("kernel_launches", C.c_ulonglong),
                 ("rebuilds", C.c_ulonglong), ("last_sweep_ms", C.c_float), ("last_build_ms", C.c_float),
                 ("last_h2d_ms", C.c_float), ("last_d2h_ms", C.c_float), ("ncells", C.c_uint * 3),
-                ("pbc_type", C.c_int)]
+                ("pbc_type", C.c_int), ("sweep_ms_sum", C.c_float), ("sweep_count", C.c_uint),
+                ("build_ms_sum", C.c_float), ("build_count", C.c_uint)]
 
 
 _lib = None
@@ -97,6 +100,12 @@ def lib():
     L.b200coord_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.b200coord_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.b200coord_device_synchronize.argtypes = []
+    L.b200coord_enqueue_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200coord_stream_mark.argtypes = [C.c_void_p, C.c_int]
+    L.b200coord_stream_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.b200coord_calculate_distributed.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_void_p, dp]
+    L.b200coord_my_slice.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    L.b200coord_measure_fp64_peak.argtypes = [C.c_int, dp]
     if L.b200coord_abi_version() != ABI_VERSION:
         raise ImportError("libb200coord ABI version mismatch")
     _lib = L

@@ -93,8 +93,13 @@ struct b200coord_ctx {
   std::vector<unsigned> abs_host;
   int device = 0;
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[8] = {nullptr};  // 0/1 h2d, 2/3 sweep, 4/5 build, 6/7 d2h
+  cudaEvent_t ev[10] = {nullptr};  // 0/1 h2d, 2/3 sweep, 4/5 build, 6/7 d2h, 8/9 user stopwatch
   bool ev_valid[4] = {false, false, false, false};
+  static constexpr int kRing = 64;
+  cudaEvent_t sweep_ev[2 * kRing] = {nullptr};  // per-step sweep stopwatch pairs since the last stream_mark(0)
+  unsigned sweep_n = 0;
+  float build_ms_acc = 0.f;
+  unsigned build_n = 0;
 
   HostPbc hpbc;
   DevPbc dpbc;
@@ -109,6 +114,7 @@ struct b200coord_ctx {
 
   // rows of this rank
   unsigned row_begin = 0, row_end = 0, row_chunk = 0;
+  unsigned slot_begin = 0, slot_count = 0;  // this rank's slice of the position array (distributed step)
 
   DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small;
   DevBuf<uint32_t> d_abs, d_perm, d_scell, d_cell_of_slot, d_tmp, d_ccount, d_cstart, d_cursor, d_rowcount, d_nbr;
@@ -320,6 +326,14 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   CU(c, cudaEventRecord(c->ev[5], c->st));
   c->ev_valid[2] = true;
   CU_LAST(c, "neighbour list rebuild");
+  {  // rebuild steps already synchronise once to size the list; read the stopwatch here
+    float ms = 0.f;
+    CU(c, cudaEventSynchronize(c->ev[5]));
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) {
+      c->build_ms_acc += ms;
+      c->build_n++;
+    }
+  }
   c->stats.rebuilds++;
   c->list_valid = true;
   return B200COORD_OK;
@@ -365,6 +379,7 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     if (c->cfg.nranks > 1) CU(c, cudaMemsetAsync(c->d_out.p, 0, sizeof(double) * 3 * (size_t)c->n, c->st));
     CU(c, c->d_partials.reserve((size_t)kPartialStride * ((pe - pb) / 256 + 2)));
     CU(c, cudaEventRecord(c->ev[2], c->st));
+    CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
     nblocks = launch_sweep_pairs(d_pos, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
                                  c->n_a, pb, pe, c->dpbc, c->dsw, c->d_out.p, c->d_partials.p, c->d_u64.p + 1, c->st);
     CU(c, cudaEventRecord(c->ev[3], c->st));
@@ -392,12 +407,15 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     CU(c, c->d_partials.reserve((size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 2)));
     a.partials = c->d_partials.p;
     CU(c, cudaEventRecord(c->ev[2], c->st));
+    CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
     nblocks = (c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? launch_sweep_list(a, c->dpbc, c->dsw, c->st)
                                                         : launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
     CU(c, cudaEventRecord(c->ev[3], c->st));
     weight = c->two_groups ? 1.0 : 0.5;
     c->stats.kernel_launches += 1 + (c->two_groups ? 2 : 1);
   }
+  CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing) + 1], c->st));
+  c->sweep_n++;
   c->ev_valid[1] = true;
   if (nblocks < 0) return fail(c, B200COORD_ERR_UNSUPPORTED, "switching function type has no GPU kernel");
   CU_LAST(c, "pair sweep launch");
@@ -541,6 +559,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   c->row_chunk = (c->n + (unsigned)c->cfg.nranks - 1) / (unsigned)c->cfg.nranks;
   c->row_begin = std::min(c->n, c->row_chunk * (unsigned)c->cfg.rank);
   c->row_end = std::min(c->n, c->row_begin + c->row_chunk);
+  c->slot_begin = c->row_begin;  // same equal-chunk partition, applied to slots instead of sorted rows
+  c->slot_count = c->row_end - c->row_begin;
 
 #define CREATE_CU(expr)                                                                        \
   do {                                                                                         \
@@ -565,10 +585,11 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
     CREATE_CU(cudaGetDevice(&c->device));
   }
   CREATE_CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  for (int i = 0; i < 8; ++i) CREATE_CU(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 10; ++i) CREATE_CU(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2 * b200coord_ctx::kRing; ++i) CREATE_CU(cudaEventCreate(&c->sweep_ev[i]));
   const size_t n = c->n;
   const size_t padded_rows = (size_t)c->row_chunk * (size_t)c->cfg.nranks;
-  CREATE_CU(c->d_pos.reserve(3 * n));
+  CREATE_CU(c->d_pos.reserve(3 * std::max(n, padded_rows)));
   CREATE_CU(c->d_out.reserve(3 * n + 10));
   CREATE_CU(c->d_sderiv.reserve(3 * padded_rows));
   CREATE_CU(c->d_small.reserve(32));
@@ -606,8 +627,10 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release();
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_u64) cudaFreeHost(c->h_u64);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 10; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2 * b200coord_ctx::kRing; ++i)
+    if (c->sweep_ev[i]) cudaEventDestroy(c->sweep_ev[i]);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -689,6 +712,84 @@ int b200coord_calculate_device(b200coord_ctx* c, const double* d_pos, double* d_
   return B200COORD_OK;
 }
 
+int b200coord_enqueue_device(b200coord_ctx* c, const double* d_pos, double* d_out) {
+  if (!c || !d_pos || !d_out) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  int rc = run_device(c, d_pos);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
+  return B200COORD_OK;
+}
+
+int b200coord_stream_mark(b200coord_ctx* c, int which) {
+  if (!c || which < 0 || which > 1) return fail(c, B200COORD_ERR_INVALID, "bad stopwatch mark");
+  CU(c, cudaSetDevice(c->device));
+  if (which == 0) {
+    c->sweep_n = 0;
+    c->build_ms_acc = 0.f;
+    c->build_n = 0;
+  }
+  CU(c, cudaEventRecord(c->ev[8 + which], c->st));
+  return B200COORD_OK;
+}
+
+int b200coord_stream_elapsed_ms(b200coord_ctx* c, float* ms) {
+  if (!c || !ms) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventSynchronize(c->ev[9]));
+  CU(c, cudaEventElapsedTime(ms, c->ev[8], c->ev[9]));
+  refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_my_slice(const b200coord_ctx* c, unsigned* slot_begin, unsigned* slot_count) {
+  if (!c || !slot_begin || !slot_count) return B200COORD_ERR_INVALID;
+  *slot_begin = c->slot_begin;
+  *slot_count = c->slot_count;
+  return B200COORD_OK;
+}
+
+int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, double* value, double* deriv_slice,
+                                    double* virial) {
+  if (!c || !pos_slice || !value || !deriv_slice || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (c->cfg.nranks > 1 && !c->comm) return fail(c, B200COORD_ERR_STATE, "b200coord_comm_init has not been called");
+  CU(c, cudaSetDevice(c->device));
+  const size_t off = 3 * (size_t)c->slot_begin, cnt = 3 * (size_t)c->slot_count;
+  CU(c, cudaEventRecord(c->ev[0], c->st));
+  if (cnt) CU(c, cudaMemcpyAsync(c->d_pos.p + off, pos_slice, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaEventRecord(c->ev[1], c->st));
+  if (c->comm) {  // positions of all ranks over NVLink (in place: every rank's slice sits at rank*chunk)
+    NcclApi& api = nccl_api();
+    ncclResult_t r = api.AllGather(c->d_pos.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_pos.p, (size_t)3 * c->row_chunk,
+                                   ncclDouble, c->comm, c->st);
+    if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
+  }
+  int rc = run_device(c, c->d_pos.p);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[6], c->st));
+  if (cnt) CU(c, cudaMemcpyAsync(deriv_slice, c->d_out.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(c->h_small, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaEventRecord(c->ev[7], c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->ev_valid[0] = c->ev_valid[3] = true;
+  for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
+  *value = c->h_small[9];
+  refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return B200COORD_ERR_INVALID;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return fail(nullptr, B200COORD_ERR_CUDA, "cudaSetDevice failed");
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail(nullptr, B200COORD_ERR_CUDA, "no CUDA device");
+  const double t = measure_dfma_tflops(nullptr, sms, 5);
+  if (t <= 0.0) return fail(nullptr, B200COORD_ERR_CUDA, "DFMA microbenchmark failed");
+  *tflops = t;
+  return B200COORD_OK;
+}
+
 int b200coord_get_stats(const b200coord_ctx* cc, b200coord_stats* out) {
   if (!cc || !out) return B200COORD_ERR_INVALID;
   b200coord_ctx* c = const_cast<b200coord_ctx*>(cc);
@@ -697,6 +798,21 @@ int b200coord_get_stats(const b200coord_ctx* cc, b200coord_stats* out) {
   if (c->ev_valid[1] && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->stats.last_sweep_ms = ms;
   if (c->ev_valid[2] && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->stats.last_build_ms = ms;
   if (c->ev_valid[3] && cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->stats.last_d2h_ms = ms;
+  {
+    const unsigned m = std::min<unsigned>(c->sweep_n, b200coord_ctx::kRing);
+    float acc = 0.f;
+    unsigned got = 0;
+    for (unsigned i = 0; i < m; ++i)
+      if (cudaEventElapsedTime(&ms, c->sweep_ev[2 * i], c->sweep_ev[2 * i + 1]) == cudaSuccess) {
+        acc += ms;
+        ++got;
+      }
+    c->stats.sweep_ms_sum = acc;
+    c->stats.sweep_count = got;
+    c->stats.build_ms_sum = c->build_ms_acc;
+    c->stats.build_count = c->build_n;
+    cudaGetLastError();
+  }
   *out = c->stats;
   return B200COORD_OK;
 }

@@ -78,4 +78,7 @@ void launch_finalize(const double* partials, int nblocks, double weight, double*
 // out[3*slot+c] = sderiv[3*k+c] for all sorted rows k in [0,n)
 void launch_unsort_derivs(const double* sderiv, const SPos* spos, unsigned n, double* out, cudaStream_t st);
 
+// ---- util
+double measure_dfma_tflops(cudaStream_t st, int sm_count, int reps);
+
 }  // namespace b200
