@@ -121,6 +121,10 @@ struct b200coord_ctx {
   DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch
   DevBuf<SPos> d_spos;
   DevBuf<uint8_t> d_active;
+  DevBuf<float4> d_lpos;
+  DevPbc dbox;           // the box itself (type/ortho flags irrelevant): lattice vectors for image shifts
+  bool f32_search = false;
+  double band_rel = 0.0;
   unsigned long long nbr_total = 0;
   int sweep_blocks = 0;
 
@@ -215,25 +219,54 @@ int setup_grid(b200coord_ctx* c, const double* d_pos) {
     g.stencil_pbc = use_bbox ? 0 : 1;
   }
   g.bbox = use_bbox ? 1 : 0;
+  g.radius = 1;
+  c->f32_search = false;
   unsigned nc[3];
+  double extent_max = 0.0;
+  HostPbc bb;
   if (use_bbox) {
     launch_bbox(d_pos, c->n, c->d_small.p + 16, c->d_u64.p + 2, c->st);
     c->stats.kernel_launches += 2;
     CU(c, cudaMemcpyAsync(c->h_small + 10, c->d_small.p + 16, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
-    double box[9] = {0};
-    for (int k = 0; k < 3; ++k) {
-      const double mn = c->h_small[10 + k], mx = c->h_small[13 + k];
-      box[4 * k] = (cut < std::sqrt(1.79769313486231570e308)) ? cut * (1 + std::ceil((mx - mn) / cut)) : (mx - mn + 1);
-      g.origin[k] = (mn + mx) / 2;
+  }
+  // NLIST only: our own search grid may use half-width cells with a 5x5x5 stencil (1.7x fewer candidates)
+  // when every periodic direction still has >= 5 of them; NLISTCELLS must keep the reference's grid.
+  for (int refine = (cells_mode ? 1 : 2); refine >= 1; --refine) {
+    const double w = cut / refine;
+    if (use_bbox) {
+      double box[9] = {0};
+      for (int k = 0; k < 3; ++k) {
+        const double mn = c->h_small[10 + k], mx = c->h_small[13 + k];
+        box[4 * k] = (w < std::sqrt(1.79769313486231570e308)) ? w * (1 + std::ceil((mx - mn) / w)) : (mx - mn + 1);
+        g.origin[k] = (mn + mx) / 2;
+        extent_max = std::max(extent_max, box[4 * k]);
+      }
+      setup_pbc(box, bb);
+      cell_grid(bb.inv_box, w, nc);
+      set_grid_from_box(g, bb.inv_box, nc);
+    } else {
+      cell_grid(c->hpbc.inv_box, w, nc);
+      set_grid_from_box(g, c->hpbc.inv_box, nc);
+      for (int k = 0; k < 9; ++k) extent_max = std::max(extent_max, std::fabs(c->hpbc.box[k]));
     }
-    HostPbc bb;
-    setup_pbc(box, bb);
-    cell_grid(bb.inv_box, cut, nc);
-    set_grid_from_box(g, bb.inv_box, nc);
+    g.radius = refine;
+    const unsigned need = 2u * refine + 1u;
+    const bool wide = use_bbox || (nc[0] >= need && nc[1] >= need && nc[2] >= need);
+    if (refine == 1 || (wide && (unsigned long long)nc[0] * nc[1] * nc[2] <= 64ull * c->n + 4096ull)) {
+      // FP32 search needs the stencil image to be the minimum image of every pair within the cutoff
+      c->f32_search = !cells_mode && wide;
+      break;
+    }
+  }
+  // rounding band of the FP32 test, relative to cutoff^2: coordinates up to ~extent/2 carry 2^-24 relative error
+  c->band_rel = 64.0 * 5.96e-8 * (extent_max / c->cfg.nl_cutoff + 4.0);
+  if (c->band_rel > 0.05) c->f32_search = false;
+  if (use_bbox) {
+    std::memset(&c->dbox, 0, sizeof(c->dbox));
   } else {
-    cell_grid(c->hpbc.inv_box, cut, nc);
-    set_grid_from_box(g, c->hpbc.inv_box, nc);
+    std::memset(&c->dbox, 0, sizeof(c->dbox));
+    std::memcpy(c->dbox.box, c->hpbc.box, sizeof(c->dbox.box));
   }
   if ((unsigned long long)nc[0] * nc[1] * nc[2] > 400000000ull)
     return fail(c, B200COORD_ERR_INVALID, "cell grid too large for the given NL_CUTOFF and box");
@@ -311,16 +344,29 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     CU(c, c->d_rowstart.reserve(rows + 1));
     CU(c, c->d_bsum.reserve(rows / 1024 + 2));
     const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
-    launch_nl_rows(false, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
-                   c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, nullptr, nullptr, c->st);
+    auto rows_pass = [&](bool fill) {
+      if (c->f32_search)
+        launch_nl_rows_f32(fill, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+                           c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
+                           fill ? c->d_rowstart.p : nullptr, fill ? c->d_nbr.p : nullptr, c->st);
+      else
+        launch_nl_rows(fill, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
+                       c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, fill ? c->d_rowstart.p : nullptr,
+                       fill ? c->d_nbr.p : nullptr, c->st);
+    };
+    if (c->f32_search) {
+      CU(c, c->d_lpos.reserve(c->n));
+      launch_make_local(c->d_spos.p, c->n, c->grid, c->dbox, c->d_lpos.p, c->st);
+      c->stats.kernel_launches += 1;
+    }
+    rows_pass(false);
     launch_scan_rows(c->d_rowcount.p, rows, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
     CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
     CU_LAST(c, "neighbour list count");
     c->nbr_total = c->h_u64[0];
     CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 1));
-    launch_nl_rows(true, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
-                   c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p, c->d_nbr.p, c->st);
+    rows_pass(true);
     c->stats.kernel_launches += 6;
   }
   CU(c, cudaEventRecord(c->ev[5], c->st));
@@ -624,7 +670,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_lpos.release();
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_u64) cudaFreeHost(c->h_u64);
   for (int i = 0; i < 10; ++i)

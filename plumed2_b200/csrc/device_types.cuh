@@ -20,6 +20,7 @@ struct DevPbc {
 struct DevGrid {
   int bbox;            // 1: no box -> bounding box around the atoms, origin subtracted (LinkCells.cpp:49-73, :279-281)
   int stencil_pbc;     // 1: neighbour stencil wraps, 0: clamps (the usePbc argument of addRequiredCells, :195-239)
+  int radius;          // stencil half-width in cells: 1 = the reference's 27 cells; 2 = our finer NLIST search grid
   int n[3];            // cells per direction
   int ncell;           // n0*n1*n2
   double inv_box_t[9]; // transpose(invBox): fpos = inv_box_t * pos   (Pbc::realToScaled, Pbc.cpp:472-474)
@@ -45,6 +46,21 @@ struct __align__(32) SPos {
   uint32_t abs_index;  // absolute atom index (self-pair skip, CoordinationBase.cpp:183)
   uint32_t slot;       // index in the caller's position array
 };
+
+// one sorted record with a single 256-bit read-only load (LDG.E.256 on sm_100a): a gather costs one L1
+// wavefront per distinct 128-byte line instead of two
+__device__ __forceinline__ SPos load_spos(const SPos* __restrict__ p) {
+  double x, y, z, w;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+  SPos r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(w);
+  r.abs_index = (uint32_t)(bits & 0xffffffffull);
+  r.slot = (uint32_t)(bits >> 32);
+  return r;
+}
 
 // ------------------------------------------------------------------ exact (never contracted) arithmetic
 // Used wherever the result feeds a comparison that must reproduce the reference's x86-64 non-FMA build

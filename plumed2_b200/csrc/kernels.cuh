@@ -12,8 +12,14 @@ __device__ __forceinline__ void stencil_bounds(const DevGrid& g, const int c[3],
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int n = g.n[k];
-    int mn = c[k] + ((n < 2) ? 0 : -1);
-    int mx = c[k] + ((n < 3 && g.stencil_pbc) ? 1 : 2);
+    int mn, mx;
+    if (g.radius == 1) {
+      mn = c[k] + ((n < 2) ? 0 : -1);
+      mx = c[k] + ((n < 3 && g.stencil_pbc) ? 1 : 2);
+    } else {  // only built for grids with n >= 2*radius+1 cells per periodic direction
+      mn = c[k] - g.radius;
+      mx = c[k] + g.radius + 1;
+    }
     if (!g.stencil_pbc) {
       mn = max(mn, 0);
       mx = min(mx, n);
@@ -22,7 +28,45 @@ __device__ __forceinline__ void stencil_bounds(const DevGrid& g, const int c[3],
     hi[k] = mx;
   }
 }
-__device__ __forceinline__ int wrap_cell(int m, int n) { return (m < 0) ? n - 1 : m % n; }  // LINKC_PBC
+// LINKC_PBC (n<0 ? num-1 : n%num).  Stencil offsets never exceed one box length (|offset| <= radius <= n),
+// so the wrap is one conditional add/subtract -- an integer modulo here costs more than the distance test.
+__device__ __forceinline__ int wrap_cell(int m, int n) { return (m < 0) ? m + n : ((m >= n) ? m - n : m); }
+// how many box lengths the unwrapped cell index m lies outside [0,n): -1, 0 or +1 for our stencils
+__device__ __forceinline__ int wrap_count(int m, int n) { return (m < 0) ? -1 : ((m >= n) ? 1 : 0); }
+
+// Visit the stencil of cell c as CONTIGUOUS sorted ranges of the partner group: cells that are neighbours
+// along x are neighbours in memory (cell id = x + y*n0 + z*n0*n1, atoms sorted by cell), so a run of x cells
+// is one range [start, start+count).  A run is split only where it wraps around the box.  f(start, count).
+template <typename F>
+__device__ __forceinline__ void for_each_stencil_range(const DevGrid& g, const int c[3], unsigned group_off,
+                                                       const uint32_t* __restrict__ cstart,
+                                                       const uint32_t* __restrict__ ccount, F&& f) {
+  int lo[3], hi[3];
+  stencil_bounds(g, c, lo, hi);
+  for (int ny = lo[1]; ny < hi[1]; ++ny) {
+    const int yv = wrap_cell(ny, g.n[1]) * g.n[0];
+    for (int nz = lo[2]; nz < hi[2]; ++nz) {
+      const unsigned base = group_off + (unsigned)(yv + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
+      int x = lo[0];
+      while (x < hi[0]) {
+        const int xw = wrap_cell(x, g.n[0]);
+        const int run = min(hi[0] - x, g.n[0] - xw);
+        const unsigned first = base + (unsigned)xw, last = first + (unsigned)run - 1u;
+        const uint32_t s = cstart[first];
+        // (wx,wy,wz): the periodic image these cells are seen through (0 without wrapping)
+        f(s, cstart[last] + ccount[last] - s, wrap_count(x, g.n[0]), wrap_count(ny, g.n[1]), wrap_count(nz, g.n[2]));
+        x += run;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void cell_coords(const DevGrid& g, int cell, int c[3]) {  // LinkCells::findMyCell(idx) :294-304
+  c[2] = cell / (g.n[0] * g.n[1]);
+  const int rem = cell - c[2] * g.n[0] * g.n[1];
+  c[1] = rem / g.n[0];
+  c[0] = rem - c[1] * g.n[0];
+}
 
 // ---- build
 void launch_bbox(const double* pos, unsigned n, double* out6, unsigned long long* scratch6, cudaStream_t st);
@@ -36,6 +80,13 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
                     const DevGrid& g, const DevPbc& pbc, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                     unsigned row_end, uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr,
                     cudaStream_t st);
+// float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits)
+void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st);
+// FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
+void launch_nl_rows_f32(bool fill, const SPos* spos, const float4* lpos, const uint32_t* scell, const uint32_t* cstart,
+                        const uint32_t* ccount, const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2,
+                        double band_rel, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
+                        uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr, cudaStream_t st);
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st);
 void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long long* bsum, unsigned long long* row_start,
                       unsigned long long* grand_total, cudaStream_t st);

@@ -189,80 +189,218 @@ __global__ void k_identity_perm(unsigned n, uint32_t* __restrict__ perm, uint32_
 // exactly as NeighborList.cpp:246-259 does.  FILL=false counts, FILL=true writes the sorted indices j in
 // stencil order (deterministic).  Self-pairs (same absolute index) are not stored: the sweep would skip
 // them anyway (CoordinationBase.cpp:183); they are accounted for in the reported list size on the host.
-template <bool FILL>
-__global__ void k_nl_rows(const SPos* __restrict__ spos, const uint32_t* __restrict__ scell,
-                          const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
-                          double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
-                          uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
-                          uint32_t* __restrict__ nbr) {
+template <bool FILL, int PBC>
+__global__ void __launch_bounds__(256)
+    k_nl_rows(const SPos* __restrict__ spos, const uint32_t* __restrict__ scell, const uint32_t* __restrict__ cstart,
+              const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc, double cutoff2, unsigned n_a, int two_groups,
+              unsigned row_begin, unsigned row_end, uint32_t* __restrict__ row_count,
+              const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr) {
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   const unsigned k = row_begin + warp;
   if (k >= row_end) return;
-  const SPos pi = spos[k];
+  const SPos pi = load_spos(spos + k);
   const unsigned my_grp = (k < n_a) ? 0u : 1u;
   const unsigned other = two_groups ? (1u - my_grp) : 0u;
   int c[3];
-  {
-    const int cell = (int)scell[k];
-    c[2] = cell / (g.n[0] * g.n[1]);
-    const int rem = cell - c[2] * g.n[0] * g.n[1];
-    c[1] = rem / g.n[0];
-    c[0] = rem - c[1] * g.n[0];
-  }
-  int lo[3], hi[3];
-  stencil_bounds(g, c, lo, hi);
+  cell_coords(g, (int)scell[k], c);
+  // Pre-filter in fused arithmetic: a candidate whose r^2 is clearly outside / inside the cutoff needs no
+  // bit-exact evaluation (the two evaluations differ by < 1e-11 relative); only the thin band around the
+  // cutoff runs the reference's exact operation sequence, so the kept SET is still the reference's.
+  const double band = 1e-9 * cutoff2;
+  const double c2_hi = cutoff2 + band, c2_lo = cutoff2 - band;
   unsigned total = 0;
-  unsigned long long base = FILL ? row_start[k - row_begin] : 0ull;
-  for (int nx = lo[0]; nx < hi[0]; ++nx) {
-    const int xv = wrap_cell(nx, g.n[0]);
-    for (int ny = lo[1]; ny < hi[1]; ++ny) {
-      const int yv = wrap_cell(ny, g.n[1]) * g.n[0];
-      for (int nz = lo[2]; nz < hi[2]; ++nz) {
-        const int zv = wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1];
-        const unsigned cc = other * (unsigned)g.ncell + (unsigned)(xv + yv + zv);
-        const uint32_t s = cstart[cc], m = ccount[cc];
-        for (uint32_t e0 = 0; e0 < m; e0 += 32) {
-          const uint32_t e = e0 + lane;
-          bool keep = false;
-          uint32_t j = 0;
-          if (e < m) {
-            j = s + e;
-            const SPos pj = spos[j];
-            if (j != k && pj.abs_index != pi.abs_index) {
-              // the reference always evaluates the pair as (index0,index1) = (lower slot, higher slot)
-              // resp. (A atom, B atom): distance = pos[index1]-pos[index0]   (NeighborList.cpp:247-254)
-              const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
-              double d[3];
-              if (i_first) {
-                d[0] = xsub(pj.x, pi.x);
-                d[1] = xsub(pj.y, pi.y);
-                d[2] = xsub(pj.z, pi.z);
-              } else {
-                d[0] = xsub(pi.x, pj.x);
-                d[1] = xsub(pi.y, pj.y);
-                d[2] = xsub(pi.z, pj.z);
-              }
-              min_image_exact(pbc, d);
-              keep = norm2_exact(d[0], d[1], d[2]) <= cutoff2;
+  const unsigned long long base = FILL ? row_start[k - row_begin] : 0ull;
+  for_each_stencil_range(g, c, other * (unsigned)g.ncell, cstart, ccount, [&](uint32_t s, uint32_t m, int, int, int) {
+    for (uint32_t e0 = 0; e0 < m; e0 += 32) {
+      const uint32_t e = e0 + lane;
+      bool keep = false;
+      uint32_t j = 0;
+      if (e < m) {
+        j = s + e;
+        const SPos pj = load_spos(spos + j);
+        if (j != k && pj.abs_index != pi.abs_index) {
+          double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+          min_image_fast<PBC>(pbc, dx, dy, dz);
+          const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          if (r2 < c2_lo) {
+            keep = true;
+          } else if (r2 <= c2_hi) {
+            // the reference evaluates the pair as (index0,index1) = (A atom, B atom) resp. (lower, higher
+            // slot): distance = pos[index1]-pos[index0]   (NeighborList.cpp:247-254)
+            const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
+            double d[3];
+            if (i_first) {
+              d[0] = xsub(pj.x, pi.x);
+              d[1] = xsub(pj.y, pi.y);
+              d[2] = xsub(pj.z, pi.z);
+            } else {
+              d[0] = xsub(pi.x, pj.x);
+              d[1] = xsub(pi.y, pj.y);
+              d[2] = xsub(pi.z, pj.z);
             }
+            min_image_exact(pbc, d);
+            keep = norm2_exact(d[0], d[1], d[2]) <= cutoff2;
           }
-          const unsigned mask = __ballot_sync(0xffffffffu, keep);
-          if (FILL && keep) nbr[base + total + __popc(mask & ((1u << lane) - 1u))] = j;
-          total += __popc(mask);
         }
       }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (FILL && keep) nbr[base + total + __popc(mask & ((1u << lane) - 1u))] = j;
+      total += __popc(mask);
     }
-  }
+  });
   if (!FILL && lane == 0) row_count[k - row_begin] = total;
 }
 
-template __global__ void k_nl_rows<false>(const SPos*, const uint32_t*, const uint32_t*, const uint32_t*, DevGrid, DevPbc,
-                                          double, unsigned, int, unsigned, unsigned, uint32_t*, const unsigned long long*,
-                                          uint32_t*);
-template __global__ void k_nl_rows<true>(const SPos*, const uint32_t*, const uint32_t*, const uint32_t*, DevGrid, DevPbc,
-                                         double, unsigned, int, unsigned, unsigned, uint32_t*, const unsigned long long*,
-                                         uint32_t*);
+
+// ------------------------------------------------------------------------------------------------
+// FP32 candidate search.  The sorted atoms are copied once per rebuild into float4 records holding the
+// position WRAPPED into the cell the atom was binned to (relative to the box centre; bounding-box mode:
+// relative to the origin), so that a candidate in a stencil cell reached through the periodic boundary is
+// seen through the image (wx,wy,wz) of that cell: d = (l_j + wx*a + wy*b + wz*c) - l_i, no per-candidate
+// minimum-image arithmetic and all of it on the FP32 pipe.  For cells at least one cutoff wide (and >=
+// 2*radius+1 of them per periodic direction) that image is the minimum image of every pair within the
+// cutoff.  FP32 rounding moves r^2 by < band_rel*cutoff^2; candidates inside that band -- a ~1e-5 fraction
+// -- are decided by the reference's exact FP64 operation sequence on the original positions, so the kept
+// SET is the reference's bit for bit.
+__global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid g, DevPbc box, float4* __restrict__ lpos) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const SPos p = load_spos(spos + k);
+  double q[3] = {p.x, p.y, p.z};
+  double out[3];
+  if (g.bbox) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) out[a] = xsub(q[a], g.origin[a]);
+  } else {
+    double fw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // same arithmetic as cell_of(): the wrapped scaled coordinate the cell came from
+      double f = xadd(0.0, xmul(g.inv_box_t[3 * i], q[0]));
+      f = xadd(f, xmul(g.inv_box_t[3 * i + 1], q[1]));
+      f = xadd(f, xmul(g.inv_box_t[3 * i + 2], q[2]));
+      fw[i] = tools_pbc_exact(f);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) out[a] = fw[0] * box.box[a] + fw[1] * box.box[3 + a] + fw[2] * box.box[6 + a];
+  }
+  lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256, 4)
+    k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
+                  const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
+                  DevPbc box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
+                  unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
+                  uint32_t* __restrict__ nbr) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned k = row_begin + warp;
+  if (k >= row_end) return;
+  const float4 li = lpos[k];
+  const unsigned my_abs = __float_as_uint(li.w);
+  const unsigned my_grp = (k < n_a) ? 0u : 1u;
+  const unsigned group_off = (two_groups ? (1u - my_grp) : 0u) * (unsigned)g.ncell;
+  int c[3], lo[3], hi[3];
+  cell_coords(g, (int)scell[k], c);
+  stencil_bounds(g, c, lo, hi);
+  const float c2_hi = (float)(cutoff2 * (1.0 + band_rel)), c2_lo = (float)(cutoff2 * (1.0 - band_rel));
+
+  // ---- range table, one (y,z) stencil column per lane (<= 25): its x-run is one contiguous sorted range, or
+  // two when it wraps around the box.  All the dependent cstart/ccount loads of a row are in flight at once.
+  const int ny_n = hi[1] - lo[1], nz_n = hi[2] - lo[2];
+  const int ncol = ny_n * nz_n;
+  uint32_t sA = 0, mA = 0, sB = 0, mB = 0;
+  int wxA = 0, wxB = 0, wy = 0, wz = 0;
+  if ((int)lane < ncol) {
+    const int ny = lo[1] + (int)lane / nz_n, nz = lo[2] + (int)lane % nz_n;
+    wy = wrap_count(ny, g.n[1]);
+    wz = wrap_count(nz, g.n[2]);
+    const unsigned cbase = group_off + (unsigned)(wrap_cell(ny, g.n[1]) * g.n[0] + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
+    int x = lo[0];
+    {
+      const int xw = wrap_cell(x, g.n[0]);
+      const int run = min(hi[0] - x, g.n[0] - xw);
+      const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
+      sA = cstart[first];
+      mA = cstart[last] + ccount[last] - sA;
+      wxA = wrap_count(x, g.n[0]);
+      x += run;
+    }
+    if (x < hi[0]) {  // the part of the run on the other side of the periodic boundary
+      const int xw = wrap_cell(x, g.n[0]);
+      const int run = min(hi[0] - x, g.n[0] - xw);
+      const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
+      sB = cstart[first];
+      mB = cstart[last] + ccount[last] - sB;
+      wxB = wrap_count(x, g.n[0]);
+    }
+  }
+  const float ax = (float)box.box[0], ay = (float)box.box[1], az = (float)box.box[2];
+  const float bx = (float)box.box[3], by = (float)box.box[4], bz = (float)box.box[5];
+  const float cx = (float)box.box[6], cy = (float)box.box[7], cz = (float)box.box[8];
+
+  unsigned total = 0;
+  const unsigned long long base = FILL ? row_start[k - row_begin] : 0ull;
+
+  // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
+  auto exact_keep = [&](uint32_t j) -> bool {
+    const SPos pi = load_spos(spos + k);
+    const SPos pj = load_spos(spos + j);
+    const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
+    double d[3];
+    if (i_first) {
+      d[0] = xsub(pj.x, pi.x);
+      d[1] = xsub(pj.y, pi.y);
+      d[2] = xsub(pj.z, pi.z);
+    } else {
+      d[0] = xsub(pi.x, pj.x);
+      d[1] = xsub(pi.y, pj.y);
+      d[2] = xsub(pi.z, pj.z);
+    }
+    min_image_exact(pbc, d);
+    return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
+  };
+  auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz) -> bool {
+    const float dx = lj.x - ox, dy = lj.y - oy, dz = lj.z - oz;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    bool keep = (j != k) && (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
+    if (keep && r2 > c2_lo) keep = exact_keep(j);
+    return keep;
+  };
+  auto emit = [&](bool keep, uint32_t j) {
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (FILL && keep) nbr[base + total + __popc(mask & ((1u << lane) - 1u))] = j;
+    total += __popc(mask);
+  };
+  // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
+  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
+    const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
+    const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
+    const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
+    for (uint32_t e0 = 0; e0 < m; e0 += 64) {
+      const uint32_t e1 = e0 + lane, e2 = e1 + 32;
+      const bool in1 = e1 < m, in2 = e2 < m;
+      const uint32_t j1 = s + e1, j2 = s + e2;
+      const float4 l1 = __ldg(lpos + (in1 ? j1 : k));
+      const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
+      const bool k1 = in1 && test(j1, l1, ox, oy, oz);
+      const bool k2 = in2 && test(j2, l2, ox, oy, oz);
+      emit(k1, j1);
+      if (e0 + 32 < m) emit(k2, j2);
+    }
+  };
+  for (int col = 0; col < ncol; ++col) {
+    const uint32_t s1 = __shfl_sync(0xffffffffu, sA, col), m1 = __shfl_sync(0xffffffffu, mA, col);
+    const uint32_t s2 = __shfl_sync(0xffffffffu, sB, col), m2 = __shfl_sync(0xffffffffu, mB, col);
+    const int w1 = __shfl_sync(0xffffffffu, wxA, col), w2 = __shfl_sync(0xffffffffu, wxB, col);
+    const int wyy = __shfl_sync(0xffffffffu, wy, col), wzz = __shfl_sync(0xffffffffu, wz, col);
+    if (m1) scan_range(s1, m1, w1, wyy, wzz);
+    if (m2) scan_range(s2, m2, w2, wyy, wzz);
+  }
+  if (!FILL && lane == 0) row_count[k - row_begin] = total;
+}
 
 // PAIR style with NLIST: pair k=(k, k+nA) is kept iff within the cutoff at build time (NeighborList.cpp:246-259)
 __global__ void k_pair_mask(const double* __restrict__ pos, unsigned n_a, DevPbc pbc, double cutoff2,
@@ -372,13 +510,39 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
                     cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
-  const unsigned blocks = (rows * 32u + 255u) / 256u;
+  const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
+#define B200_NL_LAUNCH(F, P)                                                                                         \
+  k_nl_rows<F, P><<<blocks, 256, 0, st>>>(spos, scell, cstart, ccount, g, pbc, cutoff2, n_a, two_groups, row_begin, \
+                                          row_end, row_count, row_start, nbr)
+  if (fill) {
+    if (pbc.type == 0) B200_NL_LAUNCH(true, 0);
+    else if (pbc.type == 1) B200_NL_LAUNCH(true, 1);
+    else B200_NL_LAUNCH(true, 2);
+  } else {
+    if (pbc.type == 0) B200_NL_LAUNCH(false, 0);
+    else if (pbc.type == 1) B200_NL_LAUNCH(false, 1);
+    else B200_NL_LAUNCH(false, 2);
+  }
+#undef B200_NL_LAUNCH
+}
+
+void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st) {
+  if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos);
+}
+
+void launch_nl_rows_f32(bool fill, const SPos* spos, const float4* lpos, const uint32_t* scell, const uint32_t* cstart,
+                        const uint32_t* ccount, const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2,
+                        double band_rel, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
+                        uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr, cudaStream_t st) {
+  const unsigned rows = row_end - row_begin;
+  if (!rows) return;
+  const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
   if (fill)
-    k_nl_rows<true><<<blocks, 256, 0, st>>>(spos, scell, cstart, ccount, g, pbc, cutoff2, n_a, two_groups, row_begin,
-                                            row_end, row_count, row_start, nbr);
+    k_nl_rows_f32<true><<<blocks, 256, 0, st>>>(spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a,
+                                                two_groups, row_begin, row_end, row_count, row_start, nbr);
   else
-    k_nl_rows<false><<<blocks, 256, 0, st>>>(spos, scell, cstart, ccount, g, pbc, cutoff2, n_a, two_groups, row_begin,
-                                             row_end, row_count, row_start, nbr);
+    k_nl_rows_f32<false><<<blocks, 256, 0, st>>>(spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a,
+                                                 two_groups, row_begin, row_end, row_count, row_start, nbr);
 }
 
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st) {

@@ -261,16 +261,23 @@ __global__ void __launch_bounds__(kSweepThreads)
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
   for (unsigned k = first + wid; k < last; k += kSweepWarps) {
-    const SPos pi = a.spos[k];
+    const SPos pi = load_spos(a.spos + k);
     const unsigned long long base = a.row_start[k - a.row_begin];
     const unsigned cnt = a.row_count[k - a.row_begin];
     const bool row_is_b = (k >= a.n_a);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const uint32_t* __restrict__ row = a.nbr + base;
-#pragma unroll 2
-    for (unsigned e = lane; e < cnt; e += 32) {
-      const uint32_t j = __ldg(row + e);
-      const SPos pj = a.spos[j];
+    // software pipeline: the neighbour index is fetched two iterations ahead and the 32-byte record one
+    // iteration ahead, so the dependent index -> record -> FP64 chain of one pair overlaps the arithmetic of
+    // the previous one (the kernel is otherwise bound by the latency of that chain, see profiles/)
+    unsigned e = lane;
+    uint32_t j_next = (e < cnt) ? __ldg(row + e) : 0u;
+    uint32_t j_next2 = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
+    SPos p_next = load_spos(a.spos + j_next);
+    for (; e < cnt; e += 32) {
+      const SPos pj = p_next;
+      p_next = load_spos(a.spos + j_next2);
+      j_next2 = (e + 64 < cnt) ? __ldg(row + e + 64) : 0u;
       const bool flip = a.two_groups ? row_is_b : (pi.slot > pj.slot);
       pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
     }
@@ -302,40 +309,24 @@ __global__ void __launch_bounds__(kSweepThreads)
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
   for (unsigned k = first + wid; k < last; k += kSweepWarps) {
-    const SPos pi = a.spos[k];
+    const SPos pi = load_spos(a.spos + k);
     const unsigned my_grp = (k < a.n_a) ? 0u : 1u;
     const unsigned other = a.two_groups ? (1u - my_grp) : 0u;
-    int c[3], lo[3], hi[3];
-    {
-      const int cell = (int)a.scell[k];
-      c[2] = cell / (g.n[0] * g.n[1]);
-      const int rem = cell - c[2] * g.n[0] * g.n[1];
-      c[1] = rem / g.n[0];
-      c[0] = rem - c[1] * g.n[0];
-    }
-    stencil_bounds(g, c, lo, hi);
+    int c[3];
+    cell_coords(g, (int)a.scell[k], c);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     unsigned cnt = 0;
-    for (int nx = lo[0]; nx < hi[0]; ++nx) {
-      const int xv = wrap_cell(nx, g.n[0]);
-      for (int ny = lo[1]; ny < hi[1]; ++ny) {
-        const int yv = wrap_cell(ny, g.n[1]) * g.n[0];
-        for (int nz = lo[2]; nz < hi[2]; ++nz) {
-          const int zv = wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1];
-          const unsigned cc = other * (unsigned)g.ncell + (unsigned)(xv + yv + zv);
-          const uint32_t s0 = a.cstart[cc], m = a.ccount[cc];
-          cnt += m;
+    for_each_stencil_range(g, c, other * (unsigned)g.ncell, a.cstart, a.ccount, [&](uint32_t s0, uint32_t m, int, int, int) {
+      cnt += m;
 #pragma unroll 2
-          for (uint32_t e = lane; e < m; e += 32) {
-            const uint32_t j = s0 + e;
-            const SPos pj = a.spos[j];
-            const bool valid = (j != k) && (!a.check_abs || pj.abs_index != pi.abs_index);
-            const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
-            if (valid) pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
-          }
-        }
+      for (uint32_t e = lane; e < m; e += 32) {
+        const uint32_t j = s0 + e;
+        const SPos pj = load_spos(a.spos + j);
+        const bool valid = (j != k) && (!a.check_abs || pj.abs_index != pi.abs_index);
+        const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
+        if (valid) pair_term<K, PBC, ACC>(pbc, sw, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
       }
-    }
+    });
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
@@ -386,17 +377,20 @@ __global__ void __launch_bounds__(kSweepThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// fixed-order sum of the block partials; virial = -weight * sum(df d(x)d), value = weight * sum(s)
-__global__ void k_finalize(const double* __restrict__ partials, int nblocks, double weight, double* __restrict__ tail) {
-  __shared__ double sm[8][kPartialStride];
-  const int comp = threadIdx.x & 7, grp = threadIdx.x >> 3;  // 64 threads: 8 groups x 8 components
+// fixed-order sum of the block partials; virial = -weight * sum(df d(x)d), value = weight * sum(s).
+// 1024 threads = 128 groups x 8 components; group g adds records g, g+128, ... and the 128 group sums are
+// added in index order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int nblocks, double weight,
+                                                   double* __restrict__ tail) {
+  __shared__ double sm[128][kPartialStride];
+  const int comp = threadIdx.x & 7, grp = threadIdx.x >> 3;
   double t = 0.0;
-  for (int b = grp; b < nblocks; b += 8) t += partials[(size_t)b * kPartialStride + comp];
+  for (int b = grp; b < nblocks; b += 128) t += partials[(size_t)b * kPartialStride + comp];
   sm[grp][comp] = t;
   __syncthreads();
   if (threadIdx.x < 7) {
     double r = 0.0;
-    for (int g2 = 0; g2 < 8; ++g2) r += sm[g2][threadIdx.x];
+    for (int g2 = 0; g2 < 128; ++g2) r += sm[g2][threadIdx.x];
     sm[0][threadIdx.x] = r * weight;
   }
   __syncthreads();
@@ -531,7 +525,7 @@ int launch_sweep_pairs(const double* pos, const uint32_t* abs_index, const uint8
 }
 
 void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail, cudaStream_t st) {
-  k_finalize<<<1, 64, 0, st>>>(partials, nblocks, weight, out_tail);
+  k_finalize<<<1, 1024, 0, st>>>(partials, nblocks, weight, out_tail);
 }
 
 void launch_unsort_derivs(const double* sderiv, const SPos* spos, unsigned n, double* out, cudaStream_t st) {
