@@ -329,7 +329,9 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        list_bytes = 2.0 * my_pairs * 4 + 32.0 * 2.0 * my_pairs + 24.0 * n  # list indices + 32 B gathers + derivatives
+        rows_mine = n / world
+        # algorithmic HBM bytes of one sweep: 4 B per list entry (2 per pair), the 32 B records once, 24 B of derivatives
+        list_bytes = 2.0 * my_pairs * 4 + 32.0 * n + 24.0 * rows_mine
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),

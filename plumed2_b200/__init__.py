@@ -7,6 +7,6 @@
 There is no CPU implementation in this package; the oracle lives in /oracle and is test infrastructure.
 """
 from . import capi  # noqa: F401
-from .coordination import Coordination, PlumedInputError, comm_unique_id, parse_atom_list  # noqa: F401
+from .coordination import Coordination, PlumedInputError, comm_unique_id, parse_atom_list, shard_range  # noqa: F401
 
-__all__ = ["capi", "Coordination", "PlumedInputError", "comm_unique_id", "parse_atom_list"]
+__all__ = ["capi", "Coordination", "PlumedInputError", "comm_unique_id", "parse_atom_list", "shard_range"]

@@ -268,6 +268,14 @@ class Coordination:
             pass
 
 
+def shard_range(n, rank, nranks):
+    """the equal-chunk partition the library uses for i-atom rows and for position slices:
+    chunk = ceil(n/nranks), rank r owns [r*chunk, min(n,(r+1)*chunk))  (cf. CoordinationBase.cpp:168-170)"""
+    chunk = (n + nranks - 1) // nranks
+    lo = min(n, chunk * rank)
+    return lo, min(n, lo + chunk) - lo
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(capi.UNIQUE_ID_BYTES)
     capi.check(capi.lib().b200coord_comm_unique_id(buf))

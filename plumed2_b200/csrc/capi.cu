@@ -164,6 +164,7 @@ void to_dev_switch(const b200coord_switch& s, DevSwitch& d) {
   d.nn = s.nn; d.mm = s.mm; d.preRes = s.preRes; d.preDfunc = s.preDfunc; d.preSecDev = s.preSecDev;
   d.nnf = s.nnf; d.mmf = s.mmf; d.preDfuncF = s.preDfuncF; d.preSecDevF = s.preSecDevF;
   d.a = s.a; d.b = s.b; d.c = s.c; d.d = s.d; d.beta = s.beta; d.lambda = s.lambda; d.ref = s.ref;
+  d.pre_df = 2.0 * s.invr0_2 * s.stretch;
   // rationalfixN evaluates y^(N/2-1): keep N/2 in nnf for the device (the host struct leaves the default there)
   switch (s.type) {
     case B200COORD_SW_RATIONALFIX12: d.nnf = 6; break;
@@ -174,6 +175,7 @@ void to_dev_switch(const b200coord_switch& s, DevSwitch& d) {
     case B200COORD_SW_RATIONALFIX2: d.nnf = 1; break;
     default: break;
   }
+  d.fix_df = -(double)d.nnf * d.pre_df;
 }
 
 void to_dev_pbc(const HostPbc& h, bool use_pbc, DevPbc& d) {

@@ -38,6 +38,9 @@ struct DevSwitch {
   int a, b;
   double c, d;
   double beta, lambda, ref;
+  // derived on the host (to_dev_switch): constant factors of the r^2 fast paths
+  double pre_df;   // 2*invr0_2*stretch
+  double fix_df;   // -(N/2)*pre_df for rationalfixN
 };
 
 // sorted atom record: position + slot bookkeeping in one 32-byte sector
@@ -125,6 +128,11 @@ __device__ __forceinline__ void min_image_exact(const DevPbc& pbc, double d[3]) 
       d[2] = best[2];
     }
   }
+}
+
+// conditional negation on the integer pipe (a DADD/DMUL would spend an FP64 issue slot on a sign flip)
+__device__ __forceinline__ double flip_sign(double x, unsigned sign_mask /*0 or 0x80000000*/) {
+  return __hiloint2double(__double2hiint(x) ^ (int)sign_mask, __double2loint(x));
 }
 
 // ------------------------------------------------------------------ fast arithmetic for the sweep

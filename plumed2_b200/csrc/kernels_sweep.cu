@@ -89,17 +89,17 @@ __device__ __forceinline__ void eval_switch(const DevSwitch& p, double r2, doubl
       if (K == K_FIX6) {
         const double t = y * y;
         res = fast_rcp(fma(t, y, 1.0));
-        d = -3.0 * t * res * res;
+        df = (t * res) * (res * p.fix_df);
       } else if (K == K_FIXN) {
         const double t = ipow_dev(y, p.nnf - 1);
         res = fast_rcp(fma(t, y, 1.0));
-        d = -(double)p.nnf * t * res * res;
+        df = (t * res) * (res * p.fix_df);
       } else {
         res = p.preRes;
         d = p.preDfuncF;
         rational_generic(p.type == 9, y, p.preSecDevF, p.nnf, p.mmf, res, d);
+        df = d * p.pre_df;
       }
-      df = d * (2.0 * p.invr0_2) * p.stretch;
       s = fma(res, p.stretch, p.shift);
     }
   } else if (K == K_FASTGAUSS) {  // fastgaussianSwitch::calculateSqr :414-431
@@ -182,17 +182,13 @@ struct LaneAcc {
 template <int K, int PBC, bool ACC>
 __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw, double xi, double yi, double zi,
                                           const SPos& pj, bool flip, double& fx, double& fy, double& fz, LaneAcc& acc) {
-  double dx = pj.x - xi, dy = pj.y - yi, dz = pj.z - zi;
-  if (flip) {
-    dx = -dx;
-    dy = -dy;
-    dz = -dz;
-  }
+  const unsigned sgn = flip ? 0x80000000u : 0u;
+  double dx = flip_sign(pj.x - xi, sgn), dy = flip_sign(pj.y - yi, sgn), dz = flip_sign(pj.z - zi, sgn);
   min_image_fast<PBC>(pbc, dx, dy, dz);
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
   double s, df;
   eval_switch<K>(sw, r2, s, df);
-  const double dfs = flip ? -df : df;  // deriv[i0] -= df*d ; deriv[i1] += df*d
+  const double dfs = flip_sign(df, sgn);  // deriv[i0] -= df*d ; deriv[i1] += df*d
   fx = fma(-dfs, dx, fx);
   fy = fma(-dfs, dy, fy);
   fz = fma(-dfs, dz, fz);

@@ -1,0 +1,101 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): one process per GPU, i-atoms sharded by rank,
+positions all-gathered and derivative rows all-gathered + value/virial all-reduced over NCCL inside the library.
+Every rank must end up with the single-GPU result (= the oracle's) for its slice."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import oracle_from_line, rel_err, water_box
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+LINES = ["c: COORDINATION GROUPA=1-6000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+         "c: COORDINATION GROUPA=1-500 GROUPB=501-6000 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=1",
+         "c: COORDINATION GROUPA=1-3000 GROUPB=3001-6000 R_0=0.5 PAIR"]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import plumed2_b200 as P
+    from plumed2_b200 import capi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = capi.lib()
+        n = 6000
+        pos0, box = water_box(n, 100.0, seed=31, triclinic=True)
+        rng = np.random.default_rng(1)
+        for li, line in enumerate(LINES):
+            c = P.Coordination.from_input(line, device=rank, rank=rank, nranks=world)
+            ids = [P.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            c.comm_init(ids[0])
+            lo, cnt = P.shard_range(n, rank, world)
+            sb, sc = C.c_uint(), C.c_uint()
+            capi.check(L.b200coord_my_slice(c._ctx, C.byref(sb), C.byref(sc)))
+            assert (sb.value, sc.value) == (lo, cnt)
+            pos = pos0.copy()
+            for step in range(4):
+                pos = pos + 0.01 * rng.standard_normal(pos.shape)
+                c.prepare(step)
+                c._set_box(box)
+                sl = np.ascontiguousarray(pos[lo:lo + cnt])
+                der = np.zeros((cnt, 3))
+                vir = np.zeros(9)
+                val = C.c_double(0)
+                capi.check(L.b200coord_calculate_distributed(c._ctx, sl.ctypes.data_as(C.c_void_p), C.byref(val),
+                                                             der.ctypes.data_as(C.c_void_p),
+                                                             vir.ctypes.data_as(C.POINTER(C.c_double))), c._ctx)
+                np.savez(os.path.join(out_dir, "r%d_l%d_s%d.npz" % (rank, li, step)), value=val.value, deriv=der,
+                         virial=vir.reshape(3, 3), lo=lo, cnt=cnt, pos=pos)
+            c.close()
+            dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_distributed_step_matches_oracle(tmp_path):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    _, box = water_box(6000, 100.0, seed=31, triclinic=True)
+    for li, line in enumerate(LINES):
+        list_pos = None
+        stride = 3 if "NL_STRIDE=3" in line else 1
+        for step in range(4):
+            parts = [np.load(tmp_path / ("r%d_l%d_s%d.npz" % (r, li, step))) for r in range(world)]
+            pos = parts[0]["pos"]
+            if step % stride == 0 or list_pos is None:
+                list_pos = pos.copy()
+            ref = oracle_from_line(line, pos, box, list_positions=list_pos)
+            full = np.zeros((6000, 3))
+            for p in parts:
+                assert abs(float(p["value"]) - ref["value"]) <= 1e-10 * abs(ref["value"]), (line, step)
+                assert rel_err(p["virial"], ref["virial"]) <= 1e-10
+                full[int(p["lo"]):int(p["lo"]) + int(p["cnt"])] = p["deriv"]
+            assert rel_err(full, ref["deriv"]) <= 1e-10, (line, step)
