@@ -488,7 +488,7 @@ void refresh_stats(b200coord_ctx* c) {
   const unsigned long long n = c->n;
   switch (c->cfg.nl_mode) {
     case B200COORD_NL_CLASSIC:
-      c->stats.nl_size = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : c->nbr_total / 2 + (c->cfg.rank == 0 ? c->n_self_pairs : 0);
+      c->stats.nl_size = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : c->h_u64[1] / 2 + (c->cfg.rank == 0 ? c->n_self_pairs : 0);
       break;
     case B200COORD_NL_CELLS:
       c->stats.nl_size = c->two_groups ? c->h_u64[1] / 2 : (c->h_u64[1] - (c->row_end - c->row_begin)) / 2;

@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(256)
       total += __popc(mask);
     }
   });
+  if (FILL) {  // rows are padded to 4 entries (k_scan_*): make the padding a harmless index
+    const unsigned pad = ((total + 3u) & ~3u) - total;
+    if (lane < pad) nbr[base + total + lane] = 0u;
+  }
   if (!FILL && lane == 0) row_count[k - row_begin] = total;
 }
 
@@ -399,6 +403,10 @@ __global__ void __launch_bounds__(256, 4)
     if (m1) scan_range(s1, m1, w1, wyy, wzz);
     if (m2) scan_range(s2, m2, w2, wyy, wzz);
   }
+  if (FILL) {  // rows are padded to 4 entries (k_scan_*): make the padding a harmless index
+    const unsigned pad = ((total + 3u) & ~3u) - total;
+    if (lane < pad) nbr[base + total + lane] = 0u;
+  }
   if (!FILL && lane == 0) row_count[k - row_begin] = total;
 }
 
@@ -442,10 +450,14 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
   return excl;
 }
 
+// rows are padded to a multiple of 4 entries: every row then starts 16-byte aligned and the sweep can fetch
+// four neighbour indices with one 128-bit load
+__device__ __forceinline__ uint32_t padded4(uint32_t c) { return (c + 3u) & ~3u; }
+
 __global__ void k_scan_block_sums(const uint32_t* __restrict__ in, unsigned n, unsigned long long* __restrict__ bsum) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
   unsigned long long tot;
-  block_exclusive_scan(i < n ? in[i] : 0u, &tot);
+  block_exclusive_scan(i < n ? padded4(in[i]) : 0u, &tot);
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
@@ -469,7 +481,7 @@ __global__ void k_scan_sums(unsigned long long* __restrict__ bsum, unsigned nb, 
 __global__ void k_scan_apply(const uint32_t* __restrict__ in, unsigned n, const unsigned long long* __restrict__ bsum,
                              unsigned long long* __restrict__ out) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
-  const unsigned long long ex = block_exclusive_scan(i < n ? in[i] : 0u, nullptr);
+  const unsigned long long ex = block_exclusive_scan(i < n ? padded4(in[i]) : 0u, nullptr);
   if (i < n) out[i] = bsum[blockIdx.x] + ex;
 }
 
