@@ -125,6 +125,9 @@ struct b200coord_ctx {
   DevPbc dbox;           // the box itself (type/ortho flags irrelevant): lattice vectors for image shifts
   bool f32_search = false;
   double band_rel = 0.0;
+  unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
+  DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
+  unsigned* h_capinfo = nullptr;
   unsigned long long nbr_total = 0;
   int sweep_blocks = 0;
 
@@ -346,30 +349,59 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     CU(c, c->d_rowstart.reserve(rows + 1));
     CU(c, c->d_bsum.reserve(rows / 1024 + 2));
     const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
-    auto rows_pass = [&](bool fill) {
-      if (c->f32_search)
-        launch_nl_rows_f32(fill, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
-                           c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
-                           fill ? c->d_rowstart.p : nullptr, fill ? c->d_nbr.p : nullptr, c->st);
-      else
-        launch_nl_rows(fill, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
-                       c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, fill ? c->d_rowstart.p : nullptr,
-                       fill ? c->d_nbr.p : nullptr, c->st);
+    auto two_pass = [&]() -> int {
+      auto rows_pass = [&](bool fill) {
+        if (c->f32_search)
+          launch_nl_rows_f32(fill ? 1 : 0, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid,
+                             c->dpbc, c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end,
+                             c->d_rowcount.p, c->d_rowstart.p, fill ? c->d_nbr.p : nullptr, 0u, c->d_capinfo.p, c->st);
+        else
+          launch_nl_rows(fill, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
+                         c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, fill ? c->d_rowstart.p : nullptr,
+                         fill ? c->d_nbr.p : nullptr, c->st);
+      };
+      rows_pass(false);
+      launch_scan_rows(c->d_rowcount.p, rows, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
+      CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+      CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+      CU(c, cudaStreamSynchronize(c->st));
+      CU_LAST(c, "neighbour list count");
+      c->nbr_total = c->h_u64[0];
+      CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 4));
+      rows_pass(true);
+      c->stats.kernel_launches += 5;
+      return B200COORD_OK;
     };
     if (c->f32_search) {
       CU(c, c->d_lpos.reserve(c->n));
       launch_make_local(c->d_spos.p, c->n, c->grid, c->dbox, c->d_lpos.p, c->st);
       c->stats.kernel_launches += 1;
     }
-    rows_pass(false);
-    launch_scan_rows(c->d_rowcount.p, rows, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
-    CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
-    CU(c, cudaStreamSynchronize(c->st));
-    CU_LAST(c, "neighbour list count");
-    c->nbr_total = c->h_u64[0];
-    CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 1));
-    rows_pass(true);
-    c->stats.kernel_launches += 6;
+    CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 2 * sizeof(unsigned), c->st));
+    bool done = false;
+    if (c->f32_search && c->row_cap > 0) {
+      // single pass into fixed-capacity rows (capacity = 1.2 x the longest row of the previous rebuild);
+      // an overflow is detected on the device and answered with the exact two-pass build
+      c->nbr_total = (unsigned long long)rows * c->row_cap;
+      CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 4));
+      launch_nl_rows_f32(2, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, c->dbox,
+                         cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
+                         c->d_rowstart.p, c->d_nbr.p, c->row_cap, c->d_capinfo.p, c->st);
+      CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+      CU(c, cudaStreamSynchronize(c->st));
+      CU_LAST(c, "neighbour list single-pass build");
+      c->stats.kernel_launches += 2;
+      done = (c->h_capinfo[1] == 0);
+      if (!done) CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 2 * sizeof(unsigned), c->st));
+    }
+    if (!done) {
+      int rc2 = two_pass();
+      if (rc2) return rc2;
+    }
+    if (c->f32_search) {
+      const unsigned mx = c->h_capinfo[0];
+      c->row_cap = ((mx + mx / 5 + 16u) + 3u) & ~3u;
+    }
   }
   CU(c, cudaEventRecord(c->ev[5], c->st));
   c->ev_valid[2] = true;
@@ -654,6 +686,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   CREATE_CU(cudaMemsetAsync(c->d_sderiv.p, 0, sizeof(double) * 3 * padded_rows, c->st));
   CREATE_CU(cudaHostAlloc((void**)&c->h_small, 32 * sizeof(double), cudaHostAllocDefault));
   CREATE_CU(cudaHostAlloc((void**)&c->h_u64, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CREATE_CU(cudaHostAlloc((void**)&c->h_capinfo, 4 * sizeof(unsigned), cudaHostAllocDefault));
+  CREATE_CU(c->d_capinfo.reserve(4));
   c->h_u64[0] = c->h_u64[1] = 0;
   CREATE_CU(cudaMemcpyAsync(c->d_abs.p, c->abs_host.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
   CREATE_CU(cudaStreamSynchronize(c->st));
@@ -672,7 +706,8 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_lpos.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_lpos.release(); c->d_capinfo.release();
+  if (c->h_capinfo) cudaFreeHost(c->h_capinfo);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_u64) cudaFreeHost(c->h_u64);
   for (int i = 0; i < 10; ++i)

@@ -83,10 +83,11 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 // float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits)
 void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
-void launch_nl_rows_f32(bool fill, const SPos* spos, const float4* lpos, const uint32_t* scell, const uint32_t* cstart,
-                        const uint32_t* ccount, const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2,
-                        double band_rel, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
-                        uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr, cudaStream_t st);
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+                        const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount, const DevGrid& g,
+                        const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups,
+                        unsigned row_begin, unsigned row_end, uint32_t* row_count, unsigned long long* row_start,
+                        uint32_t* nbr, unsigned row_cap, unsigned* cap_info, cudaStream_t st);
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st);
 void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long long* bsum, unsigned long long* row_start,
                       unsigned long long* grand_total, cudaStream_t st);

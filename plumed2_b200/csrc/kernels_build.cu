@@ -291,13 +291,13 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
   lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
 }
 
-template <bool FILL>
+template <bool FILL, bool CAPPED>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
                   DevPbc box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                   unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
-                  uint32_t* __restrict__ nbr) {
+                  uint32_t* __restrict__ nbr, unsigned row_cap, unsigned* __restrict__ cap_info /*[0] max count, [1] overflow*/) {
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   const unsigned k = row_begin + warp;
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256, 4)
   const float cx = (float)box.box[6], cy = (float)box.box[7], cz = (float)box.box[8];
 
   unsigned total = 0;
-  const unsigned long long base = FILL ? row_start[k - row_begin] : 0ull;
+  // CAPPED: single-pass build into fixed-capacity rows (capacity learnt from the previous rebuild)
+  const unsigned long long base = CAPPED ? (unsigned long long)(k - row_begin) * row_cap : (FILL ? row_start[k - row_begin] : 0ull);
 
   // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
   auto exact_keep = [&](uint32_t j) -> bool {
@@ -375,7 +376,10 @@ __global__ void __launch_bounds__(256, 4)
   };
   auto emit = [&](bool keep, uint32_t j) {
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (FILL && keep) nbr[base + total + __popc(mask & ((1u << lane) - 1u))] = j;
+    if (FILL && keep) {
+      const unsigned at = total + __popc(mask & ((1u << lane) - 1u));
+      if (!CAPPED || at < row_cap) nbr[base + at] = j;
+    }
     total += __popc(mask);
   };
   // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
@@ -405,9 +409,23 @@ __global__ void __launch_bounds__(256, 4)
   }
   if (FILL) {  // rows are padded to 4 entries (k_scan_*): make the padding a harmless index
     const unsigned pad = ((total + 3u) & ~3u) - total;
-    if (lane < pad) nbr[base + total + lane] = 0u;
+    if (lane < pad && (!CAPPED || total + lane < row_cap)) nbr[base + total + lane] = 0u;
   }
-  if (!FILL && lane == 0) row_count[k - row_begin] = total;
+  if (CAPPED) {
+    if (lane == 0) {
+      row_count[k - row_begin] = min(total, row_cap);
+      if (total > cap_info[0]) atomicMax(&cap_info[0], total);
+      if (total > row_cap) atomicExch(&cap_info[1], 1u);
+    }
+  } else if (!FILL && lane == 0) {
+    row_count[k - row_begin] = total;
+    if (total > cap_info[0]) atomicMax(&cap_info[0], total);
+  }
+}
+
+__global__ void k_regular_offsets(unsigned rows, unsigned row_cap, unsigned long long* __restrict__ row_start) {
+  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) row_start[r] = (unsigned long long)r * row_cap;
 }
 
 // PAIR style with NLIST: pair k=(k, k+nA) is kept iff within the cutoff at build time (NeighborList.cpp:246-259)
@@ -542,19 +560,25 @@ void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const Dev
   if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos);
 }
 
-void launch_nl_rows_f32(bool fill, const SPos* spos, const float4* lpos, const uint32_t* scell, const uint32_t* cstart,
-                        const uint32_t* ccount, const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2,
-                        double band_rel, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
-                        uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr, cudaStream_t st) {
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+                        const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount, const DevGrid& g,
+                        const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups,
+                        unsigned row_begin, unsigned row_end, uint32_t* row_count, unsigned long long* row_start,
+                        uint32_t* nbr, unsigned row_cap, unsigned* cap_info, cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
-  if (fill)
-    k_nl_rows_f32<true><<<blocks, 256, 0, st>>>(spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a,
-                                                two_groups, row_begin, row_end, row_count, row_start, nbr);
-  else
-    k_nl_rows_f32<false><<<blocks, 256, 0, st>>>(spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a,
-                                                 two_groups, row_begin, row_end, row_count, row_start, nbr);
+#define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a, two_groups, row_begin, row_end, \
+                      row_count, row_start, nbr, row_cap, cap_info
+  if (mode == 0) {
+    k_nl_rows_f32<false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  } else if (mode == 1) {
+    k_nl_rows_f32<true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  } else {
+    k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
+    k_nl_rows_f32<true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  }
+#undef B200_F32_ARGS
 }
 
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st) {
