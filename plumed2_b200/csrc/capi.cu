@@ -134,6 +134,11 @@ struct b200coord_ctx {
   double* h_small = nullptr;  // pinned: [0..9] tail, [10..15] bbox
   unsigned long long* h_u64 = nullptr;  // pinned: [0] grand total, [1] evals
 
+  // opt-in (B200COORD_PIN_HOST=1): page-lock the caller's position/derivative arrays so that the per-step
+  // copies are direct DMA instead of staged pageable copies
+  bool pin_host = false;
+  struct Pinned { const void* p = nullptr; size_t bytes = 0; } pinned[2];
+
   ncclComm_t comm = nullptr;
   b200coord_stats stats;
   std::string err;
@@ -515,6 +520,20 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
   return B200COORD_OK;
 }
 
+void maybe_pin(b200coord_ctx* c, int which, const void* p, size_t bytes) {
+  if (!c->pin_host || !p || !bytes) return;
+  b200coord_ctx::Pinned& e = c->pinned[which];
+  if (e.p == p && e.bytes == bytes) return;
+  if (e.p) cudaHostUnregister(const_cast<void*>(e.p));
+  e.p = nullptr;
+  e.bytes = 0;
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    e.p = p;
+    e.bytes = bytes;
+  }
+  cudaGetLastError();  // a failed registration just leaves the copy pageable
+}
+
 void refresh_stats(b200coord_ctx* c) {
   c->stats.pair_evals = c->h_u64[1];
   const unsigned long long n = c->n;
@@ -694,6 +713,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
 #undef CREATE_CU
   std::memset(&c->hpbc, 0, sizeof(c->hpbc));
   to_dev_pbc(c->hpbc, false, c->dpbc);
+  if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
   *out = c;
   return B200COORD_OK;
 }
@@ -702,6 +722,9 @@ void b200coord_destroy(b200coord_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
+  for (auto& e : c->pinned)
+    if (e.p) cudaHostUnregister(const_cast<void*>(e.p));
+  cudaGetLastError();
   if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
@@ -767,6 +790,8 @@ int b200coord_calculate(b200coord_ctx* c, const double* pos, double* value, doub
   if (!c || !pos || !value || !deriv || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
   CU(c, cudaSetDevice(c->device));
   const size_t n3 = 3 * (size_t)c->n;
+  maybe_pin(c, 0, pos, sizeof(double) * n3);
+  maybe_pin(c, 1, deriv, sizeof(double) * n3);
   CU(c, cudaEventRecord(c->ev[0], c->st));
   CU(c, cudaMemcpyAsync(c->d_pos.p, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st));
   CU(c, cudaEventRecord(c->ev[1], c->st));

@@ -11,8 +11,11 @@
 #include "core/ActionRegister.h"
 #include "core/Colvar.h"
 #include "tools/Communicator.h"
+#include "tools/OpenMP.h"
 #include "tools/Pbc.h"
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -26,6 +29,10 @@ class CoordinationB200 : public Colvar {
   bool serial = false;
   bool combineWithMpi = false;
   std::vector<double> derivBuffer;
+  // B200COORD_PLUGIN_TIMERS=1: seconds spent in the C-ABI call vs in handing the result to PLUMED's Value
+  bool timers = false;
+  double tEngine = 0.0, tStore = 0.0;
+  unsigned long nCalls = 0;
   void check(int rc, const char* what);
 
 public:
@@ -167,6 +174,9 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
   }
   derivBuffer.resize(3 * all.size());
   requestAtoms(all);
+  if (const char* env = std::getenv("B200COORD_PLUGIN_TIMERS")) {
+    timers = std::atoi(env) != 0;
+  }
 
   char desc[512];
   b200coord_switch_describe(&sw, desc, sizeof(desc));
@@ -184,6 +194,10 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
 }
 
 CoordinationB200::~CoordinationB200() {
+  if (timers && nCalls) {
+    std::fprintf(stderr, "B200COORD plugin timers: %lu calls, engine %.3f ms/call, store-to-Value %.3f ms/call\n", nCalls,
+                 1e3 * tEngine / nCalls, 1e3 * tStore / nCalls);
+  }
   b200coord_destroy(ctx);
 }
 
@@ -209,14 +223,29 @@ void CoordinationB200::calculate() {
   double value = 0.0;
   double virial[9];
   const double* pos = n ? &getPositions()[0][0] : nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   check(b200coord_calculate(ctx, pos, &value, derivBuffer.data(), virial), "calculate");
   if (combineWithMpi) {
     comm.Sum(value);
     comm.Sum(derivBuffer);
     comm.Sum(&virial[0], 9);
   }
-  for (unsigned i = 0; i < n; ++i) {
-    setAtomsDerivatives(i, Vector(derivBuffer[3 * i], derivBuffer[3 * i + 1], derivBuffer[3 * i + 2]));
+  const auto t1 = std::chrono::steady_clock::now();
+  // Value::data was cleared by clearDerivatives() just before calculate() (PlumedMain.cpp:1312-1318), so
+  // setting equals the reference's adding; distinct indices -> safe to spread over PLUMED's OpenMP threads
+  Value* v = getPntrToValue();
+  const double* d = derivBuffer.data();
+  const long n3 = 3L * static_cast<long>(n);
+  const unsigned nt = OpenMP::getNumThreads();
+  #pragma omp parallel for num_threads(nt) schedule(static) if (n3 > 30000)
+  for (long i = 0; i < n3; ++i) {
+    v->setDerivative(static_cast<unsigned>(i), d[i]);
+  }
+  if (timers) {
+    const auto t2 = std::chrono::steady_clock::now();
+    tEngine += std::chrono::duration<double>(t1 - t0).count();
+    tStore += std::chrono::duration<double>(t2 - t1).count();
+    nCalls++;
   }
   setValue(value);
   setBoxDerivatives(Tensor(virial[0], virial[1], virial[2], virial[3], virial[4], virial[5], virial[6], virial[7], virial[8]));
