@@ -165,7 +165,7 @@ def workload_config(args, world):
     return {"workload": "BASELINE configs[1] at headline size: COORDINATION single group, %d atoms (%d per GPU), "
                         "orthorhombic PBC, SWITCH={%s} NLIST NL_CUTOFF=%g NL_STRIDE=%d, 100 atoms/nm^3"
                         % (n, args.natoms_per_gpu, SWITCH, NL_CUTOFF, NL_STRIDE),
-            "natoms": n, "natoms_per_gpu": args.natoms_per_gpu, "parallelism": "i-atom shards x%d" % world,
+            "natoms": n, "natoms_per_gpu": args.natoms_per_gpu, "parallelism": "i-atom shards x%d%s" % (world, "" if world == 1 else (", NCCL all-gather" if args.no_peer else ", in-kernel NVLink peer stores")),
             "pair_count": "pairs within NL_CUTOFF at the last rebuild (NLIST size); both arms",
             "cache": "per-step inputs (neighbour list %.1f GB + positions) exceed the 126 MB L2" %
                      (n / world * 419 * 4 / 1e9)}
@@ -220,6 +220,10 @@ def run_b200(args):
         ids = [P.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         c.comm_init(ids[0])
+        if not args.no_peer:  # fused sweep + exchange: derivative rows go to the peers from inside the sweep kernel
+            handles = [None] * world
+            dist.all_gather_object(handles, c.peer_export())
+            c.peer_attach(handles)
     c._set_box(box)
     ctx = c._ctx
     sb, sc = C.c_uint(), C.c_uint()
@@ -376,6 +380,7 @@ def main():
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--ref-sample-atoms", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="combine with NCCL all-gather instead of in-kernel peer stores")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -171,6 +171,15 @@ int b200coord_nl_pairs(b200coord_ctx* ctx, unsigned* pairs, unsigned long long c
 int b200coord_comm_unique_id(char id[B200COORD_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */
 int b200coord_comm_init(b200coord_ctx* ctx, const char id[B200COORD_UNIQUE_ID_BYTES]); /* every rank */
 
+/* Fused sweep + exchange over NVLink peer memory (optional, after b200coord_comm_init): every rank exports IPC
+ * handles of its derivative-row buffers, the host gathers the handles of all ranks (rank order) and hands them
+ * back; from then on the sweep kernel stores each finished derivative row straight into every peer's buffer
+ * (posted NVLink writes that overlap the arithmetic) and the NCCL all-gather of the rows disappears -- only the
+ * 10-double all-reduce of virial/value remains, which also orders the ranks. */
+#define B200COORD_PEER_HANDLE_BYTES 128
+int b200coord_peer_export(b200coord_ctx* ctx, char handle[B200COORD_PEER_HANDLE_BYTES]);
+int b200coord_peer_attach(b200coord_ctx* ctx, const char* all_handles /* nranks * B200COORD_PEER_HANDLE_BYTES */);
+
 /* ---- pinned host memory for callers that want full-speed copies */
 int b200coord_host_alloc(size_t bytes, void** ptr);
 int b200coord_host_free(void* ptr);

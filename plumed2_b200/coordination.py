@@ -256,6 +256,17 @@ class Coordination:
     def comm_init(self, unique_id):
         capi.check(self._L.b200coord_comm_init(self._ctx, bytes(unique_id)), self._ctx)
 
+    def peer_export(self):
+        """IPC handles of this rank's derivative-row buffers (fused sweep + exchange over NVLink)"""
+        buf = C.create_string_buffer(capi.PEER_HANDLE_BYTES)
+        capi.check(self._L.b200coord_peer_export(self._ctx, buf), self._ctx)
+        return buf.raw
+
+    def peer_attach(self, handles_of_all_ranks):
+        """handles_of_all_ranks: list of the peer_export() blobs in rank order"""
+        blob = b"".join(bytes(h) for h in handles_of_all_ranks)
+        capi.check(self._L.b200coord_peer_attach(self._ctx, blob), self._ctx)
+
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._L.b200coord_destroy(self._ctx)

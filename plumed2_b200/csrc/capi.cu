@@ -140,6 +140,11 @@ struct b200coord_ctx {
   struct Pinned { const void* p = nullptr; size_t bytes = 0; } pinned[2];
 
   ncclComm_t comm = nullptr;
+  // fused exchange over peer memory: two row buffers (step parity) per rank, mapped into every process
+  bool peer_mode = false;
+  DevBuf<double> d_sderiv_b;          // second parity buffer (d_sderiv is the first)
+  double* peer_rows[2][8] = {{nullptr}};  // [parity][rank], own entries point at the local buffers
+  unsigned parity = 0;
   b200coord_stats stats;
   std::string err;
 };
@@ -289,6 +294,7 @@ int ensure_cell_arrays(b200coord_ctx* c) {
   CU(c, c->d_ccount.reserve(m));
   CU(c, c->d_cstart.reserve(m));
   CU(c, c->d_cursor.reserve(m));
+  CU(c, c->d_bsum.reserve(std::max<size_t>(m, (size_t)c->n) / 1024 + 4));
   return B200COORD_OK;
 }
 
@@ -344,7 +350,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   rc = ensure_cell_arrays(c);
   if (rc) return rc;
   launch_sort(d_pos, c->n, c->n_a, c->two_groups ? 2 : 1, c->grid, c->d_cell_of_slot.p, c->d_ccount.p, c->d_cstart.p,
-              c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->st);
+              c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->d_bsum.p, c->st);
   c->stats.kernel_launches += 4;
   c->sorted_valid = true;
   if (mode == B200COORD_NL_CLASSIC) {
@@ -434,6 +440,11 @@ int combine_ranks(b200coord_ctx* c) {
   }
   // every rank owns complete derivatives for its rows: all-gather the row slices (sorted order), and
   // all-reduce the 10 scalars (virial + value) -- the Comm::Sum of CoordinationBase.cpp:218-224
+  if (c->peer_mode) {  // rows were already stored into every peer by the sweep kernel; this all-reduce also orders the ranks
+    r = api.AllReduce(c->d_out.p + (size_t)3 * c->n, c->d_out.p + (size_t)3 * c->n, 10, ncclDouble, ncclSum, c->comm, c->st);
+    if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
+    return B200COORD_OK;
+  }
   api.GroupStart();
   r = api.AllGather(c->d_sderiv.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_sderiv.p, (size_t)3 * c->row_chunk,
                     ncclDouble, c->comm, c->st);
@@ -487,7 +498,15 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     a.cstart = c->d_cstart.p;
     a.ccount = c->d_ccount.p;
     a.grid = c->grid;
-    a.sderiv = c->d_sderiv.p;
+    double* rows_now = c->d_sderiv.p;
+    if (c->peer_mode) {
+      c->parity ^= 1u;
+      rows_now = c->peer_rows[c->parity][c->cfg.rank];
+      a.npeers = 0;
+      for (int r = 0; r < c->cfg.nranks; ++r)
+        if (r != c->cfg.rank) a.peers[a.npeers++] = c->peer_rows[c->parity][r];
+    }
+    a.sderiv = rows_now;
     a.evals = c->d_u64.p + 1;
     CU(c, c->d_partials.reserve((size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 2)));
     a.partials = c->d_partials.p;
@@ -512,7 +531,8 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     if (rc) return rc;
   }
   if (c->cfg.style != B200COORD_STYLE_PAIR) {
-    launch_unsort_derivs(c->d_sderiv.p, c->d_spos.p, c->n, c->d_out.p, c->st);
+    launch_unsort_derivs(c->peer_mode ? c->peer_rows[c->parity][c->cfg.rank] : c->d_sderiv.p, c->d_spos.p, c->n, c->d_out.p,
+                         c->st);
     c->stats.kernel_launches += 1;
   }
   CU(c, cudaMemcpyAsync(c->h_u64 + 1, c->d_u64.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
@@ -730,6 +750,11 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
   c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_lpos.release(); c->d_capinfo.release();
+  if (c->peer_mode)
+    for (int par = 0; par < 2; ++par)
+      for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
+        if (r != c->cfg.rank && c->peer_rows[par][r]) cudaIpcCloseMemHandle(c->peer_rows[par][r]);
+  c->d_sderiv_b.release();
   if (c->h_capinfo) cudaFreeHost(c->h_capinfo);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_u64) cudaFreeHost(c->h_u64);
@@ -1042,6 +1067,47 @@ int b200coord_comm_init(b200coord_ctx* c, const char id[B200COORD_UNIQUE_ID_BYTE
     c->comm = nullptr;
     return fail(c, B200COORD_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
   }
+  return B200COORD_OK;
+}
+
+int b200coord_peer_export(b200coord_ctx* c, char handle[B200COORD_PEER_HANDLE_BYTES]) {
+  if (!c || !handle) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == B200COORD_PEER_HANDLE_BYTES, "IPC handle size");
+  if (c->cfg.style == B200COORD_STYLE_PAIR) return fail(c, B200COORD_ERR_INVALID, "PAIR style has no row exchange");
+  CU(c, cudaSetDevice(c->device));
+  const size_t padded = (size_t)3 * c->row_chunk * (size_t)c->cfg.nranks;
+  CU(c, c->d_sderiv_b.reserve(padded));
+  CU(c, cudaMemsetAsync(c->d_sderiv_b.p, 0, sizeof(double) * padded, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  cudaIpcMemHandle_t h[2];
+  CU(c, cudaIpcGetMemHandle(&h[0], c->d_sderiv.p));
+  CU(c, cudaIpcGetMemHandle(&h[1], c->d_sderiv_b.p));
+  std::memcpy(handle, h, sizeof(h));
+  return B200COORD_OK;
+}
+
+int b200coord_peer_attach(b200coord_ctx* c, const char* all) {
+  if (!c || !all) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->comm) return fail(c, B200COORD_ERR_STATE, "b200coord_comm_init must come first");
+  if (c->cfg.nranks > 8) return fail(c, B200COORD_ERR_INVALID, "peer exchange supports up to 8 ranks");
+  if (!c->d_sderiv_b.p) return fail(c, B200COORD_ERR_STATE, "b200coord_peer_export must come first");
+  CU(c, cudaSetDevice(c->device));
+  for (int r = 0; r < c->cfg.nranks; ++r) {
+    if (r == c->cfg.rank) {
+      c->peer_rows[0][r] = c->d_sderiv.p;
+      c->peer_rows[1][r] = c->d_sderiv_b.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, all + (size_t)r * B200COORD_PEER_HANDLE_BYTES, sizeof(h));
+    for (int par = 0; par < 2; ++par) {
+      void* ptr = nullptr;
+      CU(c, cudaIpcOpenMemHandle(&ptr, h[par], cudaIpcMemLazyEnablePeerAccess));
+      c->peer_rows[par][r] = static_cast<double*>(ptr);
+    }
+  }
+  c->peer_mode = true;
+  c->parity = 0;
   return B200COORD_OK;
 }
 

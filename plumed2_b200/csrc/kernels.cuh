@@ -72,7 +72,7 @@ __device__ __forceinline__ void cell_coords(const DevGrid& g, int cell, int c[3]
 void launch_bbox(const double* pos, unsigned n, double* out6, unsigned long long* scratch6, cudaStream_t st);
 void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const DevGrid& g, uint32_t* cell_of_slot,
                  uint32_t* ccount, uint32_t* cstart, uint32_t* cursor, uint32_t* tmp, uint32_t* perm, uint32_t* scell,
-                 cudaStream_t st);
+                 unsigned long long* scan_tmp /* >= ngroups*ncell/1024+2 entries, or null */, cudaStream_t st);
 void launch_identity(unsigned n, uint32_t* perm, uint32_t* scell, cudaStream_t st);
 void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, SPos* spos,
                    cudaStream_t st);
@@ -114,6 +114,9 @@ struct SweepArgs {
   double* sderiv;          // 3 doubles per sorted row (only rows of this rank are written)
   double* partials;        // kPartialStride doubles per block
   unsigned long long* evals;  // pair evaluations executed (both directions)
+  // fused exchange: the same row is also stored into the row buffers of the other ranks (NVLink peer memory)
+  int npeers;
+  double* peers[7];
 };
 
 // returns the number of blocks launched (= number of partial records), or -1 for an unsupported switch

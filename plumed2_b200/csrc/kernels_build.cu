@@ -472,10 +472,12 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 // four neighbour indices with one 128-bit load
 __device__ __forceinline__ uint32_t padded4(uint32_t c) { return (c + 3u) & ~3u; }
 
+template <bool PAD>
 __global__ void k_scan_block_sums(const uint32_t* __restrict__ in, unsigned n, unsigned long long* __restrict__ bsum) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
   unsigned long long tot;
-  block_exclusive_scan(i < n ? padded4(in[i]) : 0u, &tot);
+  const uint32_t v = i < n ? in[i] : 0u;
+  block_exclusive_scan(PAD ? padded4(v) : v, &tot);
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
@@ -493,14 +495,25 @@ __global__ void k_scan_sums(unsigned long long* __restrict__ bsum, unsigned nb, 
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *grand_total = carry;
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry;
 }
 
+// PAD: row offsets (u64, rows padded to 4 entries).  !PAD: cell starts (u32) + cleared placement cursors.
+template <bool PAD>
 __global__ void k_scan_apply(const uint32_t* __restrict__ in, unsigned n, const unsigned long long* __restrict__ bsum,
-                             unsigned long long* __restrict__ out) {
+                             unsigned long long* __restrict__ out64, uint32_t* __restrict__ out32,
+                             uint32_t* __restrict__ cursor) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
-  const unsigned long long ex = block_exclusive_scan(i < n ? padded4(in[i]) : 0u, nullptr);
-  if (i < n) out[i] = bsum[blockIdx.x] + ex;
+  const uint32_t v = i < n ? in[i] : 0u;
+  const unsigned long long ex = block_exclusive_scan(PAD ? padded4(v) : v, nullptr);
+  if (i < n) {
+    if (PAD) {
+      out64[i] = bsum[blockIdx.x] + ex;
+    } else {
+      out32[i] = (uint32_t)(bsum[blockIdx.x] + ex);
+      cursor[i] = 0u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,11 +528,18 @@ void launch_bbox(const double* pos, unsigned n, double* out6, unsigned long long
 
 void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const DevGrid& g, uint32_t* cell_of_slot,
                  uint32_t* ccount, uint32_t* cstart, uint32_t* cursor, uint32_t* tmp, uint32_t* perm, uint32_t* scell,
-                 cudaStream_t st) {
+                 unsigned long long* scan_tmp, cudaStream_t st) {
   const unsigned m = (unsigned)ngroups * (unsigned)g.ncell;
   cudaMemsetAsync(ccount, 0, sizeof(uint32_t) * m, st);
   k_bin_atoms<<<(n + 255) / 256, 256, 0, st>>>(pos, n, n_a, g, cell_of_slot, ccount);
-  k_scan_cells<<<1, 1024, 0, st>>>(ccount, cstart, cursor, m);
+  if (m <= 4096u || !scan_tmp) {
+    k_scan_cells<<<1, 1024, 0, st>>>(ccount, cstart, cursor, m);
+  } else {  // large grids: three-kernel scan instead of one serial block
+    const unsigned nb = (m + kScanBlock - 1) / kScanBlock;
+    k_scan_block_sums<false><<<nb, kScanBlock, 0, st>>>(ccount, m, scan_tmp);
+    k_scan_sums<<<1, kScanBlock, 0, st>>>(scan_tmp, nb, nullptr);
+    k_scan_apply<false><<<nb, kScanBlock, 0, st>>>(ccount, m, scan_tmp, nullptr, cstart, cursor);
+  }
   k_place_atoms<<<(n + 255) / 256, 256, 0, st>>>(n, n_a, g.ncell, cell_of_slot, cstart, cursor, tmp);
   const unsigned long long threads = (unsigned long long)m * 32ull;
   k_order_cells<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(m, g.ncell, cstart, ccount, tmp, perm, scell);
@@ -592,9 +612,9 @@ void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long lo
     return;
   }
   const unsigned nb = (rows + kScanBlock - 1) / kScanBlock;
-  k_scan_block_sums<<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum);
+  k_scan_block_sums<true><<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum);
   k_scan_sums<<<1, kScanBlock, 0, st>>>(bsum, nb, grand_total);
-  k_scan_apply<<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum, row_start);
+  k_scan_apply<true><<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum, row_start, nullptr, nullptr);
 }
 
 }  // namespace b200

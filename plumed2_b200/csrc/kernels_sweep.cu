@@ -211,6 +211,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 constexpr int kSweepThreads = 256;
+constexpr int kMaxRowsPerBlock = 64;
 constexpr int kSweepWarps = kSweepThreads / 32;
 
 // block epilogue: reduce the lane accumulators of all warps and store one partial record
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kSweepThreads)
   unsigned long long evals = 0;
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
+  __shared__ double s_rows[3 * kMaxRowsPerBlock];  // this block's finished rows, pushed to the peers in one piece
   for (unsigned k = first + wid; k < last; k += kSweepWarps) {
     const SPos pi = load_spos(a.spos + k);
     const unsigned long long base = a.row_start[k - a.row_begin];
@@ -284,7 +286,22 @@ __global__ void __launch_bounds__(kSweepThreads)
       a.sderiv[3 * (size_t)k] = fx;
       a.sderiv[3 * (size_t)k + 1] = fy;
       a.sderiv[3 * (size_t)k + 2] = fz;
+      if (a.npeers) {
+        s_rows[3 * (k - first)] = fx;
+        s_rows[3 * (k - first) + 1] = fy;
+        s_rows[3 * (k - first) + 2] = fz;
+      }
       evals += cnt;
+    }
+  }
+  if (a.npeers) {
+    // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
+    // them over NVLink with coalesced stores while other blocks keep computing
+    __syncthreads();
+    if ((int)wid < a.npeers && last > first) {
+      double* __restrict__ q = a.peers[wid] + 3 * (size_t)first;
+      const unsigned m = 3u * (last - first);
+      for (unsigned t = lane; t < m; t += 32) q[t] = s_rows[t];
     }
   }
   if (ACC)
@@ -304,6 +321,7 @@ __global__ void __launch_bounds__(kSweepThreads)
   const DevGrid& g = a.grid;
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
+  __shared__ double s_rows[3 * kMaxRowsPerBlock];  // this block's finished rows, pushed to the peers in one piece
   for (unsigned k = first + wid; k < last; k += kSweepWarps) {
     const SPos pi = load_spos(a.spos + k);
     const unsigned my_grp = (k < a.n_a) ? 0u : 1u;
@@ -330,7 +348,22 @@ __global__ void __launch_bounds__(kSweepThreads)
       a.sderiv[3 * (size_t)k] = fx;
       a.sderiv[3 * (size_t)k + 1] = fy;
       a.sderiv[3 * (size_t)k + 2] = fz;
+      if (a.npeers) {
+        s_rows[3 * (k - first)] = fx;
+        s_rows[3 * (k - first) + 1] = fy;
+        s_rows[3 * (k - first) + 2] = fz;
+      }
       evals += cnt;
+    }
+  }
+  if (a.npeers) {
+    // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
+    // them over NVLink with coalesced stores while other blocks keep computing
+    __syncthreads();
+    if ((int)wid < a.npeers && last > first) {
+      double* __restrict__ q = a.peers[wid] + 3 * (size_t)first;
+      const unsigned m = 3u * (last - first);
+      for (unsigned t = lane; t < m; t += 32) q[t] = s_rows[t];
     }
   }
   if (ACC)

@@ -34,7 +34,7 @@ LINES = ["c: COORDINATION GROUPA=1-6000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MA
          "c: COORDINATION GROUPA=1-3000 GROUPB=3001-6000 R_0=0.5 PAIR"]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, peer):
     import torch
     import torch.distributed as dist
     import plumed2_b200 as P
@@ -53,6 +53,10 @@ def _worker(rank, world, port, out_dir):
             ids = [P.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             c.comm_init(ids[0])
+            if peer and "PAIR" not in line:
+                handles = [None] * world
+                dist.all_gather_object(handles, c.peer_export())
+                c.peer_attach(handles)
             lo, cnt = P.shard_range(n, rank, world)
             sb, sc = C.c_uint(), C.c_uint()
             capi.check(L.b200coord_my_slice(c._ctx, C.byref(sb), C.byref(sc)))
@@ -77,12 +81,13 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_gpu_distributed_step_matches_oracle(tmp_path):
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl-allgather", "peer-stores"])
+def test_two_gpu_distributed_step_matches_oracle(tmp_path, peer):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), peer), nprocs=world, join=True)
     _, box = water_box(6000, 100.0, seed=31, triclinic=True)
     for li, line in enumerate(LINES):
         list_pos = None
