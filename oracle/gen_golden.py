@@ -114,6 +114,37 @@ def parse_kats():
         entry["values"] = vals
         coord[test] = entry
     kats["coordination_regtests"] = coord
+    # --- regtest/basic/rt20-switch-*: 2-atom COORDINATION along switchtraj.xyz, every analytic switch type,
+    #     with and without NOSTRETCH: COLVAR (6 decimals) and DUMPDERIVATIVES (%8.4f: 6 atom + 9 box derivatives)
+    frames = []
+    with open(os.path.join(REF, "regtest/trajectories/switchtraj.xyz")) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while i < len(lines) and lines[i].strip():
+        n = int(lines[i]); b = [float(x) for x in lines[i + 1].split()]
+        at = [[float(x) for x in lines[i + 2 + a].split()[1:4]] for a in range(n)]
+        frames.append({"box": b, "pos": at}); i += 2 + n
+    rt20 = {"frames": frames, "tests": {}}
+    base = os.path.join(REF, "regtest/basic")
+    for d in sorted(os.listdir(base)):
+        if not d.startswith("rt20-switch-") or d.endswith("lepton"):
+            continue
+        dat = open(os.path.join(base, d, "plumed.dat")).read()
+        lines_c = {}
+        for ln in dat.split("\n"):
+            m = re.match(r"\s*(c|cs):\s*(COORDINATION.*)", ln)
+            if m:
+                lines_c[m.group(1)] = m.group(1) + ": " + m.group(2).strip()
+        colvar = [[float(x) for x in l.split()] for l in open(os.path.join(base, d, "COLVAR.reference")) if not l.startswith("#")]
+        deriv = [[float(x) for x in l.split()] for l in open(os.path.join(base, d, "deriv.reference")) if not l.startswith("#")]
+        rt20["tests"][d] = {"lines": lines_c, "colvar": colvar, "deriv": deriv}
+    kats["rt20_switch"] = rt20
+    # --- regtest/tools/rt-make-lattice-reduction/output.reference
+    with open(os.path.join(REF, "regtest/tools/rt-make-lattice-reduction/output.reference")) as f:
+        L = f.read().split("\n")
+    k = L.index("testReduceFast")
+    kats["lattice_reduction"] = {"input": [1.0, 2.0, 3.0, 5.0, 4.0, 3.0, 10.0, 8.0, 2.0],
+                                 "reduceFast": [[float(x) for x in L[k + 1 + r].split()] for r in range(3)]}
     return kats
 
 

@@ -360,3 +360,22 @@ def test_one_million_atoms_properties():
         assert np.abs(g - d[i]).max() <= 1e-9 * scale
     for x in (c, c2, c3, c4):
         x.close()
+
+
+def test_rt20_switch_regtests_on_gpu():
+    """the reference's own rt20-switch-* fixtures (value + 15 derivatives per frame, 12 switch types x stretch on/off)"""
+    with open(os.path.join(GOLD, "ref_regtest_kats.json")) as f:
+        rt = json.load(f)["rt20_switch"]
+    frames = rt["frames"]
+    for name, test in rt["tests"].items():
+        col = np.array(test["colvar"])
+        der = np.array(test["deriv"]).reshape(len(frames), 15, 4)
+        for ci, lab in enumerate(("c", "cs")):
+            c = P.Coordination.from_input(test["lines"][lab])
+            for fi, fr in enumerate(frames):
+                c.prepare(fi)
+                c.calculate(np.array(fr["pos"]), np.diag(fr["box"]))
+                assert abs(c.value - col[fi, 1 + ci]) < 6e-7, (name, lab, fi, c.value)
+                got = np.concatenate([c.derivatives.ravel(), c.virial.ravel()])
+                assert np.abs(got - der[fi, :, 2 + ci]).max() < 5.1e-5, (name, lab, fi)
+            c.close()

@@ -254,3 +254,35 @@ def test_rank_split_sums_to_full(gold):
     # OpenMP path gives the same numbers to rounding
     v4, d4, w4, _ = O.coordination(nl, pbc, True, sw, pos, nthreads=4)
     assert abs(v4 - full[0]) < 1e-12 * abs(full[0])
+
+
+# ------------------------------------------------------------------ more of the reference's own fixtures
+def test_lattice_reduction_regtest(kats):
+    """regtest/tools/rt-make-lattice-reduction/output.reference (testReduceFast)"""
+    kat = kats["lattice_reduction"]
+    np.testing.assert_array_equal(O.lattice_reduce(kat["input"]), np.array(kat["reduceFast"]))
+
+
+def _rt20_expected(test, nframes):
+    """per frame: (c, cs) values and their 15 derivatives (6 atomic + 9 box) as printed by the reference"""
+    col = np.array(test["colvar"])
+    der = np.array(test["deriv"]).reshape(nframes, 15, 4)
+    return col[:, 1:3], der[:, :, 2:4]
+
+
+def test_rt20_switch_regtests(kats):
+    """regtest/basic/rt20-switch-*: 2-atom COORDINATION along switchtraj.xyz for every analytic switch,
+    stretched and NOSTRETCH: value (%f) and DUMPDERIVATIVES (%8.4f) incl. the virial"""
+    rt = kats["rt20_switch"]
+    frames = rt["frames"]
+    assert len(rt["tests"]) == 12
+    for name, test in rt["tests"].items():
+        vals, ders = _rt20_expected(test, len(frames))
+        for fi, fr in enumerate(frames):
+            pos = np.array(fr["pos"])
+            box = np.diag(fr["box"])
+            for ci, lab in enumerate(("c", "cs")):
+                r = oracle_from_line(test["lines"][lab], pos, box)
+                assert abs(r["value"] - vals[fi, ci]) < 6e-7, (name, lab, fi)
+                got = np.concatenate([r["deriv"].ravel(), r["virial"].ravel()])
+                assert np.abs(got - ders[fi, :, ci]).max() < 5.1e-5, (name, lab, fi)
