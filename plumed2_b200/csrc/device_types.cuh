@@ -21,6 +21,7 @@ struct DevGrid {
   int bbox;            // 1: no box -> bounding box around the atoms, origin subtracted (LinkCells.cpp:49-73, :279-281)
   int stencil_pbc;     // 1: neighbour stencil wraps, 0: clamps (the usePbc argument of addRequiredCells, :195-239)
   int radius;          // stencil half-width in cells: 1 = the reference's 27 cells; 2 = our finer NLIST search grid
+  int pencil;          // tile mode: cells along x per pencil (= per block of the tile sweep)
   int n[3];            // cells per direction
   int ncell;           // n0*n1*n2
   double inv_box_t[9]; // transpose(invBox): fpos = inv_box_t * pos   (Pbc::realToScaled, Pbc.cpp:472-474)
@@ -39,6 +40,9 @@ struct DevSwitch {
   double c, d;
   double beta, lambda, ref;
   // derived on the host (to_dev_switch): constant factors of the r^2 fast paths
+  double d0_2;       // d0^2
+  double band_dmax;  // |r^2 - dmax^2| below this -> exact re-evaluation (0 when there is no D_MAX)
+  double band_d0;    // same around d0^2 (negative when d0 == 0: never)
   double pre_df;   // 2*invr0_2*stretch
   double fix_df;   // -(N/2)*pre_df for rationalfixN
 };

@@ -8,7 +8,7 @@ namespace b200 {
 // ---- 27-cell stencil, LinkCells::addRequiredCells / min_cell / max_cell (LinkCells.cpp:183-239)
 // Per axis the unwrapped range is [lo,hi); ranges shrink for grids thinner than 3 cells so that a cell is
 // never visited twice, and clamp to [0,n) without PBC.
-__device__ __forceinline__ void stencil_bounds(const DevGrid& g, const int c[3], int lo[3], int hi[3]) {
+__host__ __device__ __forceinline__ void stencil_bounds(const DevGrid& g, const int c[3], int lo[3], int hi[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int n = g.n[k];
@@ -30,9 +30,9 @@ __device__ __forceinline__ void stencil_bounds(const DevGrid& g, const int c[3],
 }
 // LINKC_PBC (n<0 ? num-1 : n%num).  Stencil offsets never exceed one box length (|offset| <= radius <= n),
 // so the wrap is one conditional add/subtract -- an integer modulo here costs more than the distance test.
-__device__ __forceinline__ int wrap_cell(int m, int n) { return (m < 0) ? m + n : ((m >= n) ? m - n : m); }
+__host__ __device__ __forceinline__ int wrap_cell(int m, int n) { return (m < 0) ? m + n : ((m >= n) ? m - n : m); }
 // how many box lengths the unwrapped cell index m lies outside [0,n): -1, 0 or +1 for our stencils
-__device__ __forceinline__ int wrap_count(int m, int n) { return (m < 0) ? -1 : ((m >= n) ? 1 : 0); }
+__host__ __device__ __forceinline__ int wrap_count(int m, int n) { return (m < 0) ? -1 : ((m >= n) ? 1 : 0); }
 
 // Visit the stencil of cell c as CONTIGUOUS sorted ranges of the partner group: cells that are neighbours
 // along x are neighbours in memory (cell id = x + y*n0 + z*n0*n1, atoms sorted by cell), so a run of x cells
@@ -61,11 +61,66 @@ __device__ __forceinline__ void for_each_stencil_range(const DevGrid& g, const i
   }
 }
 
-__device__ __forceinline__ void cell_coords(const DevGrid& g, int cell, int c[3]) {  // LinkCells::findMyCell(idx) :294-304
+__host__ __device__ __forceinline__ void cell_coords(const DevGrid& g, int cell, int c[3]) {  // LinkCells::findMyCell(idx) :294-304
   c[2] = cell / (g.n[0] * g.n[1]);
   const int rem = cell - c[2] * g.n[0] * g.n[1];
   c[1] = rem / g.n[0];
   c[0] = rem - c[1] * g.n[0];
+}
+
+// ---- tiles (kernels_tile.cu): a block of the tile sweep owns a PENCIL of consecutive cells along x and stages
+// the partner atoms of the pencil's whole stencil in shared memory; list entries are 16-bit tile-local indices.
+// The tile layout is a pure function of (grid, cell ranges, pencil): the list builder and the sweep derive it
+// with the same code below, one stencil column (dy,dz) per lane.
+struct TileCol {
+  uint32_t gA, lA, gB, lB;  // global sorted start / length of the (<=2) contiguous parts of the column's x-run
+  int wA, wB;               // periodic image (-1,0,+1) of each part along x
+};
+__host__ __device__ __forceinline__ int pencil_cells(const DevGrid& g) { return g.pencil > 0 ? g.pencil : 1; }
+
+// x-run [xa,xb) (unwrapped cell indices) of the stencil column whose wrapped (y,z) base is cbase
+__host__ __device__ __forceinline__ void column_parts(const DevGrid& g, unsigned cbase, int xa, int xb,
+                                             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
+                                             TileCol& t) {
+  t.gA = t.lA = t.gB = t.lB = 0u;
+  t.wA = t.wB = 0;
+  int x = xa;
+  if (x < xb) {
+    const int xw = wrap_cell(x, g.n[0]);
+    const int run = min(xb - x, g.n[0] - xw);
+    const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
+    t.gA = cstart[first];
+    t.lA = cstart[last] + ccount[last] - t.gA;
+    t.wA = wrap_count(x, g.n[0]);
+    x += run;
+  }
+  if (x < xb) {
+    const int xw = wrap_cell(x, g.n[0]);
+    const int run = min(xb - x, g.n[0] - xw);
+    const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
+    t.gB = cstart[first];
+    t.lB = cstart[last] + ccount[last] - t.gB;
+    t.wB = wrap_count(x, g.n[0]);
+  }
+}
+// x bounds of the stencil of the cell range [c0,c1] (tile mode is only used on grids where this is valid)
+__host__ __device__ __forceinline__ void xrun_bounds(const DevGrid& g, int c0, int c1, int& xa, int& xb) {
+  xa = c0 - g.radius;
+  xb = c1 + g.radius + 1;
+  if (!g.stencil_pbc) {
+    xa = max(xa, 0);
+    xb = min(xb, g.n[0]);
+  }
+}
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, unsigned lane, uint32_t& total) {
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (unsigned)o) x += y;
+  }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
 }
 
 // ---- build
@@ -83,14 +138,16 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 // float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits)
 void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
-                        const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount, const DevGrid& g,
-                        const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups,
-                        unsigned row_begin, unsigned row_end, uint32_t* row_count, unsigned long long* row_start,
-                        uint32_t* nbr, unsigned row_cap, unsigned* cap_info, cudaStream_t st);
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool tile, const SPos* spos,
+                        const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
+                        const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
+                        unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
+                        unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
+                        unsigned* cap_info /*[0] max row, [1] overflow, [2] max tile*/, cudaStream_t st);
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st);
-void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long long* bsum, unsigned long long* row_start,
-                      unsigned long long* grand_total, cudaStream_t st);
+void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned padq /*3: 32-bit list, 7: 16-bit tile list*/,
+                      unsigned long long* bsum, unsigned long long* row_start, unsigned long long* grand_total,
+                      cudaStream_t st);
 
 // ---- sweep
 constexpr int kPartialStride = 8;  // value, vxx, vxy, vxz, vyy, vyz, vzz, (pad)
@@ -105,6 +162,7 @@ struct SweepArgs {
   const unsigned long long* row_start;
   const uint32_t* row_count;
   const uint32_t* nbr;
+  const uint16_t* nbr16;   // tile mode: tile-local indices, rows padded to 8 entries
   // implicit ranges (no NL / NLISTCELLS)
   const uint32_t* scell;
   const uint32_t* cstart;
@@ -114,11 +172,17 @@ struct SweepArgs {
   double* sderiv;          // 3 doubles per sorted row (only rows of this rank are written)
   double* partials;        // kPartialStride doubles per block
   unsigned long long* evals;  // pair evaluations executed (both directions)
+  // box and switch parameters in global memory, for the out-of-line row patch (sweep_math.cuh: row_fixup_*)
+  const DevPbc* pbc_g;
+  const DevSwitch* sw_g;
   // fused exchange: the same row is also stored into the row buffers of the other ranks (NVLink peer memory)
   int npeers;
   double* peers[7];
 };
 
+// tile sweep (16-bit tile-local list): returns the number of partial records, -1 unsupported switch,
+// -2 the tile does not fit in shared memory
+int launch_sweep_tile(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, unsigned tile_cap, cudaStream_t st);
 // returns the number of blocks launched (= number of partial records), or -1 for an unsupported switch
 int launch_sweep_list(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);

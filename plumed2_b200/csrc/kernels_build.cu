@@ -291,7 +291,7 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
   lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
 }
 
-template <bool FILL, bool CAPPED>
+template <bool FILL, bool CAPPED, bool TILE>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
@@ -341,9 +341,34 @@ __global__ void __launch_bounds__(256, 4)
       wxB = wrap_count(x, g.n[0]);
     }
   }
+  // TILE: entries are indices into the shared-memory tile of this row's pencil (see kernels.cuh "tiles"):
+  // the pencil's column has the same (y,z) as mine and an x-run that contains mine, so an entry is
+  // tile_off(column) + (offset of my range inside the pencil's range) + position in my range.
+  uint32_t lbA = 0, lbB = 0;
+  if (TILE) {
+    const int P = pencil_cells(g);
+    const int x0 = (c[0] / P) * P, x1 = min(x0 + P, g.n[0]) - 1;
+    TileCol pc;
+    pc.gA = pc.lA = pc.gB = pc.lB = 0u;
+    pc.wA = pc.wB = 0;
+    if ((int)lane < ncol) {
+      const int ny = lo[1] + (int)lane / nz_n, nz = lo[2] + (int)lane % nz_n;
+      const unsigned cbase = group_off + (unsigned)(wrap_cell(ny, g.n[1]) * g.n[0] + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
+      int xa, xb;
+      xrun_bounds(g, x0, x1, xa, xb);
+      column_parts(g, cbase, xa, xb, cstart, ccount, pc);
+    }
+    uint32_t tile_total;
+    const uint32_t off = warp_exclusive_scan(pc.lA + pc.lB, lane, tile_total);
+    // a part of my x-run lies in the part of the pencil's x-run that is seen through the same periodic image
+    lbA = off + ((wxA == pc.wA || pc.lB == 0u) ? (sA - pc.gA) : pc.lA + (sA - pc.gB));
+    lbB = off + ((wxB == pc.wA || pc.lB == 0u) ? (sB - pc.gA) : pc.lA + (sB - pc.gB));
+    if (lane == 0 && tile_total > cap_info[2]) atomicMax(&cap_info[2], tile_total);
+  }
   const float ax = (float)box.box[0], ay = (float)box.box[1], az = (float)box.box[2];
   const float bx = (float)box.box[3], by = (float)box.box[4], bz = (float)box.box[5];
   const float cx = (float)box.box[6], cy = (float)box.box[7], cz = (float)box.box[8];
+  uint16_t* __restrict__ nbr16 = reinterpret_cast<uint16_t*>(nbr);
 
   unsigned total = 0;
   // CAPPED: single-pass build into fixed-capacity rows (capacity learnt from the previous rebuild)
@@ -374,16 +399,19 @@ __global__ void __launch_bounds__(256, 4)
     if (keep && r2 > c2_lo) keep = exact_keep(j);
     return keep;
   };
-  auto emit = [&](bool keep, uint32_t j) {
+  auto emit = [&](bool keep, uint32_t j, uint32_t local) {
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (FILL && keep) {
       const unsigned at = total + __popc(mask & ((1u << lane) - 1u));
-      if (!CAPPED || at < row_cap) nbr[base + at] = j;
+      if (!CAPPED || at < row_cap) {
+        if (TILE) nbr16[base + at] = (uint16_t)local;
+        else nbr[base + at] = j;
+      }
     }
     total += __popc(mask);
   };
   // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
-  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
+  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz, uint32_t lb) {
     const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
     const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
     const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
@@ -395,8 +423,8 @@ __global__ void __launch_bounds__(256, 4)
       const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
       const bool k1 = in1 && test(j1, l1, ox, oy, oz);
       const bool k2 = in2 && test(j2, l2, ox, oy, oz);
-      emit(k1, j1);
-      if (e0 + 32 < m) emit(k2, j2);
+      emit(k1, j1, lb + e1);
+      if (e0 + 32 < m) emit(k2, j2, lb + e2);
     }
   };
   for (int col = 0; col < ncol; ++col) {
@@ -404,12 +432,17 @@ __global__ void __launch_bounds__(256, 4)
     const uint32_t s2 = __shfl_sync(0xffffffffu, sB, col), m2 = __shfl_sync(0xffffffffu, mB, col);
     const int w1 = __shfl_sync(0xffffffffu, wxA, col), w2 = __shfl_sync(0xffffffffu, wxB, col);
     const int wyy = __shfl_sync(0xffffffffu, wy, col), wzz = __shfl_sync(0xffffffffu, wz, col);
-    if (m1) scan_range(s1, m1, w1, wyy, wzz);
-    if (m2) scan_range(s2, m2, w2, wyy, wzz);
+    const uint32_t b1 = TILE ? __shfl_sync(0xffffffffu, lbA, col) : 0u, b2 = TILE ? __shfl_sync(0xffffffffu, lbB, col) : 0u;
+    if (m1) scan_range(s1, m1, w1, wyy, wzz, b1);
+    if (m2) scan_range(s2, m2, w2, wyy, wzz, b2);
   }
-  if (FILL) {  // rows are padded to 4 entries (k_scan_*): make the padding a harmless index
-    const unsigned pad = ((total + 3u) & ~3u) - total;
-    if (lane < pad && (!CAPPED || total + lane < row_cap)) nbr[base + total + lane] = 0u;
+  if (FILL) {  // rows are padded (4 x 32-bit or 8 x 16-bit entries = 16 bytes): make the padding a harmless index
+    const unsigned q = TILE ? 7u : 3u;
+    const unsigned pad = ((total + q) & ~q) - total;
+    if (lane < pad && (!CAPPED || total + lane < row_cap)) {
+      if (TILE) nbr16[base + total + lane] = 0;
+      else nbr[base + total + lane] = 0u;
+    }
   }
   if (CAPPED) {
     if (lane == 0) {
@@ -472,12 +505,13 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 // four neighbour indices with one 128-bit load
 __device__ __forceinline__ uint32_t padded4(uint32_t c) { return (c + 3u) & ~3u; }
 
-template <bool PAD>
-__global__ void k_scan_block_sums(const uint32_t* __restrict__ in, unsigned n, unsigned long long* __restrict__ bsum) {
+// padq: 0 = plain counts (cells); 3 / 7 = list rows padded to 4 x 32-bit / 8 x 16-bit entries (16-byte rows)
+__global__ void k_scan_block_sums(const uint32_t* __restrict__ in, unsigned n, unsigned padq,
+                                  unsigned long long* __restrict__ bsum) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
   unsigned long long tot;
   const uint32_t v = i < n ? in[i] : 0u;
-  block_exclusive_scan(PAD ? padded4(v) : v, &tot);
+  block_exclusive_scan((v + padq) & ~padq, &tot);
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
@@ -499,15 +533,15 @@ __global__ void k_scan_sums(unsigned long long* __restrict__ bsum, unsigned nb, 
 }
 
 // PAD: row offsets (u64, rows padded to 4 entries).  !PAD: cell starts (u32) + cleared placement cursors.
-template <bool PAD>
-__global__ void k_scan_apply(const uint32_t* __restrict__ in, unsigned n, const unsigned long long* __restrict__ bsum,
-                             unsigned long long* __restrict__ out64, uint32_t* __restrict__ out32,
-                             uint32_t* __restrict__ cursor) {
+template <bool ROWS>
+__global__ void k_scan_apply(const uint32_t* __restrict__ in, unsigned n, unsigned padq,
+                             const unsigned long long* __restrict__ bsum, unsigned long long* __restrict__ out64,
+                             uint32_t* __restrict__ out32, uint32_t* __restrict__ cursor) {
   const unsigned i = blockIdx.x * kScanBlock + threadIdx.x;
   const uint32_t v = i < n ? in[i] : 0u;
-  const unsigned long long ex = block_exclusive_scan(PAD ? padded4(v) : v, nullptr);
+  const unsigned long long ex = block_exclusive_scan((v + padq) & ~padq, nullptr);
   if (i < n) {
-    if (PAD) {
+    if (ROWS) {
       out64[i] = bsum[blockIdx.x] + ex;
     } else {
       out32[i] = (uint32_t)(bsum[blockIdx.x] + ex);
@@ -536,9 +570,9 @@ void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const
     k_scan_cells<<<1, 1024, 0, st>>>(ccount, cstart, cursor, m);
   } else {  // large grids: three-kernel scan instead of one serial block
     const unsigned nb = (m + kScanBlock - 1) / kScanBlock;
-    k_scan_block_sums<false><<<nb, kScanBlock, 0, st>>>(ccount, m, scan_tmp);
+    k_scan_block_sums<<<nb, kScanBlock, 0, st>>>(ccount, m, 0u, scan_tmp);
     k_scan_sums<<<1, kScanBlock, 0, st>>>(scan_tmp, nb, nullptr);
-    k_scan_apply<false><<<nb, kScanBlock, 0, st>>>(ccount, m, scan_tmp, nullptr, cstart, cursor);
+    k_scan_apply<false><<<nb, kScanBlock, 0, st>>>(ccount, m, 0u, scan_tmp, nullptr, cstart, cursor);
   }
   k_place_atoms<<<(n + 255) / 256, 256, 0, st>>>(n, n_a, g.ncell, cell_of_slot, cstart, cursor, tmp);
   const unsigned long long threads = (unsigned long long)m * 32ull;
@@ -580,23 +614,26 @@ void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const Dev
   if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos);
 }
 
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
-                        const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount, const DevGrid& g,
-                        const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups,
-                        unsigned row_begin, unsigned row_end, uint32_t* row_count, unsigned long long* row_start,
-                        uint32_t* nbr, unsigned row_cap, unsigned* cap_info, cudaStream_t st) {
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool tile, const SPos* spos,
+                        const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
+                        const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
+                        unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
+                        unsigned long long* row_start, uint32_t* nbr, unsigned row_cap, unsigned* cap_info,
+                        cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
 #define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info
-  if (mode == 0) {
-    k_nl_rows_f32<false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  } else if (mode == 1) {
-    k_nl_rows_f32<true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
+  if (tile) {
+    if (mode == 0) k_nl_rows_f32<false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else if (mode == 1) k_nl_rows_f32<true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
   } else {
-    k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-    k_nl_rows_f32<true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    if (mode == 0) k_nl_rows_f32<false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else if (mode == 1) k_nl_rows_f32<true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
   }
 #undef B200_F32_ARGS
 }
@@ -605,16 +642,16 @@ void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double
   if (n_a) k_pair_mask<<<(n_a + 255) / 256, 256, 0, st>>>(pos, n_a, pbc, cutoff2, active);
 }
 
-void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned long long* bsum, unsigned long long* row_start,
-                      unsigned long long* grand_total, cudaStream_t st) {
+void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned padq, unsigned long long* bsum,
+                      unsigned long long* row_start, unsigned long long* grand_total, cudaStream_t st) {
   if (!rows) {
     cudaMemsetAsync(grand_total, 0, sizeof(unsigned long long), st);
     return;
   }
   const unsigned nb = (rows + kScanBlock - 1) / kScanBlock;
-  k_scan_block_sums<true><<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum);
+  k_scan_block_sums<<<nb, kScanBlock, 0, st>>>(row_count, rows, padq, bsum);
   k_scan_sums<<<1, kScanBlock, 0, st>>>(bsum, nb, grand_total);
-  k_scan_apply<true><<<nb, kScanBlock, 0, st>>>(row_count, rows, bsum, row_start, nullptr, nullptr);
+  k_scan_apply<true><<<nb, kScanBlock, 0, st>>>(row_count, rows, padq, bsum, row_start, nullptr, nullptr);
 }
 
 }  // namespace b200

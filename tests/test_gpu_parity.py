@@ -367,6 +367,7 @@ def test_rt20_switch_regtests_on_gpu():
     with open(os.path.join(GOLD, "ref_regtest_kats.json")) as f:
         rt = json.load(f)["rt20_switch"]
     frames = rt["frames"]
+    bad = []
     for name, test in rt["tests"].items():
         col = np.array(test["colvar"])
         der = np.array(test["deriv"]).reshape(len(frames), 15, 4)
@@ -375,7 +376,9 @@ def test_rt20_switch_regtests_on_gpu():
             for fi, fr in enumerate(frames):
                 c.prepare(fi)
                 c.calculate(np.array(fr["pos"]), np.diag(fr["box"]))
-                assert abs(c.value - col[fi, 1 + ci]) < 6e-7, (name, lab, fi, c.value)
                 got = np.concatenate([c.derivatives.ravel(), c.virial.ravel()])
-                assert np.abs(got - der[fi, :, 2 + ci]).max() < 5.1e-5, (name, lab, fi)
+                ev, ed = abs(c.value - col[fi, 1 + ci]), np.abs(got - der[fi, :, 2 + ci]).max()
+                if ev >= 6e-7 or ed >= 5.1e-5:
+                    bad.append((name, lab, fi, fr["pos"], float(c.value), float(col[fi, 1 + ci]), float(ed)))
             c.close()
+    assert not bad, bad
