@@ -105,7 +105,6 @@ typedef struct b200coord_stats {
   unsigned sweep_count;              /* ... and how many sweeps that covers (at most the last 64 are kept) */
   float build_ms_sum;                /* same for list rebuilds */
   unsigned build_count;
-  int tile_mode;                     /* 1: the opt-in shared-memory tile sweep (B200COORD_TILE=1) is in use */
   int f32_search;                    /* 1: the last rebuild used the FP32 candidate search (+ exact FP64 band) */
 } b200coord_stats;
 

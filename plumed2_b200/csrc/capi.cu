@@ -118,7 +118,7 @@ struct b200coord_ctx {
 
   DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small;
   DevBuf<uint32_t> d_abs, d_perm, d_scell, d_cell_of_slot, d_tmp, d_ccount, d_cstart, d_cursor, d_rowcount, d_nbr;
-  DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch
+  DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch, [10] max displacement^2 (bits)
   DevBuf<SPos> d_spos;
   DevBuf<uint8_t> d_active;
   DevBuf<unsigned char> d_params;  // [DevPbc | DevSwitch] in global memory for the out-of-line row patch
@@ -128,12 +128,15 @@ struct b200coord_ctx {
   bool f32_search = false;
   double band_rel = 0.0;
   unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
-  bool tile_mode = false;      // list holds 16-bit tile-local indices, sweep = k_sweep_tile (kernels_tile.cu)
-  bool tile_disabled = false;  // B200COORD_NO_TILE=1, or a tile did not fit in shared memory
-  unsigned tile_cap = 0;       // records per tile (max over pencils, rounded up)
+  DevBuf<double> d_bpos;       // positions the list was built from (sorted order), for the displacement bound
+  DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
   unsigned* h_capinfo = nullptr;
   unsigned long long nbr_total = 0;
+  unsigned far_rows = 0;     // rows of d_rowfar (offsets, then lengths)
+  bool far_split = true;     // B200COORD_NO_FAR_SPLIT=1 keeps rows in one part
+  double far_skin = 0.0;     // far partners were beyond D_MAX + far_skin when the list was built (0: no far parts)
+  unsigned long box_epoch = 0, build_box_epoch = 0;  // set_box calls that changed the box / value at the last rebuild
   int sweep_blocks = 0;
 
   double* h_small = nullptr;  // pinned: [0..9] tail, [10..15] bbox
@@ -291,12 +294,6 @@ int setup_grid(b200coord_ctx* c, const double* d_pos) {
     std::memset(&c->dbox, 0, sizeof(c->dbox));
     std::memcpy(c->dbox.box, c->hpbc.box, sizeof(c->dbox.box));
   }
-  {
-    const unsigned P = (g.radius == 2) ? 6u : 1u;
-    g.pencil = (int)P;
-    c->tile_mode = c->f32_search && !c->tile_disabled && c->cfg.style != B200COORD_STYLE_PAIR &&
-                   (use_bbox || nc[0] >= P + 2u * (unsigned)g.radius);
-  }
   if ((unsigned long long)nc[0] * nc[1] * nc[2] > 400000000ull)
     return fail(c, B200COORD_ERR_INVALID, "cell grid too large for the given NL_CUTOFF and box");
   for (int k = 0; k < 3; ++k) c->stats.ncells[k] = nc[k];
@@ -335,6 +332,14 @@ int setup_all_pairs(b200coord_ctx* c) {
 }
 
 // NeighborList::update (NeighborList.cpp:168-315) on the device
+// capacity of the fixed-size rows of the next single-pass rebuild: 1.2 x the longest row seen now; kept when the
+// current capacity is still adequate (the list buffer is sized by rows x capacity)
+unsigned next_row_cap(unsigned max_row, unsigned current) {
+  const unsigned want = ((max_row + max_row / 5 + 16u) + 7u) & ~7u;
+  if (current >= max_row + max_row / 10 + 8u && current <= want + want / 4) return current;
+  return want;
+}
+
 int rebuild(b200coord_ctx* c, const double* d_pos) {
   const int mode = c->cfg.nl_mode;
   if (c->cfg.style == B200COORD_STYLE_PAIR) {
@@ -372,27 +377,45 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     const unsigned rows = c->row_end - c->row_begin;
     CU(c, c->d_rowcount.reserve(rows + 1));
     CU(c, c->d_rowstart.reserve(rows + 1));
+    CU(c, c->d_rowfar.reserve(2 * (size_t)rows + 2));
+    c->far_rows = rows;
+    // near/far split of the rows: partners beyond D_MAX + a skin of a quarter of the list's buffer go to the far part
+    float far2 = INFINITY;
+    if (c->far_split && c->sw.dmax > 0.0 && c->sw.dmax < c->cfg.nl_cutoff) {
+      const double rf = c->sw.dmax + 0.25 * (c->cfg.nl_cutoff - c->sw.dmax);
+      far2 = (float)(rf * rf);
+      c->far_skin = rf - c->sw.dmax;
+    } else {
+      c->far_skin = 0.0;
+    }
     CU(c, c->d_bsum.reserve(rows / 1024 + 2));
     const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
     auto two_pass = [&]() -> int {
       auto rows_pass = [&](bool fill) {
         if (c->f32_search)
-          launch_nl_rows_f32(fill ? 1 : 0, c->tile_mode, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid,
+          launch_nl_rows_f32(fill ? 1 : 0, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid,
                              c->dpbc, c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end,
-                             c->d_rowcount.p, c->d_rowstart.p, fill ? c->d_nbr.p : nullptr, 0u, c->d_capinfo.p, c->st);
+                             c->d_rowcount.p, c->d_rowstart.p, fill ? c->d_nbr.p : nullptr, 0u, c->d_capinfo.p, far2,
+                             c->d_rowfar.p, c->d_rowfar.p + rows, c->st);
         else
           launch_nl_rows(fill, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
                          c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, fill ? c->d_rowstart.p : nullptr,
                          fill ? c->d_nbr.p : nullptr, c->st);
       };
       rows_pass(false);
-      launch_scan_rows(c->d_rowcount.p, rows, c->tile_mode ? 7u : 3u, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
+      launch_scan_rows(c->d_rowcount.p, rows, 3u, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
       CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
       CU_LAST(c, "neighbour list count");
-      c->nbr_total = c->h_u64[0];  // entries (32-bit, or 16-bit in tile mode)
-      CU(c, c->d_nbr.reserve((size_t)(c->tile_mode ? (c->nbr_total + 1) / 2 : c->nbr_total) + 4));
+      c->nbr_total = c->h_u64[0];
+      {
+        // the following rebuilds use fixed-capacity rows (below): size the buffer for that layout now, so that the
+        // second rebuild does not have to free and allocate gigabytes
+        size_t need = (size_t)c->nbr_total;
+        if (c->f32_search) need = std::max(need, (size_t)rows * next_row_cap(c->h_capinfo[0], 0u));
+        CU(c, c->d_nbr.reserve(need + 4));
+      }
       rows_pass(true);
       c->stats.kernel_launches += 5;
       return B200COORD_OK;
@@ -403,15 +426,17 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       c->stats.kernel_launches += 1;
     }
     CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
+    if (!c->f32_search) CU(c, cudaMemsetAsync(c->d_rowfar.p, 0, 2 * (size_t)rows * sizeof(uint32_t), c->st));
     bool done = false;
     if (c->f32_search && c->row_cap > 0) {
       // single pass into fixed-capacity rows (capacity = 1.2 x the longest row of the previous rebuild);
       // an overflow is detected on the device and answered with the exact two-pass build
       c->nbr_total = (unsigned long long)rows * c->row_cap;
-      CU(c, c->d_nbr.reserve((size_t)(c->tile_mode ? (c->nbr_total + 1) / 2 : c->nbr_total) + 4));
-      launch_nl_rows_f32(2, c->tile_mode, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, c->dbox,
+      CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 4));
+      launch_nl_rows_f32(2, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, c->dbox,
                          cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
-                         c->d_rowstart.p, c->d_nbr.p, c->row_cap, c->d_capinfo.p, c->st);
+                         c->d_rowstart.p, c->d_nbr.p, c->row_cap, c->d_capinfo.p, far2, c->d_rowfar.p, c->d_rowfar.p + rows,
+                         c->st);
       CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
       CU_LAST(c, "neighbour list single-pass build");
@@ -423,19 +448,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       int rc2 = two_pass();
       if (rc2) return rc2;
     }
-    if (c->f32_search) {
-      const unsigned mx = c->h_capinfo[0];
-      c->row_cap = ((mx + mx / 5 + 16u) + 7u) & ~7u;
-    }
-    if (c->tile_mode) {
-      c->tile_cap = (c->h_capinfo[2] + 31u) & ~31u;
-      if ((size_t)c->tile_cap * 28u + 16u > 200u * 1024u) {
-        // a pencil's stencil does not fit in shared memory (extreme density): rebuild with the global 32-bit list
-        c->tile_disabled = true;
-        c->row_cap = 0;
-        return rebuild(c, d_pos);
-      }
-    }
+    if (c->f32_search) c->row_cap = next_row_cap(c->h_capinfo[0], c->row_cap);
   }
   CU(c, cudaEventRecord(c->ev[5], c->st));
   c->ev_valid[2] = true;
@@ -513,7 +526,16 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     weight = 1.0;
     c->stats.kernel_launches += 1;
   } else {
-    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+    const bool track = (c->cfg.nl_mode == B200COORD_NL_CLASSIC);
+    if (track) {
+      CU(c, c->d_bpos.reserve(3 * (size_t)c->n));
+      if (need_rebuild) c->build_box_epoch = c->box_epoch;
+      CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));  // this step's displacement
+      launch_gather_track(need_rebuild ? 1 : 2, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->d_bpos.p, c->dpbc,
+                          c->d_u64.p + 10, c->st);
+    } else {
+      launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+    }
     SweepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.spos = c->d_spos.p;
@@ -525,7 +547,16 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     a.row_start = c->d_rowstart.p;
     a.row_count = c->d_rowcount.p;
     a.nbr = c->d_nbr.p;
-    a.nbr16 = reinterpret_cast<const uint16_t*>(c->d_nbr.p);
+    a.row_far_off = c->d_rowfar.p;
+    a.row_far_cnt = c->d_rowfar.p + c->far_rows;
+    // a pair with r^2 above this is beyond D_MAX and outside the band in which the exact patch decides (sweep_math.cuh)
+    a.far_skip2 = (c->dsw.band_dmax >= 0.0) ? c->dsw.dmax_2 + c->dsw.band_dmax : INFINITY;
+    a.disp2_bits = c->d_u64.p + 10;
+    {
+      const double half = 0.5 * c->far_skin * (1.0 - 1e-3);  // margin: the split itself was decided in FP32
+      a.far_disp2_max = half * half;
+    }
+    a.force_far = (c->box_epoch != c->build_box_epoch) ? 1 : 0;
     a.scell = c->d_scell.p;
     a.cstart = c->d_cstart.p;
     a.ccount = c->d_ccount.p;
@@ -542,18 +573,12 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     a.evals = c->d_u64.p + 1;
     a.pbc_g = pbc_g;
     a.sw_g = sw_g;
-    const bool tile_now = c->tile_mode && c->cfg.nl_mode == B200COORD_NL_CLASSIC;
-    const size_t npencil = tile_now ? (size_t)((c->grid.n[0] + c->grid.pencil - 1) / c->grid.pencil) * c->grid.n[1] * c->grid.n[2] : 0;
-    CU(c, c->d_partials.reserve((size_t)kPartialStride * (std::max<size_t>((c->row_end - c->row_begin) / 8, npencil) + 4)));
+    CU(c, c->d_partials.reserve((size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 4)));
     a.partials = c->d_partials.p;
     CU(c, cudaEventRecord(c->ev[2], c->st));
     CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
-    if (tile_now)
-      nblocks = launch_sweep_tile(a, c->dpbc, c->dsw, c->tile_cap, c->st);
-    else
-      nblocks = (c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? launch_sweep_list(a, c->dpbc, c->dsw, c->st)
-                                                          : launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
-    if (nblocks == -2) return fail(c, B200COORD_ERR_CUDA, "tile sweep: shared-memory tile could not be configured");
+    nblocks = (c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? launch_sweep_list(a, c->dpbc, c->dsw, c->st)
+                                                        : launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
     CU(c, cudaEventRecord(c->ev[3], c->st));
     weight = c->two_groups ? 1.0 : 0.5;
     c->stats.kernel_launches += 1 + (c->two_groups ? 2 : 1);
@@ -610,7 +635,6 @@ void refresh_stats(b200coord_ctx* c) {
       else c->stats.nl_size = n * (n - 1) / 2;
   }
   c->stats.pbc_type = c->hpbc.type;
-  c->stats.tile_mode = (c->tile_mode && c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? 1 : 0;
   c->stats.f32_search = c->f32_search ? 1 : 0;
 }
 
@@ -776,10 +800,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   std::memset(&c->hpbc, 0, sizeof(c->hpbc));
   to_dev_pbc(c->hpbc, false, c->dpbc);
   if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
-  // the shared-memory tile sweep (kernels_tile.cu) is an opt-in alternative: same speed as the list sweep on B200,
-  // half the list footprint
-  c->tile_disabled = true;
-  if (const char* e = std::getenv("B200COORD_TILE")) c->tile_disabled = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
   *out = c;
   return B200COORD_OK;
 }
@@ -795,7 +816,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release();
   if (c->peer_mode)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
@@ -816,6 +837,7 @@ int b200coord_set_box(b200coord_ctx* c, const double box[9]) {
   if (!c || !box) return fail(c, B200COORD_ERR_INVALID, "null argument");
   if (c->box_set && std::memcmp(box, c->box_cached, sizeof(c->box_cached)) == 0) return B200COORD_OK;
   std::memcpy(c->box_cached, box, sizeof(c->box_cached));
+  c->box_epoch++;
   setup_pbc(box, c->hpbc);
   to_dev_pbc(c->hpbc, c->cfg.pbc != 0, c->dpbc);
   c->params_dirty = true;
@@ -1028,56 +1050,14 @@ int b200coord_nl_pairs(b200coord_ctx* c, unsigned* pairs, unsigned long long cap
       std::vector<unsigned long long> st(n);
       CU(c, cudaMemcpy(cnt.data(), c->d_rowcount.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
       CU(c, cudaMemcpy(st.data(), c->d_rowstart.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      if (!c->tile_mode) {
-        std::vector<uint32_t> nbr((size_t)c->nbr_total);
-        if (c->nbr_total)
-          CU(c, cudaMemcpy(nbr.data(), c->d_nbr.p, (size_t)c->nbr_total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        for (unsigned k = 0; k < n; ++k)
-          for (uint32_t e = 0; e < cnt[k]; ++e) emit(perm[k], perm[nbr[st[k] + e]]);
-      } else {
-        // 16-bit tile-local entries: rebuild every pencil's tile layout on the host with the same code the
-        // kernels use (column_parts / xrun_bounds / stencil_bounds) and translate back to sorted indices
-        std::vector<uint16_t> nbr16((size_t)c->nbr_total);
-        if (c->nbr_total)
-          CU(c, cudaMemcpy(nbr16.data(), c->d_nbr.p, (size_t)c->nbr_total * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-        const DevGrid& g = c->grid;
-        const size_t m = (size_t)(c->two_groups ? 2 : 1) * g.ncell;
-        std::vector<uint32_t> cs(m), cn(m), sc(n);
-        CU(c, cudaMemcpy(cs.data(), c->d_cstart.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(cn.data(), c->d_ccount.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(sc.data(), c->d_scell.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        const int P = pencil_cells(g);
-        long long cached = -1;
-        std::vector<uint32_t> tile;
-        for (unsigned k = 0; k < n; ++k) {
-          const unsigned grp = k < n_a ? 0u : 1u;
-          const unsigned part_off = (c->two_groups ? (1u - grp) : 0u) * (unsigned)g.ncell;
-          int cc[3], lo[3], hi[3];
-          cell_coords(g, (int)sc[k], cc);
-          const int x0 = (cc[0] / P) * P, x1 = std::min(x0 + P, g.n[0]) - 1;
-          const long long key = ((long long)grp * g.ncell + sc[k] - cc[0] + x0);
-          if (key != cached) {
-            cached = key;
-            tile.clear();
-            int pc3[3] = {x0, cc[1], cc[2]};
-            stencil_bounds(g, pc3, lo, hi);
-            for (int ny = lo[1]; ny < hi[1]; ++ny)
-              for (int nz = lo[2]; nz < hi[2]; ++nz) {
-                const unsigned cbase = part_off + (unsigned)(wrap_cell(ny, g.n[1]) * g.n[0] + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
-                int xa, xb;
-                xrun_bounds(g, x0, x1, xa, xb);
-                TileCol tc;
-                column_parts(g, cbase, xa, xb, cs.data(), cn.data(), tc);
-                for (uint32_t t = 0; t < tc.lA; ++t) tile.push_back(tc.gA + t);
-                for (uint32_t t = 0; t < tc.lB; ++t) tile.push_back(tc.gB + t);
-              }
-          }
-          for (uint32_t e = 0; e < cnt[k]; ++e) {
-            const uint16_t l = nbr16[st[k] + e];
-            if (l >= tile.size()) return fail(c, B200COORD_ERR_STATE, "tile-local neighbour index out of range");
-            emit(perm[k], perm[tile[l]]);
-          }
-        }
+      std::vector<uint32_t> nbr((size_t)c->nbr_total);
+      if (c->nbr_total)
+        CU(c, cudaMemcpy(nbr.data(), c->d_nbr.p, (size_t)c->nbr_total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> far(2 * (size_t)n);
+      if (n) CU(c, cudaMemcpy(far.data(), c->d_rowfar.p, 2 * (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (unsigned k = 0; k < n; ++k) {
+        for (uint32_t e = 0; e < cnt[k]; ++e) emit(perm[k], perm[nbr[st[k] + e]]);
+        for (uint32_t e = 0; e < far[n + k]; ++e) emit(perm[k], perm[nbr[st[k] + far[k] + e]]);
       }
       // pairs of one and the same atom are at distance 0 <= cutoff: the reference lists them
       if (c->n_self_pairs) {

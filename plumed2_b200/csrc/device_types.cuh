@@ -21,7 +21,6 @@ struct DevGrid {
   int bbox;            // 1: no box -> bounding box around the atoms, origin subtracted (LinkCells.cpp:49-73, :279-281)
   int stencil_pbc;     // 1: neighbour stencil wraps, 0: clamps (the usePbc argument of addRequiredCells, :195-239)
   int radius;          // stencil half-width in cells: 1 = the reference's 27 cells; 2 = our finer NLIST search grid
-  int pencil;          // tile mode: cells along x per pencil (= per block of the tile sweep)
   int n[3];            // cells per direction
   int ncell;           // n0*n1*n2
   double inv_box_t[9]; // transpose(invBox): fpos = inv_box_t * pos   (Pbc::realToScaled, Pbc.cpp:472-474)

@@ -68,50 +68,6 @@ __host__ __device__ __forceinline__ void cell_coords(const DevGrid& g, int cell,
   c[0] = rem - c[1] * g.n[0];
 }
 
-// ---- tiles (kernels_tile.cu): a block of the tile sweep owns a PENCIL of consecutive cells along x and stages
-// the partner atoms of the pencil's whole stencil in shared memory; list entries are 16-bit tile-local indices.
-// The tile layout is a pure function of (grid, cell ranges, pencil): the list builder and the sweep derive it
-// with the same code below, one stencil column (dy,dz) per lane.
-struct TileCol {
-  uint32_t gA, lA, gB, lB;  // global sorted start / length of the (<=2) contiguous parts of the column's x-run
-  int wA, wB;               // periodic image (-1,0,+1) of each part along x
-};
-__host__ __device__ __forceinline__ int pencil_cells(const DevGrid& g) { return g.pencil > 0 ? g.pencil : 1; }
-
-// x-run [xa,xb) (unwrapped cell indices) of the stencil column whose wrapped (y,z) base is cbase
-__host__ __device__ __forceinline__ void column_parts(const DevGrid& g, unsigned cbase, int xa, int xb,
-                                             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
-                                             TileCol& t) {
-  t.gA = t.lA = t.gB = t.lB = 0u;
-  t.wA = t.wB = 0;
-  int x = xa;
-  if (x < xb) {
-    const int xw = wrap_cell(x, g.n[0]);
-    const int run = min(xb - x, g.n[0] - xw);
-    const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
-    t.gA = cstart[first];
-    t.lA = cstart[last] + ccount[last] - t.gA;
-    t.wA = wrap_count(x, g.n[0]);
-    x += run;
-  }
-  if (x < xb) {
-    const int xw = wrap_cell(x, g.n[0]);
-    const int run = min(xb - x, g.n[0] - xw);
-    const unsigned first = cbase + (unsigned)xw, last = first + (unsigned)run - 1u;
-    t.gB = cstart[first];
-    t.lB = cstart[last] + ccount[last] - t.gB;
-    t.wB = wrap_count(x, g.n[0]);
-  }
-}
-// x bounds of the stencil of the cell range [c0,c1] (tile mode is only used on grids where this is valid)
-__host__ __device__ __forceinline__ void xrun_bounds(const DevGrid& g, int c0, int c1, int& xa, int& xb) {
-  xa = c0 - g.radius;
-  xb = c1 + g.radius + 1;
-  if (!g.stencil_pbc) {
-    xa = max(xa, 0);
-    xb = min(xb, g.n[0]);
-  }
-}
 __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, unsigned lane, uint32_t& total) {
   uint32_t x = v;
 #pragma unroll
@@ -131,6 +87,10 @@ void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const
 void launch_identity(unsigned n, uint32_t* perm, uint32_t* scell, cudaStream_t st);
 void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, SPos* spos,
                    cudaStream_t st);
+// the same, plus displacement tracking: track 1 = store the build-time positions in bpos (sorted order),
+// track 2 = atomicMax the largest squared displacement since then into *disp2 (bits of a double)
+void launch_gather_track(int track, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+                         SPos* spos, double* bpos, const DevPbc& pbc, unsigned long long* disp2, cudaStream_t st);
 void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                     const DevGrid& g, const DevPbc& pbc, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                     unsigned row_end, uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr,
@@ -138,14 +98,15 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 // float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits)
 void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool tile, const SPos* spos,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos,
                         const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
                         unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
-                        unsigned* cap_info /*[0] max row, [1] overflow, [2] max tile*/, cudaStream_t st);
+                        unsigned* cap_info /*[0] max row, [1] overflow*/, float far2 /*near/far split, r^2*/,
+                        uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st);
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st);
-void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned padq /*3: 32-bit list, 7: 16-bit tile list*/,
+void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned padq /*3: list rows start on 16-byte boundaries*/,
                       unsigned long long* bsum, unsigned long long* row_start, unsigned long long* grand_total,
                       cudaStream_t st);
 
@@ -162,7 +123,18 @@ struct SweepArgs {
   const unsigned long long* row_start;
   const uint32_t* row_count;
   const uint32_t* nbr;
-  const uint16_t* nbr16;   // tile mode: tile-local indices, rows padded to 8 entries
+  // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)
+  // when the list was built, [row_start + row_far_off, +row_far_cnt) the rest (filled from the end of the row's
+  // allocation).  A trip of the far part whose 32 pairs are all beyond D_MAX contributes exactly zero and stops
+  // after the distance test.
+  const uint32_t* row_far_off;
+  const uint32_t* row_far_cnt;
+  double far_skip2;        // r^2 above which a pair is certainly beyond D_MAX and its boundary band (inf: never)
+  // Verlet skin: the far parts are not visited at all while the largest displacement since the rebuild is below half
+  // the skin the far partners had beyond D_MAX (k_gather_sorted tracks it)
+  const unsigned long long* disp2_bits;  // largest squared displacement since the rebuild (bits of a double)
+  double far_disp2_max;                  // visit the far parts unless disp2 < this
+  int force_far;                         // box changed since the rebuild: always visit them
   // implicit ranges (no NL / NLISTCELLS)
   const uint32_t* scell;
   const uint32_t* cstart;
@@ -180,9 +152,6 @@ struct SweepArgs {
   double* peers[7];
 };
 
-// tile sweep (16-bit tile-local list): returns the number of partial records, -1 unsupported switch,
-// -2 the tile does not fit in shared memory
-int launch_sweep_tile(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, unsigned tile_cap, cudaStream_t st);
 // returns the number of blocks launched (= number of partial records), or -1 for an unsupported switch
 int launch_sweep_list(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);

@@ -160,19 +160,51 @@ __global__ void k_order_cells(unsigned nseg, int ncell, const uint32_t* __restri
   }
 }
 
-// per step: sorted, 32-byte records from the caller's AoS positions
-__global__ void k_gather_sorted(const double* __restrict__ pos, const uint32_t* __restrict__ perm,
-                                const uint32_t* __restrict__ abs_index, unsigned n, SPos* __restrict__ spos) {
+// per step: sorted, 32-byte records from the caller's AoS positions.
+// TRACK 1 (rebuild step): also remember the positions the list was built from; TRACK 2 (other steps): largest squared
+// minimum-image displacement of any atom since then -> disp2 (bits of a non-negative double order like integers).
+// The sweep uses it for the Verlet-skin argument: while 2 * max displacement < skin, no partner of the far parts of
+// the rows (r > D_MAX + skin at build time) can have come inside D_MAX.
+template <int TRACK, int PBC>
+__global__ void __launch_bounds__(256)
+    k_gather_sorted(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ abs_index,
+                    unsigned n, SPos* __restrict__ spos, double* __restrict__ bpos, DevPbc pbc,
+                    unsigned long long* __restrict__ disp2) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t slot = perm[k];
-  SPos r;
-  r.x = pos[3 * (size_t)slot];
-  r.y = pos[3 * (size_t)slot + 1];
-  r.z = pos[3 * (size_t)slot + 2];
-  r.abs_index = abs_index[slot];
-  r.slot = slot;
-  spos[k] = r;
+  double d2 = 0.0;
+  if (k < n) {
+    const uint32_t slot = perm[k];
+    SPos r;
+    r.x = pos[3 * (size_t)slot];
+    r.y = pos[3 * (size_t)slot + 1];
+    r.z = pos[3 * (size_t)slot + 2];
+    r.abs_index = abs_index[slot];
+    r.slot = slot;
+    spos[k] = r;
+    if (TRACK == 1) {
+      bpos[3 * (size_t)k] = r.x;
+      bpos[3 * (size_t)k + 1] = r.y;
+      bpos[3 * (size_t)k + 2] = r.z;
+    } else if (TRACK == 2) {
+      double dx = r.x - bpos[3 * (size_t)k], dy = r.y - bpos[3 * (size_t)k + 1], dz = r.z - bpos[3 * (size_t)k + 2];
+      min_image_fast<PBC>(pbc, dx, dy, dz);
+      d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      if (!(d2 >= 0.0)) d2 = INFINITY;  // NaN positions: never skip anything
+    }
+  }
+  if (TRACK == 2) {
+    __shared__ double sm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = d2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = sm[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = fmax(m, sm[w]);
+      if (m > 0.0) atomicMax(disp2, (unsigned long long)__double_as_longlong(m));
+    }
+  }
 }
 
 __global__ void k_identity_perm(unsigned n, uint32_t* __restrict__ perm, uint32_t* __restrict__ scell) {
@@ -291,13 +323,14 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
   lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
 }
 
-template <bool FILL, bool CAPPED, bool TILE>
+template <bool FILL, bool CAPPED>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
                   DevPbc box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                   unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
-                  uint32_t* __restrict__ nbr, unsigned row_cap, unsigned* __restrict__ cap_info /*[0] max count, [1] overflow*/) {
+                  uint32_t* __restrict__ nbr, unsigned row_cap, unsigned* __restrict__ cap_info /*[0] max count, [1] overflow*/,
+                  float far2, uint32_t* __restrict__ row_far_off, uint32_t* __restrict__ row_far_cnt) {
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   const unsigned k = row_begin + warp;
@@ -341,38 +374,16 @@ __global__ void __launch_bounds__(256, 4)
       wxB = wrap_count(x, g.n[0]);
     }
   }
-  // TILE: entries are indices into the shared-memory tile of this row's pencil (see kernels.cuh "tiles"):
-  // the pencil's column has the same (y,z) as mine and an x-run that contains mine, so an entry is
-  // tile_off(column) + (offset of my range inside the pencil's range) + position in my range.
-  uint32_t lbA = 0, lbB = 0;
-  if (TILE) {
-    const int P = pencil_cells(g);
-    const int x0 = (c[0] / P) * P, x1 = min(x0 + P, g.n[0]) - 1;
-    TileCol pc;
-    pc.gA = pc.lA = pc.gB = pc.lB = 0u;
-    pc.wA = pc.wB = 0;
-    if ((int)lane < ncol) {
-      const int ny = lo[1] + (int)lane / nz_n, nz = lo[2] + (int)lane % nz_n;
-      const unsigned cbase = group_off + (unsigned)(wrap_cell(ny, g.n[1]) * g.n[0] + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
-      int xa, xb;
-      xrun_bounds(g, x0, x1, xa, xb);
-      column_parts(g, cbase, xa, xb, cstart, ccount, pc);
-    }
-    uint32_t tile_total;
-    const uint32_t off = warp_exclusive_scan(pc.lA + pc.lB, lane, tile_total);
-    // a part of my x-run lies in the part of the pencil's x-run that is seen through the same periodic image
-    lbA = off + ((wxA == pc.wA || pc.lB == 0u) ? (sA - pc.gA) : pc.lA + (sA - pc.gB));
-    lbB = off + ((wxB == pc.wA || pc.lB == 0u) ? (sB - pc.gA) : pc.lA + (sB - pc.gB));
-    if (lane == 0 && tile_total > cap_info[2]) atomicMax(&cap_info[2], tile_total);
-  }
   const float ax = (float)box.box[0], ay = (float)box.box[1], az = (float)box.box[2];
   const float bx = (float)box.box[3], by = (float)box.box[4], bz = (float)box.box[5];
   const float cx = (float)box.box[6], cy = (float)box.box[7], cz = (float)box.box[8];
-  uint16_t* __restrict__ nbr16 = reinterpret_cast<uint16_t*>(nbr);
 
-  unsigned total = 0;
+  unsigned total = 0, total_far = 0;
   // CAPPED: single-pass build into fixed-capacity rows (capacity learnt from the previous rebuild)
   const unsigned long long base = CAPPED ? (unsigned long long)(k - row_begin) * row_cap : (FILL ? row_start[k - row_begin] : 0ull);
+  // 32-bit list: the row's allocation is filled from both ends, near partners (r^2 <= far2 now) forwards from its
+  // start, far ones backwards from its end (two-pass build: row_count still holds the total of the count pass)
+  const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
 
   // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
   auto exact_keep = [&](uint32_t j) -> bool {
@@ -392,26 +403,26 @@ __global__ void __launch_bounds__(256, 4)
     min_image_exact(pbc, d);
     return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
   };
-  auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz) -> bool {
+  auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz, bool& far) -> bool {
     const float dx = lj.x - ox, dy = lj.y - oy, dz = lj.z - oz;
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     bool keep = (j != k) && (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
     if (keep && r2 > c2_lo) keep = exact_keep(j);
+    far = r2 > far2;  // only orders the row: any classification gives the same results
     return keep;
   };
-  auto emit = [&](bool keep, uint32_t j, uint32_t local) {
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+  auto emit = [&](bool keep, bool far, uint32_t j) {
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned mn = __ballot_sync(0xffffffffu, keep && !far), mf = __ballot_sync(0xffffffffu, keep && far);
     if (FILL && keep) {
-      const unsigned at = total + __popc(mask & ((1u << lane) - 1u));
-      if (!CAPPED || at < row_cap) {
-        if (TILE) nbr16[base + at] = (uint16_t)local;
-        else nbr[base + at] = j;
-      }
+      const unsigned at = far ? total_far + __popc(mf & below) : total + __popc(mn & below);
+      if (at < alloc) nbr[base + (far ? alloc - 1u - at : at)] = j;
     }
-    total += __popc(mask);
+    total += __popc(mn);
+    total_far += __popc(mf);
   };
   // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
-  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz, uint32_t lb) {
+  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
     const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
     const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
     const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
@@ -421,10 +432,11 @@ __global__ void __launch_bounds__(256, 4)
       const uint32_t j1 = s + e1, j2 = s + e2;
       const float4 l1 = __ldg(lpos + (in1 ? j1 : k));
       const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
-      const bool k1 = in1 && test(j1, l1, ox, oy, oz);
-      const bool k2 = in2 && test(j2, l2, ox, oy, oz);
-      emit(k1, j1, lb + e1);
-      if (e0 + 32 < m) emit(k2, j2, lb + e2);
+      bool f1, f2;
+      const bool k1 = in1 && test(j1, l1, ox, oy, oz, f1);
+      const bool k2 = in2 && test(j2, l2, ox, oy, oz, f2);
+      emit(k1, f1, j1);
+      if (e0 + 32 < m) emit(k2, f2, j2);
     }
   };
   for (int col = 0; col < ncol; ++col) {
@@ -432,27 +444,22 @@ __global__ void __launch_bounds__(256, 4)
     const uint32_t s2 = __shfl_sync(0xffffffffu, sB, col), m2 = __shfl_sync(0xffffffffu, mB, col);
     const int w1 = __shfl_sync(0xffffffffu, wxA, col), w2 = __shfl_sync(0xffffffffu, wxB, col);
     const int wyy = __shfl_sync(0xffffffffu, wy, col), wzz = __shfl_sync(0xffffffffu, wz, col);
-    const uint32_t b1 = TILE ? __shfl_sync(0xffffffffu, lbA, col) : 0u, b2 = TILE ? __shfl_sync(0xffffffffu, lbB, col) : 0u;
-    if (m1) scan_range(s1, m1, w1, wyy, wzz, b1);
-    if (m2) scan_range(s2, m2, w2, wyy, wzz, b2);
+    if (m1) scan_range(s1, m1, w1, wyy, wzz);
+    if (m2) scan_range(s2, m2, w2, wyy, wzz);
   }
-  if (FILL) {  // rows are padded (4 x 32-bit or 8 x 16-bit entries = 16 bytes): make the padding a harmless index
-    const unsigned q = TILE ? 7u : 3u;
-    const unsigned pad = ((total + q) & ~q) - total;
-    if (lane < pad && (!CAPPED || total + lane < row_cap)) {
-      if (TILE) nbr16[base + total + lane] = 0;
-      else nbr[base + total + lane] = 0u;
+  const unsigned all = total + total_far;
+  if (lane == 0) {
+    if (FILL) {
+      row_count[k - row_begin] = min(total, alloc);
+      row_far_cnt[k - row_begin] = min(total_far, alloc);
+      row_far_off[k - row_begin] = alloc - min(total_far, alloc);
+    } else {
+      row_count[k - row_begin] = all;
     }
-  }
-  if (CAPPED) {
-    if (lane == 0) {
-      row_count[k - row_begin] = min(total, row_cap);
-      if (total > cap_info[0]) atomicMax(&cap_info[0], total);
-      if (total > row_cap) atomicExch(&cap_info[1], 1u);
+    if (CAPPED || !FILL) {
+      if (all > cap_info[0]) atomicMax(&cap_info[0], all);
     }
-  } else if (!FILL && lane == 0) {
-    row_count[k - row_begin] = total;
-    if (total > cap_info[0]) atomicMax(&cap_info[0], total);
+    if (CAPPED && all > row_cap) atomicExch(&cap_info[1], 1u);
   }
 }
 
@@ -585,7 +592,20 @@ void launch_identity(unsigned n, uint32_t* perm, uint32_t* scell, cudaStream_t s
 
 void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, SPos* spos,
                    cudaStream_t st) {
-  k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, spos);
+  k_gather_sorted<0, 0><<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, spos, nullptr, DevPbc{}, nullptr);
+}
+void launch_gather_track(int track, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+                         SPos* spos, double* bpos, const DevPbc& pbc, unsigned long long* disp2, cudaStream_t st) {
+  const unsigned blocks = (n + 255) / 256;
+  if (track == 1) {
+    k_gather_sorted<1, 0><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, spos, bpos, pbc, disp2);
+  } else {
+    switch (pbc.type) {
+      case 0: k_gather_sorted<2, 0><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, spos, bpos, pbc, disp2); break;
+      case 1: k_gather_sorted<2, 1><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, spos, bpos, pbc, disp2); break;
+      default: k_gather_sorted<2, 2><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, spos, bpos, pbc, disp2); break;
+    }
+  }
 }
 
 void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
@@ -614,27 +634,21 @@ void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const Dev
   if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos);
 }
 
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool tile, const SPos* spos,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos,
                         const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
-                        unsigned long long* row_start, uint32_t* nbr, unsigned row_cap, unsigned* cap_info,
-                        cudaStream_t st) {
+                        unsigned long long* row_start, uint32_t* nbr, unsigned row_cap, unsigned* cap_info, float far2,
+                        uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
 #define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a, two_groups, row_begin, row_end, \
-                      row_count, row_start, nbr, row_cap, cap_info
+                      row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (tile) {
-    if (mode == 0) k_nl_rows_f32<false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else if (mode == 1) k_nl_rows_f32<true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  } else {
-    if (mode == 0) k_nl_rows_f32<false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else if (mode == 1) k_nl_rows_f32<true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  }
+  if (mode == 0) k_nl_rows_f32<false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  else if (mode == 1) k_nl_rows_f32<true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  else k_nl_rows_f32<true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
 #undef B200_F32_ARGS
 }
 

@@ -14,53 +14,65 @@
 //     instead of the IEEE division slow path; the minimum image uses 2-add rounding instead of F2I/I2F.
 //   * Rows come either from the stream-compacted CSR list (NLIST) or, for NLISTCELLS / no list, from the
 //     contiguous sorted ranges of the <=27 stencil cells (no index traffic, coalesced 32-byte records).
+#include <cstdlib>
+#include <type_traits>
+
 #include "sweep_math.cuh"
 
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------------
-// rows from the CSR list (classic NLIST)
+// rows from the neighbour list (classic NLIST)
+//
+// 128 registers / 2 blocks per SM on purpose: with fewer registers ptxas sinks the record loads of the next trip
+// down to their first use (and spills the accumulators), which exposes the L2 latency of the gather in every trip.
 template <int K, int PBC, bool ACC>
-__global__ void __launch_bounds__(kSweepThreads, 3)
+__global__ void __launch_bounds__(kSweepThreads, 2)
     k_sweep_list(SweepArgs a, DevPbc pbc, DevSwitch sw, unsigned rows_per_block, unsigned seg_begin, unsigned seg_end) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LaneAcc acc = {0, 0, 0, 0, 0, 0, 0};
   unsigned long long evals = 0;
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
+  unsigned fixmask = 0u;  // rows of this warp with a pair on a D_MAX / D_0 boundary (rows_per_block <= 32 warps' worth)
+  const bool far_on = a.force_far || !(__longlong_as_double((long long)*a.disp2_bits) < a.far_disp2_max);
   for (unsigned k = first + wid; k < last; k += kSweepWarps) {
     const SPos pi = load_spos(a.spos + k);
+    const unsigned long long wi = ((unsigned long long)pi.slot << 32) | pi.abs_index;
     const unsigned long long base = a.row_start[k - a.row_begin];
-    const unsigned cnt = a.row_count[k - a.row_begin];
+    const unsigned cnt_near = a.row_count[k - a.row_begin], cnt_far = a.row_far_cnt[k - a.row_begin];
+    const unsigned far_off = a.row_far_off[k - a.row_begin];
     const bool row_is_b = (k >= a.n_a);
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    const uint32_t* __restrict__ row = a.nbr + base;
     bool near = false;
     // Two pairs per lane and trip, evaluated as two independent straight-line chains: one pair is a ~25-deep
     // chain of dependent FP64 operations, so a single chain per warp leaves the FP64 pipe half idle.  Indices
     // are fetched two trips ahead, the two 32-byte records one trip ahead.
-    unsigned e = lane;
-    uint32_t ja = (e < cnt) ? __ldg(row + e) : 0u;
-    uint32_t jb = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
-    SPos pa = load_spos(a.spos + ja);
-    SPos pb = load_spos(a.spos + jb);
-    ja = (e + 64 < cnt) ? __ldg(row + e + 64) : 0u;
-    jb = (e + 96 < cnt) ? __ldg(row + e + 96) : 0u;
-    for (; e < cnt; e += 64) {
-      const SPos ca = pa, cb = pb;
-      pa = load_spos(a.spos + ja);
-      pb = load_spos(a.spos + jb);
-      ja = (e + 128 < cnt) ? __ldg(row + e + 128) : 0u;
-      jb = (e + 160 < cnt) ? __ldg(row + e + 160) : 0u;
-      const bool vb = (e + 32 < cnt);
-      const bool flipa = a.two_groups ? row_is_b : (pi.slot > ca.slot);
-      const bool flipb = a.two_groups ? row_is_b : (pi.slot > cb.slot);
-      pair_term2<K, PBC, ACC>(pbc, sw, near, pi.x, pi.y, pi.z, ca, flipa, cb, flipb, vb, fx, fy, fz, acc);
-    }
-    if (__any_sync(0xffffffffu, near)) {  // some pair of this row sits on a D_MAX / D_0 boundary: patch the row exactly
-      const RowFix f = row_fixup_list<K, PBC>(a.pbc_g, a.sw_g, a.spos, row, cnt, k, lane, a.two_groups, row_is_b);
-      apply_fix(f, ACC, fx, fy, fz, acc);
-    }
+    auto part = [&](const uint32_t* __restrict__ row, unsigned cnt, auto far_tag) {
+      constexpr bool FAR = decltype(far_tag)::value;
+      unsigned e = lane;
+      uint32_t ja = (e < cnt) ? __ldg(row + e) : 0u;
+      uint32_t jb = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
+      RecBuf pa, pb;
+      load_rec(a.spos + ja, pa);
+      load_rec(a.spos + jb, pb);
+      ja = (e + 64 < cnt) ? __ldg(row + e + 64) : 0u;
+      jb = (e + 96 < cnt) ? __ldg(row + e + 96) : 0u;
+      for (unsigned e0 = 0; e0 < cnt; e0 += 64, e += 64) {  // warp-uniform trip count: the far part votes
+        const RecBuf ca = pa, cb = pb;
+        load_rec(a.spos + ja, pa);
+        load_rec(a.spos + jb, pb);
+        ja = (e + 128 < cnt) ? __ldg(row + e + 128) : 0u;
+        jb = (e + 160 < cnt) ? __ldg(row + e + 160) : 0u;
+        pair_term2<K, PBC, ACC, FAR>(pbc, sw, near, pi.x, pi.y, pi.z, wi, a.two_groups, row_is_b, ca, cb, e < cnt,
+                                     e + 32 < cnt, a.far_skip2, fx, fy, fz, acc);
+      }
+    };
+    if (cnt_near) part(a.nbr + base, cnt_near, std::false_type{});
+    if (cnt_far && far_on) part(a.nbr + base + far_off, cnt_far, std::true_type{});
+    // a pair of this row sits on a D_MAX / D_0 boundary: the row is patched after the loop (the cold call is kept
+    // out of it so that nothing is spilled around it)
+    if (__any_sync(0xffffffffu, near)) fixmask |= 1u << ((k - first) / kSweepWarps);
     fx = warp_sum(fx);
     fy = warp_sum(fy);
     fz = warp_sum(fz);
@@ -68,7 +80,26 @@ __global__ void __launch_bounds__(kSweepThreads, 3)
       a.sderiv[3 * (size_t)k] = fx;
       a.sderiv[3 * (size_t)k + 1] = fy;
       a.sderiv[3 * (size_t)k + 2] = fz;
-      evals += cnt;
+      evals += cnt_near + cnt_far;
+    }
+  }
+  while (fixmask) {
+    const unsigned m = (unsigned)__ffs((int)fixmask) - 1u;
+    fixmask &= fixmask - 1u;
+    const unsigned kf = first + wid + kSweepWarps * m;
+    const uint32_t* __restrict__ row = a.nbr + a.row_start[kf - a.row_begin];
+    const RowFix f = row_fixup_list<K, PBC>(a.pbc_g, a.sw_g, a.spos, row, a.row_count[kf - a.row_begin],
+                                            row + a.row_far_off[kf - a.row_begin], a.row_far_cnt[kf - a.row_begin], kf, lane,
+                                            a.two_groups, kf >= a.n_a);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    apply_fix(f, ACC, gx, gy, gz, acc);
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    gz = warp_sum(gz);
+    if (lane == 0) {  // the same lane stored these three values above
+      a.sderiv[3 * (size_t)kf] += gx;
+      a.sderiv[3 * (size_t)kf + 1] += gy;
+      a.sderiv[3 * (size_t)kf + 2] += gz;
     }
   }
   if (a.npeers) {

@@ -1,4 +1,4 @@
-// Pair arithmetic shared by the sweep kernels (kernels_sweep.cu, kernels_tile.cu): switching functions,
+// Pair arithmetic of the sweep kernels (kernels_sweep.cu): switching functions,
 // one pair term, warp/block reductions.
 #pragma once
 #include "kernels.cuh"
@@ -248,11 +248,29 @@ __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw
   }
 }
 
-// two pairs at once (second one masked out when `vb` is false) as independent instruction streams
-template <int K, int PBC, bool ACC>
-__device__ __forceinline__ void pair_term2(const DevPbc& pbc, const DevSwitch& sw, bool& near, double xi, double yi,
-                                           double zi, const SPos& pa, bool flipa, const SPos& pb, bool flipb, bool vb,
+// One prefetched partner record.  All four loaded doubles stay live until they are used (w = slot:abs bits is
+// compared as a whole): ptxas otherwise hands a dead destination register of the pending 256-bit load to the next
+// temporary, and that write-after-write waits for the load -- the latency the prefetch is there to hide.
+struct RecBuf {
+  double x, y, z, w;
+};
+__device__ __forceinline__ void load_rec(const SPos* __restrict__ p, RecBuf& b) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b.x), "=d"(b.y), "=d"(b.z), "=d"(b.w) : "l"(p));
+}
+
+// two pairs at once (masked out when `va` / `vb` is false) as independent instruction streams; the whole warp must
+// call this together (FAR votes).
+// `wi` = slot:abs bits of atom i; slots are unique, so comparing the whole 64 bits orders by slot.
+// FAR: the far part of a row (partners beyond D_MAX when the list was built) -- when no lane of the warp has a pair
+// inside far_skip2 = D_MAX^2 + boundary band, every contribution is exactly zero and the trip ends after the
+// distance test.  Returns false in that case.
+template <int K, int PBC, bool ACC, bool FAR>
+__device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitch& sw, bool& near, double xi, double yi,
+                                           double zi, unsigned long long wi, int two_groups, bool row_is_b,
+                                           const RecBuf& pa, const RecBuf& pb, bool va, bool vb, double far_skip2,
                                            double& fx, double& fy, double& fz, LaneAcc& acc) {
+  const bool flipa = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pa.w));
+  const bool flipb = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pb.w));
   const unsigned sga = flipa ? 0x80000000u : 0u, sgb = flipb ? 0x80000000u : 0u;
   double ax = flip_sign(pa.x - xi, sga), ay = flip_sign(pa.y - yi, sga), az = flip_sign(pa.z - zi, sga);
   double bx = flip_sign(pb.x - xi, sgb), by = flip_sign(pb.y - yi, sgb), bz = flip_sign(pb.z - zi, sgb);
@@ -260,10 +278,17 @@ __device__ __forceinline__ void pair_term2(const DevPbc& pbc, const DevSwitch& s
   min_image_fast<PBC>(pbc, bx, by, bz);
   const double ra = fma(az, az, fma(ay, ay, ax * ax));
   const double rb = fma(bz, bz, fma(by, by, bx * bx));
+  if (FAR) {
+    if (__all_sync(0xffffffffu, (!va || ra > far_skip2) && (!vb || rb > far_skip2))) return false;
+  }
   double sa, dfa, sb, dfb;
   eval_switch<K>(sw, ra, sa, dfa);
   eval_switch<K>(sw, rb, sb, dfb);
-  near |= on_boundary(sw, ra) | (vb & on_boundary(sw, rb));
+  near |= (va & on_boundary(sw, ra)) | (vb & on_boundary(sw, rb));
+  if (!va) {
+    sa = 0.0;
+    dfa = 0.0;
+  }
   if (!vb) {
     sb = 0.0;
     dfb = 0.0;
@@ -283,6 +308,7 @@ __device__ __forceinline__ void pair_term2(const DevPbc& pbc, const DevSwitch& s
     acc.vyz = fma(gay, az, fma(gby, bz, acc.vyz));
     acc.vzz = fma(gaz, az, fma(gbz, bz, acc.vzz));
   }
+  return true;
 }
 
 // Patch of one row in which some lane saw a boundary pair (rare: constructed inputs).  Walks the row again, and for
@@ -317,25 +343,13 @@ __device__ __forceinline__ void fix_one(const DevPbc& pbc, const DevSwitch& sw, 
 template <int K, int PBC>
 __device__ __noinline__ RowFix row_fixup_list(const DevPbc* __restrict__ pbc_g, const DevSwitch* __restrict__ sw_g,
                                               const SPos* __restrict__ spos, const uint32_t* __restrict__ row, unsigned cnt,
-                                              unsigned k, unsigned lane, int two_groups, bool row_is_b) {
+                                              const uint32_t* __restrict__ far_row, unsigned far_cnt, unsigned k,
+                                              unsigned lane, int two_groups, bool row_is_b) {
   RowFix f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const SPos pi = spos[k];
-  for (unsigned e = lane; e < cnt; e += 32) {
-    const SPos pj = spos[row[e]];
+  for (unsigned e = lane; e < cnt + far_cnt; e += 32) {
+    const SPos pj = spos[e < cnt ? row[e] : far_row[e - cnt]];
     fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, two_groups ? row_is_b : (pi.slot > pj.slot), f);
-  }
-  return f;
-}
-template <int K, int PBC>
-__device__ __noinline__ RowFix row_fixup_tile(const DevPbc* __restrict__ pbc_g, const DevSwitch* __restrict__ sw_g,
-                                              const SPos* __restrict__ spos, const double* tx, const double* ty,
-                                              const double* tz, const uint32_t* tslot, const uint16_t* __restrict__ row,
-                                              unsigned cnt, unsigned k, unsigned lane, int two_groups, bool row_is_b) {
-  RowFix f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const SPos pi = spos[k];
-  for (unsigned e = lane; e < cnt; e += 32) {
-    const unsigned j = row[e];
-    fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, tx[j], ty[j], tz[j], two_groups ? row_is_b : (pi.slot > tslot[j]), f);
   }
   return f;
 }

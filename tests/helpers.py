@@ -23,7 +23,7 @@ def water_box(n, density=100.0, seed=SEED, triclinic=False, jitter=None):
 
 
 def oracle_eval(pos, box, style, n_a, n_b, switch, do_pbc=True, nl_mode="none", cutoff=1e30, stride=0,
-                abs_index=None, nthreads=4, list_pos=None, fast_list=False):
+                abs_index=None, nthreads=4, list_pos=None, fast_list=False, list_box=None):
     """value, deriv, virial, pairs from the C oracle for one frame; list built on list_pos (default pos)"""
     pbc = O.make_pbc(np.zeros(9) if box is None else box)
     st = {"pair": O.NL_PAIR, "two": O.NL_TWOLIST, "single": O.NL_SINGLELIST}[style]
@@ -31,7 +31,8 @@ def oracle_eval(pos, box, style, n_a, n_b, switch, do_pbc=True, nl_mode="none", 
     nl = O.NeighborList(st, n_a, n_b, do_pbc=do_pbc, use_cells=use_cells, cutoff=cutoff,
                         stride=(stride if nl_mode != "none" else 0))
     if nl_mode != "none":
-        nl.update(pbc, pos if list_pos is None else list_pos, fast=(fast_list and nl_mode == "classic"))
+        lpbc = pbc if list_box is None else O.make_pbc(list_box)  # the box of the step the list was built at
+        nl.update(lpbc, pos if list_pos is None else list_pos, fast=(fast_list and nl_mode == "classic"))
     v, d, vir, npairs = O.coordination(nl, pbc, do_pbc, switch, pos, abs_index, nthreads=nthreads)
     pairs = nl.pairs() if nl_mode != "none" else None
     return v, d, vir, pairs, npairs
@@ -54,7 +55,7 @@ def oracle_switch_from_kv(kv):
     return O.make_switch(nn=int(kv.get("NN", 6)), mm=int(kv.get("MM", 0)), r0=float(kv["R_0"]), d0=float(kv.get("D_0", 0.0)))
 
 
-def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast_list=False):
+def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast_list=False, list_box=None):
     """evaluate a `c: COORDINATION ...` input line with the C oracle on full-system positions.
     Returns dict(value, deriv (n,3) per requested atom, virial, pairs, atoms)"""
     from plumed2_b200.coordination import parse_atom_list, split_input_line
@@ -71,7 +72,7 @@ def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast
     v, d, vir, pairs, npairs = oracle_eval(pos, box, style, int(ga.size), int(gb.size), sw, do_pbc="NOPBC" not in flags,
                                            nl_mode=mode, cutoff=float(kv.get("NL_CUTOFF", 1e30)),
                                            stride=int(kv.get("NL_STRIDE", 0)), abs_index=atoms, nthreads=nthreads,
-                                           list_pos=lpos, fast_list=fast_list)
+                                           list_pos=lpos, fast_list=fast_list, list_box=list_box)
     return dict(value=v, deriv=d, virial=vir, pairs=pairs, atoms=atoms, npairs=npairs)
 
 

@@ -185,6 +185,44 @@ def test_frozen_list_between_rebuilds(mode, tri):
     c.close()
 
 
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("sw", ["RATIONAL R_0=0.3 D_MAX=0.6", "EXP R_0=0.2 D_MAX=0.6", "GAUSSIAN R_0=0.25 D_0=0.1 D_MAX=0.6"])
+def test_far_parts_of_rows_and_displacement_bound(sw, tri):
+    """NLIST rows are stored as near part + far part (partners beyond D_MAX + skin at the rebuild); the far parts
+    are skipped while 2 x (largest displacement since the rebuild) < skin and visited (trip by trip) otherwise.
+    Small steps, steps beyond the skin, atoms wrapped by a box vector and a box change must all give the
+    frozen-list reference numbers."""
+    n = 3000
+    pos0, box = water_box(n, 100.0, seed=33, triclinic=tri)
+    rng = np.random.default_rng(5)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=1.0 NL_STRIDE=100" % (n, sw)  # skin = 0.1 nm
+    c = P.Coordination.from_input(line)
+    c.prepare(0)
+    c.calculate(pos0, box)
+    direction = rng.standard_normal(pos0.shape)
+    direction /= np.linalg.norm(direction, axis=1)[:, None]
+    step = 0
+    for amp in (0.0, 0.01, 0.04, 0.049, 0.051, 0.09, 0.3, 0.02):
+        step += 1
+        pos = pos0 + amp * direction
+        if amp == 0.04:  # the MD engine may re-wrap atoms into the box: a jump by a box vector is no displacement
+            pos[::7] += box[0]
+            pos[::11] -= box[2]
+        assert not c.prepare(step)
+        c.calculate(pos, box)
+        ref = oracle_from_line(line, pos, box, list_positions=pos0)
+        assert_parity(c, ref, "%s amp %g" % (sw, amp))
+    # a changed box (NPT): the bound is not trusted, far parts are always visited
+    box2 = box * 1.01
+    step += 1
+    assert not c.prepare(step)
+    c.calculate(pos0 * 1.01, box2)
+    ref = oracle_from_line(line, pos0 * 1.01, box2, list_positions=pos0, list_box=box)
+    assert_parity(c, ref, "%s scaled box" % sw)
+    np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+    c.close()
+
+
 def test_exchange_step_rules():
     c = P.Coordination.from_input("c: COORDINATION GROUPA=1-50 R_0=0.3 NLIST NL_CUTOFF=1.0 NL_STRIDE=5")
     assert c.prepare(0) is True
