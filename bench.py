@@ -111,7 +111,11 @@ def pinned_array(L, shape):
 
 # ------------------------------------------------------------------------------------------------
 def reference_cpu(sample_atoms, steps, warmup, threads):
-    """the reference's CPU COORDINATION on a bounded sample; returns dict(value, ms_per_step, ...)"""
+    """the reference's CPU COORDINATION on a bounded sample; returns dict(value, ms_per_step, ...).
+
+    Both list flavours are timed and the FASTER one is reported: NLIST (the keyword our arm uses; the reference
+    can only run it below 32768 atoms and its rebuild is O(N^2), so a 20000-atom sample flatters it) and NLISTCELLS
+    (the only flavour it can run at the headline size; cost linear in N, but it sweeps the 27-cell superset)."""
     os.environ["PLUMED_NUM_THREADS"] = str(threads)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
@@ -121,21 +125,29 @@ def reference_cpu(sample_atoms, steps, warmup, threads):
         return None
     n = sample_atoms
     frames, box = make_frames(n, 4)
-    # numerator: pairs within NL_CUTOFF at the rebuild frame (what NLIST would list)
+    # numerator: pairs within NL_CUTOFF at the rebuild frame (what NLIST lists)
     nl = O.NeighborList(O.NL_SINGLELIST, n, 0, cutoff=NL_CUTOFF, stride=NL_STRIDE)
     nl.update(O.make_pbc(box), frames[0], fast=True)
     pairs = int(nl.size())
-    line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLISTCELLS NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
-    p = R.Plumed(n, [line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"])
-    for s in range(warmup):
-        p.calc(s, frames[s % len(frames)], box)
-    t0 = time.perf_counter()
-    for s in range(warmup, warmup + steps):
-        p.calc(s, frames[s % len(frames)], box)
-    dt = time.perf_counter() - t0
-    p.close()
-    return {"value": pairs * steps / dt, "ms_per_step": 1e3 * dt / steps, "pairs_per_step": pairs, "atoms": n,
-            "keywords": line, "seconds": dt}
+    best = None
+    flavours = {}
+    for flavour in (["NLIST", "NLISTCELLS"] if n <= 32768 else ["NLISTCELLS"]):
+        line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} %s NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, flavour, NL_CUTOFF, NL_STRIDE)
+        p = R.Plumed(n, [line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"])
+        for s in range(warmup):
+            p.calc(s, frames[s % len(frames)], box)
+        t0 = time.perf_counter()
+        for s in range(warmup, warmup + steps):
+            p.calc(s, frames[s % len(frames)], box)
+        dt = time.perf_counter() - t0
+        p.close()
+        r = {"value": pairs * steps / dt, "ms_per_step": 1e3 * dt / steps, "pairs_per_step": pairs, "atoms": n,
+             "keywords": line, "seconds": dt, "flavour": flavour}
+        flavours[flavour] = r["value"]
+        if best is None or r["value"] > best["value"]:
+            best = r
+    best["flavours"] = flavours
+    return best
 
 
 def run_reference(args):
@@ -147,9 +159,11 @@ def run_reference(args):
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
         return
-    sample = ("%d-atom box of the same density/keywords (reference cost is linear in atoms with NLISTCELLS, its only list "
-              "above 32768 atoms); %d warm-up + %d timed steps incl. rebuilds every %d" %
-              (r["atoms"], args.warmup, args.steps, NL_STRIDE))
+    sample = ("%d-atom box of the same density/keywords, faster of the reference's two list flavours (%s; pair evals/s: %s); "
+              "%d warm-up + %d timed steps incl. rebuilds every %d.  The reference cannot run NLIST above 32768 atoms, "
+              "NLISTCELLS costs the same per atom at any size" %
+              (r["atoms"], r["flavour"], ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), args.warmup, args.steps,
+               NL_STRIDE))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -358,8 +372,11 @@ def run_b200(args):
             r = reference_cpu(args.ref_sample_atoms, NL_STRIDE, 0, threads)
             if r is not None:
                 out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
-                                       "sample": "%d-atom box, same density/keywords with NLISTCELLS, one NL cycle "
-                                                 "(%d steps, 1 rebuild), %.1f s" % (r["atoms"], NL_STRIDE, r["seconds"])}
+                                       "sample": "%d-atom box, same density/keywords, faster of NLIST / NLISTCELLS (%s; %s), "
+                                                 "one NL cycle (%d steps, 1 rebuild), %.1f s" %
+                                                 (r["atoms"], r["flavour"],
+                                                  ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), NL_STRIDE,
+                                                  r["seconds"])}
             else:
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
                                        "sample": "oracle/_ref not present on this box"}
