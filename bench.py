@@ -136,13 +136,14 @@ def reference_cpu(sample_atoms, steps, warmup, threads):
         p = R.Plumed(n, [line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"])
         for s in range(warmup):
             p.calc(s, frames[s % len(frames)], box)
+        nsteps = steps * (3 if flavour == "NLIST" else 1)  # NLIST steps are ~8x cheaper: time three times as many
         t0 = time.perf_counter()
-        for s in range(warmup, warmup + steps):
+        for s in range(warmup, warmup + nsteps):
             p.calc(s, frames[s % len(frames)], box)
         dt = time.perf_counter() - t0
         p.close()
-        r = {"value": pairs * steps / dt, "ms_per_step": 1e3 * dt / steps, "pairs_per_step": pairs, "atoms": n,
-             "keywords": line, "seconds": dt, "flavour": flavour}
+        r = {"value": pairs * nsteps / dt, "ms_per_step": 1e3 * dt / nsteps, "pairs_per_step": pairs, "atoms": n,
+             "keywords": line, "seconds": dt, "flavour": flavour, "steps": nsteps}
         flavours[flavour] = r["value"]
         if best is None or r["value"] > best["value"]:
             best = r
@@ -373,10 +374,10 @@ def run_b200(args):
             if r is not None:
                 out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
                                        "sample": "%d-atom box, same density/keywords, faster of NLIST / NLISTCELLS (%s; %s), "
-                                                 "one NL cycle (%d steps, 1 rebuild), %.1f s" %
+                                                 "%d steps with a rebuild every %d, %.1f s" %
                                                  (r["atoms"], r["flavour"],
-                                                  ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), NL_STRIDE,
-                                                  r["seconds"])}
+                                                  ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), r["steps"],
+                                                  NL_STRIDE, r["seconds"])}
             else:
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
                                        "sample": "oracle/_ref not present on this box"}

@@ -323,11 +323,17 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
   lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
 }
 
+// FP32 constants of the candidate search
+struct SearchF32 {
+  float box[9];        // box rows
+  float c2_hi, c2_lo;  // cutoff^2 * (1 +- band): outside -> decided in FP32, inside -> exact FP64 test
+};
+
 template <bool FILL, bool CAPPED>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
-                  DevPbc box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
+                  SearchF32 f, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                   unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
                   uint32_t* __restrict__ nbr, unsigned row_cap, unsigned* __restrict__ cap_info /*[0] max count, [1] overflow*/,
                   float far2, uint32_t* __restrict__ row_far_off, uint32_t* __restrict__ row_far_cnt) {
@@ -342,7 +348,8 @@ __global__ void __launch_bounds__(256, 4)
   int c[3], lo[3], hi[3];
   cell_coords(g, (int)scell[k], c);
   stencil_bounds(g, c, lo, hi);
-  const float c2_hi = (float)(cutoff2 * (1.0 + band_rel)), c2_lo = (float)(cutoff2 * (1.0 - band_rel));
+  const float c2_hi = f.c2_hi, c2_lo = f.c2_lo;  // FP32 constants come ready from the host: converting them here costs
+                                                  // XU-pipe instructions in every stencil column
 
   // ---- range table, one (y,z) stencil column per lane (<= 25): its x-run is one contiguous sorted range, or
   // two when it wraps around the box.  All the dependent cstart/ccount loads of a row are in flight at once.
@@ -374,9 +381,9 @@ __global__ void __launch_bounds__(256, 4)
       wxB = wrap_count(x, g.n[0]);
     }
   }
-  const float ax = (float)box.box[0], ay = (float)box.box[1], az = (float)box.box[2];
-  const float bx = (float)box.box[3], by = (float)box.box[4], bz = (float)box.box[5];
-  const float cx = (float)box.box[6], cy = (float)box.box[7], cz = (float)box.box[8];
+  const float ax = f.box[0], ay = f.box[1], az = f.box[2];
+  const float bx = f.box[3], by = f.box[4], bz = f.box[5];
+  const float cx = f.box[6], cy = f.box[7], cz = f.box[8];
 
   unsigned total = 0, total_far = 0;
   // CAPPED: single-pass build into fixed-capacity rows (capacity learnt from the previous rebuild)
@@ -643,7 +650,11 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, cons
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
-#define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, box, cutoff2, band_rel, n_a, two_groups, row_begin, row_end, \
+  SearchF32 f;
+  for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
+  f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
+  f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
+#define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
   if (mode == 0) k_nl_rows_f32<false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
