@@ -63,6 +63,11 @@ enum {
   B200COORD_SW_LEPTON, B200COORD_SW_NOT_INITIALIZED
 };
 
+/* pairing functions of COORDINATION's siblings on CoordinationBase, carried in the same struct:
+ * DHENERGY (src/colvar/DHEnergy.cpp:130-143): s = exp(-k r)/r * constant/epsilon * q_i q_j, dfunc = -(k + 1/r) s / r;
+ * beta = k, lambda = constant/epsilon, no D_MAX; needs b200coord_set_charges */
+enum { B200COORD_PAIR_DHENERGY = 32 };
+
 /* mirrors switchContainers::Data (src/tools/SwitchingFunction.h:58-94) */
 typedef struct b200coord_switch {
   int type;
@@ -117,6 +122,10 @@ int b200coord_abi_version(void);
 int b200coord_switch_parse(const char* definition, b200coord_switch* out, char* err, size_t errlen);
 /* R_0= NN= MM= D_0= keyword form: automatic D_MAX and stretch (SwitchingFunction.cpp:1176-1184) */
 int b200coord_switch_rational(int nn, int mm, double r0, double d0, b200coord_switch* out);
+/* DHENERGY constants from its keywords I, TEMP, EPSILON and the unit factors of the host code (all 1 for PLUMED's
+ * default kJ/mol, nm, e), DHEnergy.cpp:104-128 */
+int b200coord_pairing_dhenergy(double ionic_strength, double temp, double epsilon, double energy_unit, double length_unit,
+                               double charge_unit, b200coord_switch* out);
 /* text like SwitchingFunction::description() for the action's log */
 int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen);
 
@@ -125,6 +134,10 @@ int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t bufl
  * absolute index, CoordinationBase.cpp:183) */
 int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, const unsigned* abs_index,
                      b200coord_ctx** out);
+/* charges of the n_group_a+n_group_b atoms in GROUPA-then-GROUPB order (ActionAtomistic::getCharge, used by
+ * DHEnergy::pairing); required before calculate when the pairing is B200COORD_PAIR_DHENERGY; may be called again
+ * whenever the charges change */
+int b200coord_set_charges(b200coord_ctx* ctx, const double* charges);
 void b200coord_destroy(b200coord_ctx* ctx);
 /* last error text of this context (ctx==NULL: of the last failed create/parse in this thread) */
 const char* b200coord_last_error(const b200coord_ctx* ctx);

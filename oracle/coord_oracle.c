@@ -1067,9 +1067,48 @@ void orc_nl_prepare(const orc_nl* nl, long step, int exchange_step, int* firstti
 
 /* ------------------------------------------------------------------ CoordinationBase::calculate */
 /* colvar/CoordinationBase.cpp:142-232 */
+/* DHEnergy::pairing, colvar/DHEnergy.cpp:130-143 (beta = k, lambda = constant, ref = epsilon) */
+static double dhenergy_pairing(const orc_switch* s, double distance2, double qi, double qj, double* dfunc) {
+  double distance = sqrt(distance2);
+  double invdistance = 1.0 / distance;
+  double tmp = exp(-s->beta * distance) * invdistance * s->lambda * qi * qj / s->ref;
+  double dtmp = -(s->beta + invdistance) * tmp;
+  *dfunc = dtmp * invdistance;
+  return tmp;
+}
+
+/* DHEnergy::DHEnergy, colvar/DHEnergy.cpp:104-128, default units (energy kJ/mol, length nm, charge e) */
+void orc_dhenergy_setup(orc_switch* sw, double I, double T, double epsilon) {
+  memset(sw, 0, sizeof(*sw));
+  sw->type = ORC_PAIR_DHENERGY;
+  sw->lambda = 138.935458111;                              /* constant */
+  sw->beta = sqrt(I / (epsilon * T)) * 502.903741125;      /* k */
+  sw->ref = epsilon;
+}
+
+static size_t coordination_base_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
+                                          const double* pos, const unsigned* abs_index, const double* charges, size_t n,
+                                          unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv,
+                                          double* virial);
+
+size_t orc_dhenergy_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,
+                              const unsigned* abs_index, const double* charges, size_t n, unsigned rank, unsigned nranks,
+                              int nthreads, double* value, double* deriv, double* virial) {
+  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, charges, n, rank, nranks, nthreads, value, deriv,
+                                     virial);
+}
+
 size_t orc_coordination_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
                                   const double* pos, const unsigned* abs_index, size_t n, unsigned rank,
                                   unsigned nranks, int nthreads, double* value, double* deriv, double* virial) {
+  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, NULL, n, rank, nranks, nthreads, value, deriv,
+                                     virial);
+}
+
+static size_t coordination_base_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
+                                          const double* pos, const unsigned* abs_index, const double* charges, size_t n,
+                                          unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv,
+                                          double* virial) {
   double ncoord = 0.;
   memset(deriv, 0, sizeof(double) * 3 * n);
   memset(virial, 0, sizeof(double) * 9);
@@ -1112,7 +1151,10 @@ size_t orc_coordination_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_p
       else
         for (int k = 0; k < 3; k++) distance[k] = pos[3 * (size_t)i1 + k] - pos[3 * (size_t)i0 + k];
       double dfunc = 0.;
-      ncoord += orc_switch_calculate_sqr(sw, mod2(distance), &dfunc); /* Coordination::pairing */
+      if (sw->type == ORC_PAIR_DHENERGY)
+        ncoord += dhenergy_pairing(sw, mod2(distance), charges[i0], charges[i1], &dfunc); /* DHEnergy::pairing */
+      else
+        ncoord += orc_switch_calculate_sqr(sw, mod2(distance), &dfunc); /* Coordination::pairing */
       double dd[3] = {dfunc * distance[0], dfunc * distance[1], dfunc * distance[2]};
       for (int a = 0; a < 3; a++) {
         mderiv[3 * (size_t)i0 + a] -= dd[a];

@@ -109,6 +109,13 @@ void orc_nl_prepare(const orc_nl* nl, long step, int exchange_step, int* firstti
  * pos: n*3 AoS; abs_index: n absolute atom indices (self-pair skip :183); rank/nranks: MPI stride split
  * :152-170 (results are this rank's partial sums; nranks=1 -> full result); nthreads: OpenMP threads.
  * deriv: n*3, virial: 9 (row-major), value: 1.  Returns pairs iterated. */
+/* DHENERGY (colvar/DHEnergy.cpp): the same CoordinationBase loop with the Debye-Hueckel pairing; k and constant as
+ * computed by its constructor (:119-120), charges per requested atom (GROUPA then GROUPB) */
+#define ORC_PAIR_DHENERGY 32
+void orc_dhenergy_setup(orc_switch* sw, double I, double T, double epsilon); /* default PLUMED units */
+size_t orc_dhenergy_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,
+                              const unsigned* abs_index, const double* charges, size_t n, unsigned rank, unsigned nranks,
+                              int nthreads, double* value, double* deriv, double* virial);
 size_t orc_coordination_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
                                   const double* pos, const unsigned* abs_index, size_t n,
                                   unsigned rank, unsigned nranks, int nthreads,

@@ -90,6 +90,10 @@ def lib():
         L.orc_coordination_calculate.restype = C.c_size_t
         L.orc_coordination_calculate.argtypes = [C.c_void_p, C.POINTER(Pbc), C.c_int, C.POINTER(Switch), dp, up,
                                                  C.c_size_t, C.c_uint, C.c_uint, C.c_int, dp, dp, dp]
+        L.orc_dhenergy_setup.argtypes = [C.POINTER(Switch), C.c_double, C.c_double, C.c_double]
+        L.orc_dhenergy_calculate.restype = C.c_size_t
+        L.orc_dhenergy_calculate.argtypes = [C.c_void_p, C.POINTER(Pbc), C.c_int, C.POINTER(Switch), dp, up, dp,
+                                             C.c_size_t, C.c_uint, C.c_uint, C.c_int, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -220,8 +224,16 @@ class NeighborList:
         return self.invalidate
 
 
-def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nthreads=1):
-    """CoordinationBase::calculate: returns value, deriv (n,3), virial (3,3), pairs iterated"""
+def make_dhenergy(I, T=300.0, epsilon=80.0):
+    """DHENERGY pairing constants (DHEnergy.cpp:104-128, default units)"""
+    s = Switch()
+    lib().orc_dhenergy_setup(C.byref(s), float(I), float(T), float(epsilon))
+    return s
+
+
+def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nthreads=1, charges=None):
+    """CoordinationBase::calculate: returns value, deriv (n,3), virial (3,3), pairs iterated.
+    charges: per requested atom, for a DHENERGY pairing (make_dhenergy)"""
     pos = np.ascontiguousarray(pos, dtype=np.float64)
     n = pos.shape[0]
     if abs_index is None:
@@ -230,7 +242,13 @@ def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nth
     val = C.c_double(0)
     deriv = np.zeros((n, 3))
     vir = np.zeros(9)
-    npairs = lib().orc_coordination_calculate(nl.h, C.byref(pbc), int(do_pbc), C.byref(sw), _dp(pos),
-                                              _up(abs_index), n, rank, nranks, nthreads, C.byref(val),
-                                              _dp(deriv), _dp(vir))
+    if charges is not None:
+        q = np.ascontiguousarray(charges, dtype=np.float64)
+        assert q.shape[0] == n
+        npairs = lib().orc_dhenergy_calculate(nl.h, C.byref(pbc), int(do_pbc), C.byref(sw), _dp(pos), _up(abs_index),
+                                              _dp(q), n, rank, nranks, nthreads, C.byref(val), _dp(deriv), _dp(vir))
+    else:
+        npairs = lib().orc_coordination_calculate(nl.h, C.byref(pbc), int(do_pbc), C.byref(sw), _dp(pos),
+                                                  _up(abs_index), n, rank, nranks, nthreads, C.byref(val),
+                                                  _dp(deriv), _dp(vir))
     return val.value, deriv, vir.reshape(3, 3), npairs

@@ -30,7 +30,8 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_device_alloc", "b200coord_device_free", "b200coord_memcpy_h2d", "b200coord_memcpy_d2h",
             "b200coord_device_synchronize", "b200coord_enqueue_device", "b200coord_stream_mark",
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
-            "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach"]
+            "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach",
+            "b200coord_pairing_dhenergy", "b200coord_set_charges"]
 
 
 class B200CoordError(RuntimeError):
@@ -80,6 +81,8 @@ def lib():
     L.b200coord_switch_parse.argtypes = [C.c_char_p, C.POINTER(Switch), C.c_char_p, C.c_size_t]
     L.b200coord_switch_rational.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Switch)]
     L.b200coord_switch_describe.argtypes = [C.POINTER(Switch), C.c_char_p, C.c_size_t]
+    L.b200coord_pairing_dhenergy.argtypes = [C.c_double] * 6 + [C.POINTER(Switch)]
+    L.b200coord_set_charges.argtypes = [C.c_void_p, dp]
     L.b200coord_create.argtypes = [C.POINTER(Config), C.POINTER(Switch), C.POINTER(C.c_uint), C.POINTER(C.c_void_p)]
     L.b200coord_destroy.argtypes = [C.c_void_p]
     L.b200coord_destroy.restype = None
@@ -133,6 +136,13 @@ def switch_parse(definition):
 def switch_rational(nn, mm, r0, d0):
     s = Switch()
     check(lib().b200coord_switch_rational(int(nn), int(mm), float(r0), float(d0), C.byref(s)))
+    return s
+
+
+def pairing_dhenergy(ionic_strength, temp, epsilon, energy_unit=1.0, length_unit=1.0, charge_unit=1.0):
+    s = Switch()
+    check(lib().b200coord_pairing_dhenergy(float(ionic_strength), float(temp), float(epsilon), float(energy_unit),
+                                           float(length_unit), float(charge_unit), C.byref(s)))
     return s
 
 

@@ -105,7 +105,9 @@ class Coordination:
 
     def __init__(self, GROUPA, GROUPB=None, PAIR=False, NLIST=False, NLISTCELLS=False, NL_CUTOFF=None,
                  NL_STRIDE=None, NOPBC=False, SERIAL=False, SWITCH=None, R_0=None, NN=6, MM=0, D_0=0.0, D_MAX=None,
-                 label="c", device=-1, rank=0, nranks=1, precision=capi.FP64):
+                 label="c", device=-1, rank=0, nranks=1, precision=capi.FP64, DHENERGY=None):
+        """DHENERGY: None for COORDINATION, else dict(I=..., TEMP=..., EPSILON=...) -> the sibling action DHENERGY
+        (src/colvar/DHEnergy.cpp): same groups / lists, Debye-Hueckel pairing, needs set_charges()"""
         self.label = label
         ga = parse_atom_list(GROUPA)
         gb = parse_atom_list(GROUPB)
@@ -129,7 +131,10 @@ class Coordination:
             raise PlumedInputError("when using PAIR option, the two groups should have the same number of elements\n"
                                    "the groups you specified have size %d and %d" % (ga.size, gb.size))
         # --- Coordination ctor, Coordination.cpp:128-157 (+ cudaCoord's top-level D_MAX rewrite)
-        if SWITCH:
+        if DHENERGY is not None:  # DHEnergy ctor, DHEnergy.cpp:104-128 (default units)
+            self.switch = capi.pairing_dhenergy(float(DHENERGY["I"]), float(DHENERGY.get("TEMP", 300.0)),
+                                                float(DHENERGY["EPSILON"]))
+        elif SWITCH:
             try:
                 self.switch = capi.switch_parse(str(SWITCH))
             except capi.B200CoordError as e:
@@ -177,8 +182,25 @@ class Coordination:
     @classmethod
     def from_input(cls, line, **kw):
         label, action, kv, flags = split_input_line(line)
+        if action == "DHENERGY":  # DHEnergy::registerKeywords, DHEnergy.cpp:77-90: CoordinationBase + I, TEMP, EPSILON
+            allowed = {"GROUPA", "GROUPB", "NL_CUTOFF", "NL_STRIDE", "I", "TEMP", "EPSILON"}
+            for k in kv:
+                if k not in allowed:
+                    raise PlumedInputError("cannot understand the following words from the input line : " + k)
+            for f in flags:
+                if f not in _FLAGS:
+                    raise PlumedInputError("cannot understand the following words from the input line : " + f)
+            if "GROUPA" not in kv:
+                raise PlumedInputError("GROUPA: no atoms specified")
+            args = dict(GROUPA=kv["GROUPA"], GROUPB=kv.get("GROUPB"), PAIR="PAIR" in flags, NLIST="NLIST" in flags,
+                        NLISTCELLS="NLISTCELLS" in flags, NL_CUTOFF=kv.get("NL_CUTOFF"), NL_STRIDE=kv.get("NL_STRIDE"),
+                        NOPBC="NOPBC" in flags, SERIAL="SERIAL" in flags, label=label or "c",
+                        DHENERGY=dict(I=float(kv.get("I", 1.0)), TEMP=float(kv.get("TEMP", 300.0)),
+                                      EPSILON=float(kv.get("EPSILON", 80.0))))
+            args.update(kw)
+            return cls(**args)
         if action != "COORDINATION":
-            raise PlumedInputError("this mirror only implements COORDINATION, got " + action)
+            raise PlumedInputError("this mirror only implements COORDINATION and DHENERGY, got " + action)
         for k in kv:
             if k not in _KEYS:
                 raise PlumedInputError("cannot understand the following words from the input line : " + k)
@@ -201,6 +223,11 @@ class Coordination:
         flag = C.c_int(0)
         capi.check(self._L.b200coord_prepare(self._ctx, int(step), int(bool(exchange_step)), C.byref(flag)), self._ctx)
         return bool(flag.value)
+
+    def set_charges(self, charges):
+        """charges of ALL system atoms (ActionAtomistic::getCharge); required for DHENERGY"""
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64)[self.atoms])
+        capi.check(self._L.b200coord_set_charges(self._ctx, q.ctypes.data_as(C.POINTER(C.c_double))), self._ctx)
 
     def _set_box(self, box):
         b = self._zero_box if box is None else np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(9))

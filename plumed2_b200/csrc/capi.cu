@@ -128,6 +128,8 @@ struct b200coord_ctx {
   bool f32_search = false;
   double band_rel = 0.0;
   unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
+  DevBuf<double> d_q, d_sq;    // charges in slot order / sorted order (DHENERGY)
+  bool have_charges = false, sq_valid = false;
   DevBuf<double> d_bpos;       // positions the list was built from (sorted order), for the displacement bound
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
@@ -372,6 +374,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
               c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->d_bsum.p, c->st);
   c->stats.kernel_launches += 4;
   c->sorted_valid = true;
+  c->sq_valid = false;  // new permutation
   if (mode == B200COORD_NL_CLASSIC) {
     launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
     const unsigned rows = c->row_end - c->row_begin;
@@ -496,6 +499,8 @@ int combine_ranks(b200coord_ctx* c) {
 // the whole per-step device pipeline on c->st; d_pos device positions, result left in c->d_out
 int run_device(b200coord_ctx* c, const double* d_pos) {
   if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
+  if (c->dsw.type == B200COORD_PAIR_DHENERGY && !c->have_charges)
+    return fail(c, B200COORD_ERR_STATE, "b200coord_set_charges must be called before calculate (DHENERGY)");
   const bool need_rebuild = !c->list_valid || (c->cfg.nl_mode != B200COORD_NL_NONE && c->invalidate);
   if (need_rebuild) {
     int rc = rebuild(c, d_pos);
@@ -520,7 +525,7 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     CU(c, c->d_partials.reserve((size_t)kPartialStride * ((pe - pb) / 256 + 2)));
     CU(c, cudaEventRecord(c->ev[2], c->st));
     CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
-    nblocks = launch_sweep_pairs(d_pos, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
+    nblocks = launch_sweep_pairs(d_pos, c->d_q.p, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
                                  c->n_a, pb, pe, c->dpbc, c->dsw, c->d_out.p, c->d_partials.p, c->d_u64.p + 1, c->st);
     CU(c, cudaEventRecord(c->ev[3], c->st));
     weight = 1.0;
@@ -539,6 +544,14 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     SweepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.spos = c->d_spos.p;
+    if (c->dsw.type == B200COORD_PAIR_DHENERGY) {
+      if (!c->sq_valid) {
+        CU(c, c->d_sq.reserve(c->n));
+        launch_gather_charges(c->d_q.p, c->d_perm.p, c->n, c->d_sq.p, c->st);
+        c->sq_valid = true;
+      }
+      a.sq = c->d_sq.p;
+    }
     a.n_a = c->n_a;
     a.two_groups = c->two_groups;
     a.check_abs = c->check_abs;
@@ -661,6 +674,15 @@ int b200coord_switch_rational(int nn, int mm, double r0, double d0, b200coord_sw
   return B200COORD_OK;
 }
 
+int b200coord_pairing_dhenergy(double ionic_strength, double temp, double epsilon, double energy_unit, double length_unit,
+                               double charge_unit, b200coord_switch* out) {
+  if (!out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  if (!(epsilon > 0.0) || !(temp > 0.0) || !(ionic_strength >= 0.0) || !(energy_unit > 0.0) || !(length_unit > 0.0))
+    return fail(nullptr, B200COORD_ERR_INVALID, "DHENERGY needs EPSILON > 0, TEMP > 0, I >= 0");
+  dhenergy_pairing(ionic_strength, temp, epsilon, energy_unit, length_unit, charge_unit, *out);
+  return B200COORD_OK;
+}
+
 int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen) {
   if (!sw || !buf || !buflen) return B200COORD_ERR_INVALID;
   std::snprintf(buf, buflen, "%s", describe_switch(*sw).c_str());
@@ -687,7 +709,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
                 "when using PAIR option, the two groups should have the same number of elements");
   if (cfg->style == B200COORD_STYLE_SINGLELIST && cfg->n_group_b != 0)
     return fail(nullptr, B200COORD_ERR_INVALID, "SINGLELIST style takes GROUPA only");
-  if (sw->type < 0 || sw->type >= B200COORD_SW_LEPTON)
+  if ((sw->type < 0 || sw->type >= B200COORD_SW_LEPTON) && sw->type != B200COORD_PAIR_DHENERGY)
     return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "switching function is not available on the GPU");
   if (cfg->precision != B200COORD_FP64)
     return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "only the FP64 sweep is built in this version");
@@ -805,6 +827,17 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   return B200COORD_OK;
 }
 
+int b200coord_set_charges(b200coord_ctx* c, const double* charges) {
+  if (!c || !charges) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, c->d_q.reserve(c->n));
+  CU(c, cudaMemcpyAsync(c->d_q.p, charges, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));  // the caller's array may go away
+  c->have_charges = true;
+  c->sq_valid = false;
+  return B200COORD_OK;
+}
+
 void b200coord_destroy(b200coord_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -816,7 +849,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_q.release(); c->d_sq.release();
   if (c->peer_mode)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)

@@ -348,6 +348,18 @@ double switch_value_host(const b200coord_switch& s, double r) {  // baseSwitch::
   return s.stretch + s.shift;
 }
 
+void dhenergy_pairing(double I, double T, double epsilon, double energy_unit, double length_unit, double charge_unit,
+                      b200coord_switch& out) {
+  std::memset(&out, 0, sizeof(out));
+  out.type = B200COORD_PAIR_DHENERGY;
+  out.d0 = 0.0;
+  out.dmax = DBL_MAX;  // no cutoff: every listed pair contributes
+  out.dmax_2 = DBL_MAX;
+  const double constant = 138.935458111 / energy_unit / length_unit * charge_unit * charge_unit;  // :119
+  out.beta = std::sqrt(I / (epsilon * T)) * 502.903741125 * length_unit;                           // :120 (k)
+  out.lambda = constant / epsilon;
+}
+
 void rational_switch(int nn, int mm, double r0, double d0, b200coord_switch& out) {
   if (mm == 0) mm = 2 * nn;
   const double dmax = d0 + r0 * std::pow(0.00001, 1. / (nn - mm));
@@ -442,6 +454,10 @@ std::string describe_switch(const b200coord_switch& s) {
                                 "rational", "rational", "rational", "rational", "exponential", "gaussian",
                                 "fastgaussian", "smap", "cubic", "tanh", "cosinus", "nativeq", "lepton", "unset"};
   std::ostringstream os;
+  if (s.type == B200COORD_PAIR_DHENERGY) {
+    os << "Debye-Hueckel pairing: screening length " << (s.beta > 0.0 ? 1.0 / s.beta : INFINITY) << ", constant/epsilon " << s.lambda;
+    return os.str();
+  }
   const int t = (s.type >= 0 && s.type <= B200COORD_SW_NOT_INITIALIZED) ? s.type : B200COORD_SW_NOT_INITIALIZED;
   os << 1.0 / s.invr0 << ".  Using " << names[t] << " switching function with parameters d0=" << s.d0;
   const int fp = fixed_power(s.type);

@@ -601,6 +601,15 @@ void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_
                    cudaStream_t st) {
   k_gather_sorted<0, 0><<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, spos, nullptr, DevPbc{}, nullptr);
 }
+__global__ void k_gather_charges(const double* __restrict__ q, const uint32_t* __restrict__ perm, unsigned n,
+                                 double* __restrict__ sq) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) sq[k] = q[perm[k]];
+}
+void launch_gather_charges(const double* charges, const uint32_t* perm, unsigned n, double* sq, cudaStream_t st) {
+  if (n) k_gather_charges<<<(n + 255) / 256, 256, 0, st>>>(charges, perm, n, sq);
+}
+
 void launch_gather_track(int track, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
                          SPos* spos, double* bpos, const DevPbc& pbc, unsigned long long* disp2, cudaStream_t st) {
   const unsigned blocks = (n + 255) / 256;

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     const unsigned cnt_near = a.row_count[k - a.row_begin], cnt_far = a.row_far_cnt[k - a.row_begin];
     const unsigned far_off = a.row_far_off[k - a.row_begin];
     const bool row_is_b = (k >= a.n_a);
+    const double qi = (K == K_DH) ? __ldg(a.sq + k) : 1.0;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     bool near = false;
     // Two pairs per lane and trip, evaluated as two independent straight-line chains: one pair is a ~25-deep
@@ -58,14 +59,26 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       load_rec(a.spos + jb, pb);
       ja = (e + 64 < cnt) ? __ldg(row + e + 64) : 0u;
       jb = (e + 96 < cnt) ? __ldg(row + e + 96) : 0u;
+      uint32_t ia = 0u, ib = 0u;  // entries of the records in flight (DHENERGY looks their charges up)
       for (unsigned e0 = 0; e0 < cnt; e0 += 64, e += 64) {  // warp-uniform trip count: the far part votes
         const RecBuf ca = pa, cb = pb;
+        double qqa = 1.0, qqb = 1.0;
+        if (K == K_DH) {
+          if (e0 == 0u) {
+            ia = (e < cnt) ? __ldg(row + e) : 0u;
+            ib = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
+          }
+          qqa = qi * __ldg(a.sq + ia);
+          qqb = qi * __ldg(a.sq + ib);
+          ia = ja;
+          ib = jb;
+        }
         load_rec(a.spos + ja, pa);
         load_rec(a.spos + jb, pb);
         ja = (e + 128 < cnt) ? __ldg(row + e + 128) : 0u;
         jb = (e + 160 < cnt) ? __ldg(row + e + 160) : 0u;
         pair_term2<K, PBC, ACC, FAR>(pbc, sw, near, pi.x, pi.y, pi.z, wi, a.two_groups, row_is_b, ca, cb, e < cnt,
-                                     e + 32 < cnt, a.far_skip2, fx, fy, fz, acc);
+                                     e + 32 < cnt, a.far_skip2, fx, fy, fz, acc, qqa, qqb);
       }
     };
     if (cnt_near) part(a.nbr + base, cnt_near, std::false_type{});
@@ -136,6 +149,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     const unsigned other = a.two_groups ? (1u - my_grp) : 0u;
     int c[3];
     cell_coords(g, (int)a.scell[k], c);
+    const double qi = (K == K_DH) ? __ldg(a.sq + k) : 1.0;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     unsigned cnt = 0;
     bool unused_near = false;
@@ -147,7 +161,9 @@ __global__ void __launch_bounds__(kSweepThreads)
         const SPos pj = load_spos(a.spos + j);
         const bool valid = (j != k) && (!a.check_abs || pj.abs_index != pi.abs_index);
         const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
-        if (valid) pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
+        if (valid)
+          pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc,
+                                       (K == K_DH) ? qi * __ldg(a.sq + j) : 1.0);
       }
     });
     fx = warp_sum(fx);
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(kSweepThreads)
 // PAIR style: pair k = (k, k+n_a) (NeighborList.cpp:150-152); each atom slot occurs in exactly one pair
 template <int K, int PBC>
 __global__ void __launch_bounds__(kSweepThreads)
-    k_sweep_pairs(const double* __restrict__ pos, const uint32_t* __restrict__ abs_index, const uint8_t* __restrict__ active,
+    k_sweep_pairs(const double* __restrict__ pos, const double* __restrict__ charges, const uint32_t* __restrict__ abs_index, const uint8_t* __restrict__ active,
                   unsigned n_a, unsigned pair_begin, unsigned pair_end, DevPbc pbc, DevSwitch sw, double* __restrict__ out,
                   double* partials, unsigned long long* evals_out) {
   LaneAcc acc = {0, 0, 0, 0, 0, 0, 0};
@@ -201,6 +217,11 @@ __global__ void __launch_bounds__(kSweepThreads)
       double s, df;
       const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
       eval_switch<K>(sw, r2, s, df);
+      if (K == K_DH) {
+        const double qq = charges[k] * charges[k + n_a];
+        s *= qq;
+        df *= qq;
+      }
       if (on_boundary(sw, r2)) {  // one pair per thread: the exact evaluation is simply done in place
         const ExactPair o = exact_pair<K>(pbc, sw, pos[ia], pos[ia + 1], pos[ia + 2], pj.x, pj.y, pj.z, false);
         dx = o.dx;
@@ -333,6 +354,7 @@ static int run_sweep_kind(const SweepArgs& a, const DevPbc& pbc, const DevSwitch
     case K_TANH: return run_sweep_pbc<K_TANH, LIST>(a, pbc, sw, st);
     case K_COS: return run_sweep_pbc<K_COS, LIST>(a, pbc, sw, st);
     case K_NATIVEQ: return run_sweep_pbc<K_NATIVEQ, LIST>(a, pbc, sw, st);
+    case K_DH: return run_sweep_pbc<K_DH, LIST>(a, pbc, sw, st);
     default: return -1;
   }
 }
@@ -345,24 +367,24 @@ int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& s
 }
 
 template <int K>
-static int run_pairs(const double* pos, const uint32_t* abs_index, const uint8_t* active, unsigned n_a, unsigned pb,
+static int run_pairs(const double* pos, const double* charges, const uint32_t* abs_index, const uint8_t* active, unsigned n_a, unsigned pb,
                      unsigned pe, const DevPbc& pbc, const DevSwitch& sw, double* out, double* partials,
                      unsigned long long* evals, cudaStream_t st) {
   const int nblocks = (int)((pe - pb + kSweepThreads - 1) / kSweepThreads);
   if (nblocks == 0) return 0;
   switch (pbc.type) {
-    case 0: k_sweep_pairs<K, 0><<<nblocks, kSweepThreads, 0, st>>>(pos, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
-    case 1: k_sweep_pairs<K, 1><<<nblocks, kSweepThreads, 0, st>>>(pos, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
-    default: k_sweep_pairs<K, 2><<<nblocks, kSweepThreads, 0, st>>>(pos, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    case 0: k_sweep_pairs<K, 0><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    case 1: k_sweep_pairs<K, 1><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    default: k_sweep_pairs<K, 2><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
   }
   return nblocks;
 }
 
-int launch_sweep_pairs(const double* pos, const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
+int launch_sweep_pairs(const double* pos, const double* charges, const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
                        unsigned pair_begin, unsigned pair_end, const DevPbc& pbc, const DevSwitch& sw, double* out,
                        double* partials, unsigned long long* evals, cudaStream_t st) {
 #define B200_PAIR_CASE(KK) \
-  case KK: return run_pairs<KK>(pos, abs_index, active, n_a, pair_begin, pair_end, pbc, sw, out, partials, evals, st);
+  case KK: return run_pairs<KK>(pos, charges, abs_index, active, n_a, pair_begin, pair_end, pbc, sw, out, partials, evals, st);
   switch (kind_of(sw.type)) {
     B200_PAIR_CASE(K_FIX6)
     B200_PAIR_CASE(K_FIXN)
@@ -376,6 +398,7 @@ int launch_sweep_pairs(const double* pos, const uint32_t* abs_index, const uint8
     B200_PAIR_CASE(K_TANH)
     B200_PAIR_CASE(K_COS)
     B200_PAIR_CASE(K_NATIVEQ)
+    B200_PAIR_CASE(K_DH)
     default: return -1;
   }
 #undef B200_PAIR_CASE

@@ -19,6 +19,7 @@ enum SwKind {
   K_TANH,
   K_COS,
   K_NATIVEQ,
+  K_DH,         // DHENERGY pairing (src/colvar/DHEnergy.cpp:130-143): screened Coulomb, scaled by q_i q_j
   K_COUNT
 };
 
@@ -36,6 +37,7 @@ static inline int kind_of(int type) {
     case 15: return K_TANH;
     case 16: return K_COS;
     case 17: return K_NATIVEQ;
+    case 32: return K_DH;  // B200COORD_PAIR_DHENERGY
     default: return -1;
   }
 }
@@ -107,7 +109,11 @@ __device__ __forceinline__ void eval_switch(const DevSwitch& p, double r2, doubl
       rinv = (r2 > 0.0) ? fast_rsqrt(r2) : 0.0;
       r = r2 * rinv;
     }
-    if (K == K_NATIVEQ) {  // nativeqSwitch::calculate :524-549
+    if (K == K_DH) {  // DHEnergy::pairing: tmp = exp(-k r)/r * constant/epsilon [* q_i q_j: caller]; dfunc = -(k+1/r) tmp / r
+      const double tmp = exp(-p.beta * r) * rinv * p.lambda;
+      s = tmp;
+      df = -(p.beta + rinv) * tmp * rinv;
+    } else if (K == K_NATIVEQ) {  // nativeqSwitch::calculate :524-549
       if (r <= p.dmax) {
         double res = 1.0;
         if (r > p.d0) {
@@ -213,13 +219,17 @@ struct LaneAcc {
 template <int K, int PBC, bool ACC, bool INLINE_EXACT = false>
 __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw, bool& near, double xi, double yi,
                                           double zi, const SPos& pj, bool flip, double& fx, double& fy, double& fz,
-                                          LaneAcc& acc) {
+                                          LaneAcc& acc, double qq = 1.0) {
   const unsigned sgn = flip ? 0x80000000u : 0u;
   double dx = flip_sign(pj.x - xi, sgn), dy = flip_sign(pj.y - yi, sgn), dz = flip_sign(pj.z - zi, sgn);
   min_image_fast<PBC>(pbc, dx, dy, dz);
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
   double s, df;
   eval_switch<K>(sw, r2, s, df);
+  if (K == K_DH) {  // product of the two charges (DHENERGY only; no D_MAX / D_0 boundaries there)
+    s *= qq;
+    df *= qq;
+  }
   if (INLINE_EXACT) {
     if (on_boundary(sw, r2)) {
       const ExactPair o = exact_pair<K>(pbc, sw, xi, yi, zi, pj.x, pj.y, pj.z, flip);
@@ -268,7 +278,8 @@ template <int K, int PBC, bool ACC, bool FAR>
 __device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitch& sw, bool& near, double xi, double yi,
                                            double zi, unsigned long long wi, int two_groups, bool row_is_b,
                                            const RecBuf& pa, const RecBuf& pb, bool va, bool vb, double far_skip2,
-                                           double& fx, double& fy, double& fz, LaneAcc& acc) {
+                                           double& fx, double& fy, double& fz, LaneAcc& acc, double qqa = 1.0,
+                                           double qqb = 1.0) {
   const bool flipa = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pa.w));
   const bool flipb = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pb.w));
   const unsigned sga = flipa ? 0x80000000u : 0u, sgb = flipb ? 0x80000000u : 0u;
@@ -284,6 +295,12 @@ __device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitch& s
   double sa, dfa, sb, dfb;
   eval_switch<K>(sw, ra, sa, dfa);
   eval_switch<K>(sw, rb, sb, dfb);
+  if (K == K_DH) {
+    sa *= qqa;
+    dfa *= qqa;
+    sb *= qqb;
+    dfb *= qqb;
+  }
   near |= (va & on_boundary(sw, ra)) | (vb & on_boundary(sw, rb));
   if (!va) {
     sa = 0.0;
