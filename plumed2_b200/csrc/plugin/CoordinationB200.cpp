@@ -10,6 +10,7 @@
 #include "b200coord.h"
 #include "core/ActionRegister.h"
 #include "core/Colvar.h"
+#include "core/PlumedMain.h"
 #include "tools/Communicator.h"
 #include "tools/OpenMP.h"
 #include "tools/Pbc.h"
@@ -23,29 +24,49 @@
 namespace PLMD {
 namespace colvar {
 
-class CoordinationB200 : public Colvar {
+// Everything of CoordinationBase (src/colvar/CoordinationBase.cpp) lives here; the two registered actions only differ
+// in the keywords of their pairing function, as Coordination.cpp / DHEnergy.cpp do in the reference.
+class CoordinationBaseB200 : public Colvar {
+protected:
   b200coord_ctx* ctx = nullptr;
+  bool needCharges = false;
   bool pbc = true;
   bool serial = false;
   bool combineWithMpi = false;
-  std::vector<double> derivBuffer;
+  std::vector<double> derivBuffer, chargeBuffer, chargeSent;
   // B200COORD_PLUGIN_TIMERS=1: seconds spent in the C-ABI call vs in handing the result to PLUMED's Value
   bool timers = false;
   double tEngine = 0.0, tStore = 0.0;
   unsigned long nCalls = 0;
   void check(int rc, const char* what);
 
+  // group / list keywords and engine set-up; `sw` is the pairing the derived constructor parsed
+  void setup(const b200coord_switch& sw, const char* what);
+
 public:
-  explicit CoordinationB200(const ActionOptions&);
-  ~CoordinationB200() override;
+  explicit CoordinationBaseB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT(ao) {}
+  ~CoordinationBaseB200() override;
   static void registerKeywords(Keywords& keys);
   void prepare() override;
   void calculate() override;
 };
 
+class CoordinationB200 : public CoordinationBaseB200 {
+public:
+  explicit CoordinationB200(const ActionOptions&);
+  static void registerKeywords(Keywords& keys);
+};
 PLUMED_REGISTER_ACTION(CoordinationB200, "COORDINATION")
 
-void CoordinationB200::registerKeywords(Keywords& keys) {
+// DHENERGY (src/colvar/DHEnergy.cpp): Debye-Hueckel interaction energy between the two groups
+class DHEnergyB200 : public CoordinationBaseB200 {
+public:
+  explicit DHEnergyB200(const ActionOptions&);
+  static void registerKeywords(Keywords& keys);
+};
+PLUMED_REGISTER_ACTION(DHEnergyB200, "DHENERGY")
+
+void CoordinationBaseB200::registerKeywords(Keywords& keys) {
   Colvar::registerKeywords(keys);
   keys.addFlag("SERIAL", false, "Perform the calculation in serial - for debug purpose");
   keys.addFlag("PAIR", false, "Pair only 1st element of the 1st group with 1st element in the second, etc");
@@ -55,6 +76,11 @@ void CoordinationB200::registerKeywords(Keywords& keys) {
   keys.add("optional", "NL_STRIDE", "The frequency with which we are updating the atoms in the neighbor list");
   keys.add("atoms", "GROUPA", "First list of atoms");
   keys.add("atoms", "GROUPB", "Second list of atoms (if empty, N*(N-1)/2 pairs in GROUPA are counted)");
+  keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
+}
+
+void CoordinationB200::registerKeywords(Keywords& keys) {
+  CoordinationBaseB200::registerKeywords(keys);
   keys.add("compulsory", "NN", "6", "The n parameter of the switching function ");
   keys.add("compulsory", "MM", "0", "The m parameter of the switching function; 0 implies 2*NN");
   keys.add("compulsory", "D_0", "0.0", "The d_0 parameter of the switching function");
@@ -62,47 +88,24 @@ void CoordinationB200::registerKeywords(Keywords& keys) {
   keys.add("optional", "D_MAX", "cut the rational switching function built from R_0/NN/MM/D_0 at this distance (stretched to zero)");
   keys.add("optional", "SWITCH", "This keyword is used if you want to employ an alternative to the continuous switching function defined above. "
            "When this keyword is present you no longer need the NN, MM, D_0 and R_0 keywords.");
-  keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
   keys.setValueDescription("scalar", "the value of the coordination");
 }
 
-void CoordinationB200::check(int rc, const char* what) {
+void DHEnergyB200::registerKeywords(Keywords& keys) {  // DHEnergy.cpp:76-83
+  CoordinationBaseB200::registerKeywords(keys);
+  keys.add("compulsory", "I", "1.0", "Ionic strength (M)");
+  keys.add("compulsory", "TEMP", "300.0", "Simulation temperature (K)");
+  keys.add("compulsory", "EPSILON", "80.0", "Dielectric constant of solvent");
+  keys.setValueDescription("scalar", "the value of the DHENERGY");
+}
+
+void CoordinationBaseB200::check(int rc, const char* what) {
   if (rc != B200COORD_OK) {
     error(std::string(what) + " failed on the GPU: " + b200coord_last_error(ctx));
   }
 }
 
-CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT(ao) {
-  parseFlag("SERIAL", serial);
-  std::vector<AtomNumber> ga, gb;
-  parseAtomList("GROUPA", ga);
-  parseAtomList("GROUPB", gb);
-  bool nopbc = !pbc;
-  parseFlag("NOPBC", nopbc);
-  pbc = !nopbc;
-  bool dopair = false;
-  parseFlag("PAIR", dopair);
-  bool classic = false, cells = false;
-  parseFlag("NLIST", classic);
-  parseFlag("NLISTCELLS", cells);
-  plumed_assert(!(cells && classic)) << "Please activate only one of the two version of the NL";
-  plumed_assert(!(cells && dopair)) << "Pair is not compatible with the CELLS implementation of the NL";
-  double nlCut = 0.0;
-  int nlStride = 0;
-  if (classic || cells) {
-    parse("NL_CUTOFF", nlCut);
-    if (nlCut <= 0.0) {
-      error("NL_CUTOFF should be explicitly specified and positive");
-    }
-    parse("NL_STRIDE", nlStride);
-    if (nlStride <= 0) {
-      error("NL_STRIDE should be explicitly specified and positive");
-    }
-  }
-  if (dopair && ga.size() != gb.size()) {
-    error("when using PAIR option, the two groups should have the same number of elements");
-  }
-
+CoordinationB200::CoordinationB200(const ActionOptions& ao) : Action(ao), CoordinationBaseB200(ao) {
   b200coord_switch sw;
   std::string swDef;
   parse("SWITCH", swDef);
@@ -134,6 +137,61 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
       b200coord_switch_rational(nn, mm, r0, d0, &sw);
     }
   }
+  setup(sw, "COORDINATION");
+}
+
+DHEnergyB200::DHEnergyB200(const ActionOptions& ao) : Action(ao), CoordinationBaseB200(ao) {  // DHEnergy.cpp:104-128
+  double I = 1.0, T = 300.0, epsilon = 80.0;
+  parse("I", I);
+  parse("TEMP", T);
+  parse("EPSILON", epsilon);
+  if (usingNaturalUnits()) {
+    error("DHENERGY cannot be used for calculations performed with natural units");
+  }
+  b200coord_switch sw;
+  if (b200coord_pairing_dhenergy(I, T, epsilon, getUnits().getEnergy(), getUnits().getLength(), getUnits().getCharge(), &sw) !=
+      B200COORD_OK) {
+    error(b200coord_last_error(nullptr));
+  }
+  needCharges = true;
+  setup(sw, "DHENERGY");
+  log << "  with solvent dielectric constant " << epsilon << "\n";
+  log << "  at temperature " << T << " K\n";
+  log << "  at ionic strength " << I << "M\n";
+  log << "  Bibliography " << plumed.cite("Do, Carloni, Varani and Bussi, J. Chem. Theory Comput. 9, 1720 (2013)") << " \n";
+}
+
+void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
+  parseFlag("SERIAL", serial);
+  std::vector<AtomNumber> ga, gb;
+  parseAtomList("GROUPA", ga);
+  parseAtomList("GROUPB", gb);
+  bool nopbc = !pbc;
+  parseFlag("NOPBC", nopbc);
+  pbc = !nopbc;
+  bool dopair = false;
+  parseFlag("PAIR", dopair);
+  bool classic = false, cells = false;
+  parseFlag("NLIST", classic);
+  parseFlag("NLISTCELLS", cells);
+  plumed_assert(!(cells && classic)) << "Please activate only one of the two version of the NL";
+  plumed_assert(!(cells && dopair)) << "Pair is not compatible with the CELLS implementation of the NL";
+  double nlCut = 0.0;
+  int nlStride = 0;
+  if (classic || cells) {
+    parse("NL_CUTOFF", nlCut);
+    if (nlCut <= 0.0) {
+      error("NL_CUTOFF should be explicitly specified and positive");
+    }
+    parse("NL_STRIDE", nlStride);
+    if (nlStride <= 0) {
+      error("NL_STRIDE should be explicitly specified and positive");
+    }
+  }
+  if (dopair && ga.size() != gb.size()) {
+    error("when using PAIR option, the two groups should have the same number of elements");
+  }
+
   int device = -1;
   if (const char* env = std::getenv("B200COORD_DEVICE")) {
     device = std::atoi(env);
@@ -170,7 +228,7 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
   cfg.nranks = combineWithMpi ? comm.Get_size() : 1;
   const int rc = b200coord_create(&cfg, &sw, absIndex.data(), &ctx);
   if (rc != B200COORD_OK) {
-    error(std::string("cannot set up the B200 COORDINATION engine: ") + b200coord_last_error(nullptr));
+    error(std::string("cannot set up the B200 ") + what + " engine: " + b200coord_last_error(nullptr));
   }
   derivBuffer.resize(3 * all.size());
   requestAtoms(all);
@@ -180,7 +238,7 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
 
   char desc[512];
   b200coord_switch_describe(&sw, desc, sizeof(desc));
-  log.printf("  B200-native COORDINATION (libb200coord, sm_100a kernels)\n");
+  log.printf("  B200-native %s (libb200coord, sm_100a kernels)\n", what);
   log.printf("  between two groups of %u and %u atoms\n", static_cast<unsigned>(ga.size()), static_cast<unsigned>(gb.size()));
   log.printf(pbc ? "  using periodic boundary conditions\n" : "  without periodic boundary conditions\n");
   if (dopair) {
@@ -193,7 +251,7 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : PLUMED_COLVAR_INIT
   log << "  contacts are counted with cutoff " << desc << "\n";
 }
 
-CoordinationB200::~CoordinationB200() {
+CoordinationBaseB200::~CoordinationBaseB200() {
   if (timers && nCalls) {
     std::fprintf(stderr, "B200COORD plugin timers: %lu calls, engine %.3f ms/call, store-to-Value %.3f ms/call\n", nCalls,
                  1e3 * tEngine / nCalls, 1e3 * tStore / nCalls);
@@ -201,7 +259,7 @@ CoordinationB200::~CoordinationB200() {
   b200coord_destroy(ctx);
 }
 
-void CoordinationB200::prepare() {
+void CoordinationBaseB200::prepare() {
   // NeighborList::prepare (src/tools/NeighborList.cpp:433-456); the full atom list stays requested on
   // every step (legal: the reduced list is only a communication optimisation of the CPU code)
   int willRebuild = 0;
@@ -211,8 +269,20 @@ void CoordinationB200::prepare() {
   }
 }
 
-void CoordinationB200::calculate() {
+void CoordinationBaseB200::calculate() {
   const unsigned n = getNumberOfAtoms();
+  if (needCharges) {  // ActionAtomistic::getCharge, as DHEnergy::pairing reads them every step
+    chargeBuffer.resize(n);
+    bool changed = chargeBuffer.size() != chargeSent.size();
+    for (unsigned i = 0; i < n; ++i) {
+      chargeBuffer[i] = getCharge(i);
+      changed = changed || chargeBuffer[i] != chargeSent[i];
+    }
+    if (changed) {
+      check(b200coord_set_charges(ctx, chargeBuffer.data()), "set_charges");
+      chargeSent = chargeBuffer;
+    }
+  }
   double box[9];
   const Tensor& b = getBox();
   for (unsigned i = 0; i < 3; ++i)

@@ -24,12 +24,14 @@ def _need():
         pytest.skip("plugin .so not built")
 
 
-def run_both(natoms, lines, frames, box, watch=("c",)):
+def run_both(natoms, lines, frames, box, watch=("c",), charges=None, key="COORDINATION"):
     os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
     outs = []
     for load in (False, True):
         pre = ["LOAD FILE=" + PLUGIN] if load else []
         p = R.Plumed(natoms, pre + lines, watch=watch, log="/tmp/plumed_%s.log" % ("gpu" if load else "cpu"))
+        if charges is not None:
+            p.charges[:] = charges
         res = []
         for step, pos in enumerate(frames):
             r = p.calc(step, pos, box)
@@ -37,9 +39,9 @@ def run_both(natoms, lines, frames, box, watch=("c",)):
             res.append(r)
         p.close()
         outs.append(res)
-    if "B200-native COORDINATION" not in open("/tmp/plumed_gpu.log").read():
-        raise AssertionError("the loaded plugin did not take over the COORDINATION key")
-    assert "B200-native COORDINATION" not in open("/tmp/plumed_cpu.log").read()
+    if "B200-native " + key not in open("/tmp/plumed_gpu.log").read():
+        raise AssertionError("the loaded plugin did not take over the %s key" % key)
+    assert "B200-native " + key not in open("/tmp/plumed_cpu.log").read()
     return outs
 
 
@@ -76,6 +78,21 @@ def test_driver_style_runs_match(body, tri):
     frames, box = trajectory(2000, 7, seed=12, triclinic=tri)
     lines = ["c: COORDINATION " + body, "RESTRAINT ARG=c AT=100 KAPPA=0.01 SLOPE=0.5"]
     cpu, gpu = run_both(2000, lines, frames, box)
+    compare(cpu, gpu)
+
+
+@pytest.mark.parametrize("body", [
+    "GROUPA=1-300 GROUPB=301-2000 I=0.1 EPSILON=80.0 TEMP=300",
+    "GROUPA=1-2000 I=0.2 EPSILON=78.4 NLIST NL_CUTOFF=1.2 NL_STRIDE=3",
+    "GROUPA=1-300 GROUPB=301-2000 I=0.0 EPSILON=80.0 NLISTCELLS NL_CUTOFF=1.2 NL_STRIDE=2",
+])
+def test_dhenergy_sibling_action(body):
+    """DHENERGY (src/colvar/DHEnergy.cpp) answered by the plugin: charges come from the MD engine (setCharges)"""
+    _need()
+    frames, box = trajectory(2000, 5, seed=17, triclinic=True)
+    q = np.random.default_rng(3).standard_normal(2000)
+    lines = ["c: DHENERGY " + body, "RESTRAINT ARG=c AT=1 KAPPA=0.01 SLOPE=0.5"]
+    cpu, gpu = run_both(2000, lines, frames, box, charges=q, key="DHENERGY")
     compare(cpu, gpu)
 
 
