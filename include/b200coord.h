@@ -66,7 +66,10 @@ enum {
 /* pairing functions of COORDINATION's siblings on CoordinationBase, carried in the same struct:
  * DHENERGY (src/colvar/DHEnergy.cpp:130-143): s = exp(-k r)/r * constant/epsilon * q_i q_j, dfunc = -(k + 1/r) s / r;
  * beta = k, lambda = constant/epsilon, no D_MAX; needs b200coord_set_charges */
-enum { B200COORD_PAIR_DHENERGY = 32 };
+enum { B200COORD_PAIR_DHENERGY = 32, B200COORD_PAIR_GHBFIX = 33 };
+/* GHBFIX (src/colvar/GHBFIX.cpp:186-220): typed piecewise polynomial, s = eta(t_i0,t_i1) * f(r), zero beyond D_MAX;
+ * d0, dmax, dmax_2 as named; preRes = A, preDfunc = B, preSecDev = C, d = D, c = C_keyword*(D_MAX-D_0) (the joint of
+ * the two polynomials), GHBFIX.cpp:108-113; needs b200coord_set_types */
 
 /* mirrors switchContainers::Data (src/tools/SwitchingFunction.h:58-94) */
 typedef struct b200coord_switch {
@@ -126,6 +129,8 @@ int b200coord_switch_rational(int nn, int mm, double r0, double d0, b200coord_sw
  * default kJ/mol, nm, e), DHEnergy.cpp:104-128 */
 int b200coord_pairing_dhenergy(double ionic_strength, double temp, double epsilon, double energy_unit, double length_unit,
                                double charge_unit, b200coord_switch* out);
+/* GHBFIX polynomial constants from its keywords D_MAX, D_0, C (GHBFIX.cpp:98-113) */
+int b200coord_pairing_ghbfix(double dmax, double d0, double c, b200coord_switch* out);
 /* text like SwitchingFunction::description() for the action's log */
 int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen);
 
@@ -138,6 +143,10 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
  * DHEnergy::pairing); required before calculate when the pairing is B200COORD_PAIR_DHENERGY; may be called again
  * whenever the charges change */
 int b200coord_set_charges(b200coord_ctx* ctx, const double* charges);
+/* GHBFIX: interaction type of each of the n_group_a+n_group_b atoms (typesTable[absolute index], GHBFIX.cpp:117-140)
+ * and the ntypes x ntypes scaling table etas (row = type of the pair's first atom, :142-163), already in PLUMED energy
+ * units; required before calculate when the pairing is B200COORD_PAIR_GHBFIX */
+int b200coord_set_types(b200coord_ctx* ctx, const unsigned* types, unsigned ntypes, const double* etas);
 void b200coord_destroy(b200coord_ctx* ctx);
 /* last error text of this context (ctx==NULL: of the last failed create/parse in this thread) */
 const char* b200coord_last_error(const b200coord_ctx* ctx);

@@ -1077,6 +1077,50 @@ static double dhenergy_pairing(const orc_switch* s, double distance2, double qi,
   return tmp;
 }
 
+/* GHBFIX::pairing, colvar/GHBFIX.cpp:186-220 (preRes = A, preDfunc = B, preSecDev = C, d = D, c = c*dmax2) */
+static double ghbfix_pairing(const orc_switch* s, double distance2, double scale, double* dfunc) {
+  double result;
+  if (distance2 > s->dmax_2) {
+    *dfunc = 0.0;
+    return 0.;
+  }
+  double distance = sqrt(distance2);
+  const double rdist = (distance - s->d0);
+  if (rdist <= 0.) {
+    result = -1.;
+    *dfunc = 0.0;
+  } else {
+    result = -1.;
+    *dfunc = 0.0;
+    if (rdist > s->c) {
+      result += (s->preRes + s->preDfunc * rdist + s->preSecDev * rdist * rdist);
+      *dfunc += s->preDfunc + 2 * s->preSecDev * rdist;
+    } else if (rdist > 0.0) {
+      result += s->d * (rdist * rdist);
+      *dfunc += 2 * s->d * rdist;
+    }
+    *dfunc /= distance;
+  }
+  result *= scale;
+  *dfunc *= scale;
+  return result;
+}
+
+/* GHBFIX::GHBFIX, colvar/GHBFIX.cpp:98-113 */
+void orc_ghbfix_setup(orc_switch* sw, double dmax, double d0, double c) {
+  memset(sw, 0, sizeof(*sw));
+  sw->type = ORC_PAIR_GHBFIX;
+  sw->dmax = dmax;
+  sw->dmax_2 = dmax * dmax;
+  sw->d0 = d0;
+  const double dmax2 = dmax - d0;
+  sw->preRes = (-c * dmax2 * dmax2) / ((1 - c) * dmax2 * dmax2);
+  sw->preDfunc = (2 * dmax2) / ((1 - c) * dmax2 * dmax2);
+  sw->preSecDev = -1 / ((1 - c) * dmax2 * dmax2);
+  sw->d = 1 / (c * dmax2 * dmax2);
+  sw->c = c * dmax2;
+}
+
 /* DHEnergy::DHEnergy, colvar/DHEnergy.cpp:104-128, default units (energy kJ/mol, length nm, charge e) */
 void orc_dhenergy_setup(orc_switch* sw, double I, double T, double epsilon) {
   memset(sw, 0, sizeof(*sw));
@@ -1087,26 +1131,35 @@ void orc_dhenergy_setup(orc_switch* sw, double I, double T, double epsilon) {
 }
 
 static size_t coordination_base_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
-                                          const double* pos, const unsigned* abs_index, const double* charges, size_t n,
+                                          const double* pos, const unsigned* abs_index, const double* charges,
+                                          const unsigned* types, unsigned ntypes, const double* etas, size_t n,
                                           unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv,
                                           double* virial);
+
+size_t orc_ghbfix_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,
+                            const unsigned* abs_index, const unsigned* types, unsigned ntypes, const double* etas, size_t n,
+                            unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv, double* virial) {
+  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, NULL, types, ntypes, etas, n, rank, nranks,
+                                     nthreads, value, deriv, virial);
+}
 
 size_t orc_dhenergy_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,
                               const unsigned* abs_index, const double* charges, size_t n, unsigned rank, unsigned nranks,
                               int nthreads, double* value, double* deriv, double* virial) {
-  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, charges, n, rank, nranks, nthreads, value, deriv,
-                                     virial);
+  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, charges, NULL, 0, NULL, n, rank, nranks, nthreads,
+                                     value, deriv, virial);
 }
 
 size_t orc_coordination_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
                                   const double* pos, const unsigned* abs_index, size_t n, unsigned rank,
                                   unsigned nranks, int nthreads, double* value, double* deriv, double* virial) {
-  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, NULL, n, rank, nranks, nthreads, value, deriv,
-                                     virial);
+  return coordination_base_calculate(nl, pbc, do_pbc, sw, pos, abs_index, NULL, NULL, 0, NULL, n, rank, nranks, nthreads,
+                                     value, deriv, virial);
 }
 
 static size_t coordination_base_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw,
-                                          const double* pos, const unsigned* abs_index, const double* charges, size_t n,
+                                          const double* pos, const unsigned* abs_index, const double* charges,
+                                          const unsigned* types, unsigned ntypes, const double* etas, size_t n,
                                           unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv,
                                           double* virial) {
   double ncoord = 0.;
@@ -1151,7 +1204,9 @@ static size_t coordination_base_calculate(const orc_nl* nl, const orc_pbc* pbc, 
       else
         for (int k = 0; k < 3; k++) distance[k] = pos[3 * (size_t)i1 + k] - pos[3 * (size_t)i0 + k];
       double dfunc = 0.;
-      if (sw->type == ORC_PAIR_DHENERGY)
+      if (sw->type == ORC_PAIR_GHBFIX) /* GHBFIX::pairing: scale = etas[n*t1+t2], t1 = type of i0 (:189-197) */
+        ncoord += ghbfix_pairing(sw, mod2(distance), etas[(size_t)ntypes * types[i0] + types[i1]], &dfunc);
+      else if (sw->type == ORC_PAIR_DHENERGY)
         ncoord += dhenergy_pairing(sw, mod2(distance), charges[i0], charges[i1], &dfunc); /* DHEnergy::pairing */
       else
         ncoord += orc_switch_calculate_sqr(sw, mod2(distance), &dfunc); /* Coordination::pairing */

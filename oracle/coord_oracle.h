@@ -111,6 +111,13 @@ void orc_nl_prepare(const orc_nl* nl, long step, int exchange_step, int* firstti
  * deriv: n*3, virial: 9 (row-major), value: 1.  Returns pairs iterated. */
 /* DHENERGY (colvar/DHEnergy.cpp): the same CoordinationBase loop with the Debye-Hueckel pairing; k and constant as
  * computed by its constructor (:119-120), charges per requested atom (GROUPA then GROUPB) */
+#define ORC_PAIR_GHBFIX 33
+/* GHBFIX (colvar/GHBFIX.cpp): constants of the constructor (:98-113); types = typesTable[absolute index] per requested
+ * atom, etas = ntypes x ntypes table in PLUMED energy units */
+void orc_ghbfix_setup(orc_switch* sw, double dmax, double d0, double c);
+size_t orc_ghbfix_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,
+                            const unsigned* abs_index, const unsigned* types, unsigned ntypes, const double* etas, size_t n,
+                            unsigned rank, unsigned nranks, int nthreads, double* value, double* deriv, double* virial);
 #define ORC_PAIR_DHENERGY 32
 void orc_dhenergy_setup(orc_switch* sw, double I, double T, double epsilon); /* default PLUMED units */
 size_t orc_dhenergy_calculate(const orc_nl* nl, const orc_pbc* pbc, int do_pbc, const orc_switch* sw, const double* pos,

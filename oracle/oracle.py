@@ -94,6 +94,10 @@ def lib():
         L.orc_dhenergy_calculate.restype = C.c_size_t
         L.orc_dhenergy_calculate.argtypes = [C.c_void_p, C.POINTER(Pbc), C.c_int, C.POINTER(Switch), dp, up, dp,
                                              C.c_size_t, C.c_uint, C.c_uint, C.c_int, dp, dp, dp]
+        L.orc_ghbfix_setup.argtypes = [C.POINTER(Switch), C.c_double, C.c_double, C.c_double]
+        L.orc_ghbfix_calculate.restype = C.c_size_t
+        L.orc_ghbfix_calculate.argtypes = [C.c_void_p, C.POINTER(Pbc), C.c_int, C.POINTER(Switch), dp, up, up, C.c_uint, dp,
+                                           C.c_size_t, C.c_uint, C.c_uint, C.c_int, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -231,7 +235,42 @@ def make_dhenergy(I, T=300.0, epsilon=80.0):
     return s
 
 
-def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nthreads=1, charges=None):
+def make_ghbfix(dmax, d0, c):
+    """GHBFIX polynomial constants (GHBFIX.cpp:98-113)"""
+    s = Switch()
+    lib().orc_ghbfix_setup(C.byref(s), float(dmax), float(d0), float(c))
+    return s
+
+
+# energy units of src/tools/Units.cpp (kJ/mol = 1), for GHBFIX's ENERGY_UNITS keyword
+ENERGY_UNITS = {"kj/mol": 1.0, "kcal/mol": 4.184, "j/mol": 0.001, "eV": 96.48530749925792, "Ha": 2625.499638}
+
+
+def read_ghbfix_tables(types_file, params_file, energy_units="plumed"):
+    """GHBFIX.cpp:115-172: types per absolute atom index and the n x n eta table.  std::map::operator[] semantics are kept:
+    a type name of the parameter file that the types file does not know reads as index 0."""
+    def fields(fn):
+        rows = []
+        for ln in open(fn):
+            ln = ln.split("#")[0].split()
+            if ln:
+                rows.append(ln)
+        return rows
+    table, types = {}, []
+    for (name,) in fields(types_file):
+        if name not in table:
+            table[name] = (max(table.values()) + 1) if table else 0
+        types.append(table[name])
+    n = max(types) + 1
+    etas = np.zeros(n * n)
+    for it, jt, eta in fields(params_file):
+        etas[n * table.setdefault(it, 0) + table.setdefault(jt, 0)] = float(eta)
+    if energy_units != "plumed":
+        etas *= ENERGY_UNITS[energy_units]
+    return np.array(types, dtype=np.uint32), n, etas
+
+
+def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nthreads=1, charges=None, types=None):
     """CoordinationBase::calculate: returns value, deriv (n,3), virial (3,3), pairs iterated.
     charges: per requested atom, for a DHENERGY pairing (make_dhenergy)"""
     pos = np.ascontiguousarray(pos, dtype=np.float64)
@@ -242,7 +281,14 @@ def coordination(nl, pbc, do_pbc, sw, pos, abs_index=None, rank=0, nranks=1, nth
     val = C.c_double(0)
     deriv = np.zeros((n, 3))
     vir = np.zeros(9)
-    if charges is not None:
+    if types is not None:  # (types per requested atom, ntypes, etas)
+        t = np.ascontiguousarray(types[0], dtype=np.uint32)
+        e = np.ascontiguousarray(types[2], dtype=np.float64)
+        assert t.shape[0] == n
+        npairs = lib().orc_ghbfix_calculate(nl.h, C.byref(pbc), int(do_pbc), C.byref(sw), _dp(pos), _up(abs_index), _up(t),
+                                            int(types[1]), _dp(e), n, rank, nranks, nthreads, C.byref(val), _dp(deriv),
+                                            _dp(vir))
+    elif charges is not None:
         q = np.ascontiguousarray(charges, dtype=np.float64)
         assert q.shape[0] == n
         npairs = lib().orc_dhenergy_calculate(nl.h, C.byref(pbc), int(do_pbc), C.byref(sw), _dp(pos), _up(abs_index),

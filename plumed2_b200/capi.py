@@ -31,7 +31,8 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_device_synchronize", "b200coord_enqueue_device", "b200coord_stream_mark",
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
             "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach",
-            "b200coord_pairing_dhenergy", "b200coord_set_charges"]
+            "b200coord_pairing_dhenergy", "b200coord_set_charges", "b200coord_pairing_ghbfix",
+            "b200coord_set_types"]
 
 
 class B200CoordError(RuntimeError):
@@ -83,6 +84,8 @@ def lib():
     L.b200coord_switch_describe.argtypes = [C.POINTER(Switch), C.c_char_p, C.c_size_t]
     L.b200coord_pairing_dhenergy.argtypes = [C.c_double] * 6 + [C.POINTER(Switch)]
     L.b200coord_set_charges.argtypes = [C.c_void_p, dp]
+    L.b200coord_pairing_ghbfix.argtypes = [C.c_double] * 3 + [C.POINTER(Switch)]
+    L.b200coord_set_types.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_uint, dp]
     L.b200coord_create.argtypes = [C.POINTER(Config), C.POINTER(Switch), C.POINTER(C.c_uint), C.POINTER(C.c_void_p)]
     L.b200coord_destroy.argtypes = [C.c_void_p]
     L.b200coord_destroy.restype = None
@@ -143,6 +146,12 @@ def pairing_dhenergy(ionic_strength, temp, epsilon, energy_unit=1.0, length_unit
     s = Switch()
     check(lib().b200coord_pairing_dhenergy(float(ionic_strength), float(temp), float(epsilon), float(energy_unit),
                                            float(length_unit), float(charge_unit), C.byref(s)))
+    return s
+
+
+def pairing_ghbfix(dmax, d0, c):
+    s = Switch()
+    check(lib().b200coord_pairing_ghbfix(float(dmax), float(d0), float(c), C.byref(s)))
     return s
 
 

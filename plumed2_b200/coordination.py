@@ -105,7 +105,7 @@ class Coordination:
 
     def __init__(self, GROUPA, GROUPB=None, PAIR=False, NLIST=False, NLISTCELLS=False, NL_CUTOFF=None,
                  NL_STRIDE=None, NOPBC=False, SERIAL=False, SWITCH=None, R_0=None, NN=6, MM=0, D_0=0.0, D_MAX=None,
-                 label="c", device=-1, rank=0, nranks=1, precision=capi.FP64, DHENERGY=None):
+                 label="c", device=-1, rank=0, nranks=1, precision=capi.FP64, DHENERGY=None, GHBFIX=None):
         """DHENERGY: None for COORDINATION, else dict(I=..., TEMP=..., EPSILON=...) -> the sibling action DHENERGY
         (src/colvar/DHEnergy.cpp): same groups / lists, Debye-Hueckel pairing, needs set_charges()"""
         self.label = label
@@ -131,7 +131,9 @@ class Coordination:
             raise PlumedInputError("when using PAIR option, the two groups should have the same number of elements\n"
                                    "the groups you specified have size %d and %d" % (ga.size, gb.size))
         # --- Coordination ctor, Coordination.cpp:128-157 (+ cudaCoord's top-level D_MAX rewrite)
-        if DHENERGY is not None:  # DHEnergy ctor, DHEnergy.cpp:104-128 (default units)
+        if GHBFIX is not None:  # GHBFIX ctor, GHBFIX.cpp:98-113; dict(D_MAX, D_0, C); types/etas: set_types()
+            self.switch = capi.pairing_ghbfix(float(GHBFIX["D_MAX"]), float(GHBFIX["D_0"]), float(GHBFIX["C"]))
+        elif DHENERGY is not None:  # DHEnergy ctor, DHEnergy.cpp:104-128 (default units)
             self.switch = capi.pairing_dhenergy(float(DHENERGY["I"]), float(DHENERGY.get("TEMP", 300.0)),
                                                 float(DHENERGY["EPSILON"]))
         elif SWITCH:
@@ -182,6 +184,26 @@ class Coordination:
     @classmethod
     def from_input(cls, line, **kw):
         label, action, kv, flags = split_input_line(line)
+        if action == "GHBFIX":  # GHBFIX::registerKeywords, GHBFIX.cpp:91-103; the TYPES / PARAMS files are read by
+            # set_types_from_files (the mirror does not open files behind the caller's back)
+            allowed = {"GROUPA", "GROUPB", "NL_CUTOFF", "NL_STRIDE", "D_MAX", "D_0", "C", "TYPES", "PARAMS", "ENERGY_UNITS"}
+            for k in kv:
+                if k not in allowed:
+                    raise PlumedInputError("cannot understand the following words from the input line : " + k)
+            for f in flags:
+                if f not in _FLAGS:
+                    raise PlumedInputError("cannot understand the following words from the input line : " + f)
+            for k in ("GROUPA", "TYPES", "PARAMS", "D_MAX", "D_0", "C"):
+                if k not in kv:
+                    raise PlumedInputError("%s is compulsory" % k)
+            args = dict(GROUPA=kv["GROUPA"], GROUPB=kv.get("GROUPB"), PAIR="PAIR" in flags, NLIST="NLIST" in flags,
+                        NLISTCELLS="NLISTCELLS" in flags, NL_CUTOFF=kv.get("NL_CUTOFF"), NL_STRIDE=kv.get("NL_STRIDE"),
+                        NOPBC="NOPBC" in flags, SERIAL="SERIAL" in flags, label=label or "c",
+                        GHBFIX=dict(D_MAX=float(kv["D_MAX"]), D_0=float(kv["D_0"]), C=float(kv["C"])))
+            args.update(kw)
+            obj = cls(**args)
+            obj.ghbfix_files = (kv["TYPES"], kv["PARAMS"], kv.get("ENERGY_UNITS", "plumed"))
+            return obj
         if action == "DHENERGY":  # DHEnergy::registerKeywords, DHEnergy.cpp:77-90: CoordinationBase + I, TEMP, EPSILON
             allowed = {"GROUPA", "GROUPB", "NL_CUTOFF", "NL_STRIDE", "I", "TEMP", "EPSILON"}
             for k in kv:
@@ -200,7 +222,7 @@ class Coordination:
             args.update(kw)
             return cls(**args)
         if action != "COORDINATION":
-            raise PlumedInputError("this mirror only implements COORDINATION and DHENERGY, got " + action)
+            raise PlumedInputError("this mirror only implements COORDINATION, DHENERGY and GHBFIX, got " + action)
         for k in kv:
             if k not in _KEYS:
                 raise PlumedInputError("cannot understand the following words from the input line : " + k)
@@ -228,6 +250,13 @@ class Coordination:
         """charges of ALL system atoms (ActionAtomistic::getCharge); required for DHENERGY"""
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64)[self.atoms])
         capi.check(self._L.b200coord_set_charges(self._ctx, q.ctypes.data_as(C.POINTER(C.c_double))), self._ctx)
+
+    def set_types(self, types_of_all_atoms, ntypes, etas):
+        """GHBFIX: interaction type per SYSTEM atom (typesTable[absolute index]) and the ntypes x ntypes eta table"""
+        t = np.ascontiguousarray(np.asarray(types_of_all_atoms, dtype=np.uint32)[self.atoms])
+        e = np.ascontiguousarray(np.asarray(etas, dtype=np.float64).reshape(-1))
+        capi.check(self._L.b200coord_set_types(self._ctx, t.ctypes.data_as(C.POINTER(C.c_uint)), int(ntypes),
+                                               e.ctypes.data_as(C.POINTER(C.c_double))), self._ctx)
 
     def _set_box(self, box):
         b = self._zero_box if box is None else np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(9))

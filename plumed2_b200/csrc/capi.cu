@@ -130,6 +130,10 @@ struct b200coord_ctx {
   unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
   DevBuf<double> d_q, d_sq;    // charges in slot order / sorted order (DHENERGY)
   bool have_charges = false, sq_valid = false;
+  DevBuf<uint32_t> d_types, d_stype;  // interaction types in slot order / sorted order (GHBFIX)
+  DevBuf<double> d_etas;
+  unsigned ntypes = 0;
+  bool have_types = false, stype_valid = false;
   DevBuf<double> d_bpos;       // positions the list was built from (sorted order), for the displacement bound
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
@@ -191,6 +195,10 @@ void to_dev_switch(const b200coord_switch& s, DevSwitch& d) {
   d.d0_2 = s.d0 * s.d0;
   d.band_dmax = (s.dmax < 1.0e150) ? 1e-10 * s.dmax_2 : -1.0;
   d.band_d0 = (s.d0 > 0.0) ? 1e-10 * d.d0_2 : -1.0;
+  if (s.type == B200COORD_PAIR_GHBFIX || s.type == B200COORD_PAIR_DHENERGY) {
+    d.band_dmax = -1.0;  // GHBFIX is C1 at D_0, at the joint and at D_MAX; DHENERGY has no cutoff: nothing to patch
+    d.band_d0 = -1.0;
+  }
   // rationalfixN evaluates y^(N/2-1): keep N/2 in nnf for the device (the host struct leaves the default there)
   switch (s.type) {
     case B200COORD_SW_RATIONALFIX12: d.nnf = 6; break;
@@ -375,6 +383,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   c->stats.kernel_launches += 4;
   c->sorted_valid = true;
   c->sq_valid = false;  // new permutation
+  c->stype_valid = false;
   if (mode == B200COORD_NL_CLASSIC) {
     launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
     const unsigned rows = c->row_end - c->row_begin;
@@ -501,6 +510,8 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
   if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
   if (c->dsw.type == B200COORD_PAIR_DHENERGY && !c->have_charges)
     return fail(c, B200COORD_ERR_STATE, "b200coord_set_charges must be called before calculate (DHENERGY)");
+  if (c->dsw.type == B200COORD_PAIR_GHBFIX && !c->have_types)
+    return fail(c, B200COORD_ERR_STATE, "b200coord_set_types must be called before calculate (GHBFIX)");
   const bool need_rebuild = !c->list_valid || (c->cfg.nl_mode != B200COORD_NL_NONE && c->invalidate);
   if (need_rebuild) {
     int rc = rebuild(c, d_pos);
@@ -525,7 +536,7 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     CU(c, c->d_partials.reserve((size_t)kPartialStride * ((pe - pb) / 256 + 2)));
     CU(c, cudaEventRecord(c->ev[2], c->st));
     CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
-    nblocks = launch_sweep_pairs(d_pos, c->d_q.p, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
+    nblocks = launch_sweep_pairs(d_pos, c->d_q.p, c->d_types.p, c->d_etas.p, c->ntypes, c->d_abs.p, c->cfg.nl_mode == B200COORD_NL_CLASSIC ? c->d_active.p : nullptr,
                                  c->n_a, pb, pe, c->dpbc, c->dsw, c->d_out.p, c->d_partials.p, c->d_u64.p + 1, c->st);
     CU(c, cudaEventRecord(c->ev[3], c->st));
     weight = 1.0;
@@ -551,6 +562,16 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
         c->sq_valid = true;
       }
       a.sq = c->d_sq.p;
+    }
+    if (c->dsw.type == B200COORD_PAIR_GHBFIX) {
+      if (!c->stype_valid) {
+        CU(c, c->d_stype.reserve(c->n));
+        launch_gather_types(c->d_types.p, c->d_perm.p, c->n, c->d_stype.p, c->st);
+        c->stype_valid = true;
+      }
+      a.stype = c->d_stype.p;
+      a.etas = c->d_etas.p;
+      a.ntypes = c->ntypes;
     }
     a.n_a = c->n_a;
     a.two_groups = c->two_groups;
@@ -683,6 +704,14 @@ int b200coord_pairing_dhenergy(double ionic_strength, double temp, double epsilo
   return B200COORD_OK;
 }
 
+int b200coord_pairing_ghbfix(double dmax, double d0, double c, b200coord_switch* out) {
+  if (!out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  if (!(dmax > d0) || !(c > 0.0) || !(c < 1.0))
+    return fail(nullptr, B200COORD_ERR_INVALID, "GHBFIX needs D_MAX > D_0 and 0 < C < 1");
+  ghbfix_pairing(dmax, d0, c, *out);
+  return B200COORD_OK;
+}
+
 int b200coord_switch_describe(const b200coord_switch* sw, char* buf, size_t buflen) {
   if (!sw || !buf || !buflen) return B200COORD_ERR_INVALID;
   std::snprintf(buf, buflen, "%s", describe_switch(*sw).c_str());
@@ -709,7 +738,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
                 "when using PAIR option, the two groups should have the same number of elements");
   if (cfg->style == B200COORD_STYLE_SINGLELIST && cfg->n_group_b != 0)
     return fail(nullptr, B200COORD_ERR_INVALID, "SINGLELIST style takes GROUPA only");
-  if ((sw->type < 0 || sw->type >= B200COORD_SW_LEPTON) && sw->type != B200COORD_PAIR_DHENERGY)
+  if ((sw->type < 0 || sw->type >= B200COORD_SW_LEPTON) && sw->type != B200COORD_PAIR_DHENERGY &&
+      sw->type != B200COORD_PAIR_GHBFIX)
     return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "switching function is not available on the GPU");
   if (cfg->precision != B200COORD_FP64)
     return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "only the FP64 sweep is built in this version");
@@ -838,6 +868,22 @@ int b200coord_set_charges(b200coord_ctx* c, const double* charges) {
   return B200COORD_OK;
 }
 
+int b200coord_set_types(b200coord_ctx* c, const unsigned* types, unsigned ntypes, const double* etas) {
+  if (!c || !types || !etas || !ntypes) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  for (unsigned i = 0; i < c->n; ++i)
+    if (types[i] >= ntypes) return fail(c, B200COORD_ERR_INVALID, "interaction type out of range");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, c->d_types.reserve(c->n));
+  CU(c, c->d_etas.reserve((size_t)ntypes * ntypes));
+  CU(c, cudaMemcpyAsync(c->d_types.p, types, sizeof(uint32_t) * (size_t)c->n, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->d_etas.p, etas, sizeof(double) * (size_t)ntypes * ntypes, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));  // the caller's arrays may go away
+  c->ntypes = ntypes;
+  c->have_types = true;
+  c->stype_valid = false;
+  return B200COORD_OK;
+}
+
 void b200coord_destroy(b200coord_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -849,7 +895,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_q.release(); c->d_sq.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
   if (c->peer_mode)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)

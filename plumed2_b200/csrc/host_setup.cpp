@@ -348,6 +348,20 @@ double switch_value_host(const b200coord_switch& s, double r) {  // baseSwitch::
   return s.stretch + s.shift;
 }
 
+void ghbfix_pairing(double dmax, double d0, double c, b200coord_switch& out) {
+  std::memset(&out, 0, sizeof(out));
+  out.type = B200COORD_PAIR_GHBFIX;
+  out.d0 = d0;
+  out.dmax = dmax;
+  out.dmax_2 = dmax * dmax;  // dmax_squared, :99
+  const double dmax2 = dmax - d0;  // :106
+  out.preRes = (-c * dmax2 * dmax2) / ((1 - c) * dmax2 * dmax2);  // A :108
+  out.preDfunc = (2 * dmax2) / ((1 - c) * dmax2 * dmax2);         // B :109
+  out.preSecDev = -1 / ((1 - c) * dmax2 * dmax2);                 // C :110
+  out.d = 1 / (c * dmax2 * dmax2);                                // D :111
+  out.c = c * dmax2;                                              // joint of the two pieces, :206
+}
+
 void dhenergy_pairing(double I, double T, double epsilon, double energy_unit, double length_unit, double charge_unit,
                       b200coord_switch& out) {
   std::memset(&out, 0, sizeof(out));
@@ -454,6 +468,10 @@ std::string describe_switch(const b200coord_switch& s) {
                                 "rational", "rational", "rational", "rational", "exponential", "gaussian",
                                 "fastgaussian", "smap", "cubic", "tanh", "cosinus", "nativeq", "lepton", "unset"};
   std::ostringstream os;
+  if (s.type == B200COORD_PAIR_GHBFIX) {
+    os << "GHBFIX pairing: d0=" << s.d0 << " dmax=" << s.dmax << " joint at d0+" << s.c;
+    return os.str();
+  }
   if (s.type == B200COORD_PAIR_DHENERGY) {
     os << "Debye-Hueckel pairing: screening length " << (s.beta > 0.0 ? 1.0 / s.beta : INFINITY) << ", constant/epsilon " << s.lambda;
     return os.str();

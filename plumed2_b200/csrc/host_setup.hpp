@@ -27,6 +27,8 @@ void reduce_lattice(double rows[9]);
 int parse_switch(const std::string& definition, b200coord_switch& out, std::string& err);
 // SwitchingFunction::set(nn,mm,r0,d0) (:1176-1184)
 void rational_switch(int nn, int mm, double r0, double d0, b200coord_switch& out);
+// GHBFIX ctor (src/colvar/GHBFIX.cpp:98-113)
+void ghbfix_pairing(double dmax, double d0, double c, b200coord_switch& out);
 // DHEnergy ctor (src/colvar/DHEnergy.cpp:104-128): k and constant/epsilon
 void dhenergy_pairing(double I, double T, double epsilon, double energy_unit, double length_unit, double charge_unit,
                       b200coord_switch& out);

@@ -89,6 +89,7 @@ void launch_gather(const double* pos, const uint32_t* perm, const uint32_t* abs_
                    cudaStream_t st);
 // sq[k] = charges[perm[k]] (DHENERGY; after every re-sort)
 void launch_gather_charges(const double* charges, const uint32_t* perm, unsigned n, double* sq, cudaStream_t st);
+void launch_gather_types(const uint32_t* types, const uint32_t* perm, unsigned n, uint32_t* stype, cudaStream_t st);
 // the same, plus displacement tracking: track 1 = store the build-time positions in bpos (sorted order),
 // track 2 = atomicMax the largest squared displacement since then into *disp2 (bits of a double)
 void launch_gather_track(int track, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
@@ -118,6 +119,9 @@ constexpr int kPartialStride = 8;  // value, vxx, vxy, vxz, vyy, vyz, vzz, (pad)
 struct SweepArgs {
   const SPos* spos;
   const double* sq;        // charges in sorted order (DHENERGY), else null
+  const uint32_t* stype;   // interaction types in sorted order, the ntypes x ntypes table (GHBFIX), else null
+  const double* etas;
+  unsigned ntypes;
   unsigned n_a;            // atoms of group A (sorted rows [0,n_a) are A rows)
   int two_groups;          // TwoList
   int check_abs;           // skip pairs whose absolute indices coincide (only when the groups overlap)
@@ -159,7 +163,8 @@ struct SweepArgs {
 int launch_sweep_list(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 // PAIR style: one thread per pair (k, k+n_a); writes derivatives straight into out (slot order)
-int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DHENERGY*/, const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
+int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DHENERGY*/,
+                       const uint32_t* types /*slot order*/, const double* etas, unsigned ntypes /*GHBFIX*/, const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
                        unsigned pair_begin, unsigned pair_end, const DevPbc& pbc, const DevSwitch& sw, double* out,
                        double* partials, unsigned long long* evals, cudaStream_t st);
 

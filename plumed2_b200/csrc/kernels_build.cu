@@ -610,6 +610,15 @@ void launch_gather_charges(const double* charges, const uint32_t* perm, unsigned
   if (n) k_gather_charges<<<(n + 255) / 256, 256, 0, st>>>(charges, perm, n, sq);
 }
 
+__global__ void k_gather_types(const uint32_t* __restrict__ t, const uint32_t* __restrict__ perm, unsigned n,
+                               uint32_t* __restrict__ st) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st[k] = t[perm[k]];
+}
+void launch_gather_types(const uint32_t* types, const uint32_t* perm, unsigned n, uint32_t* stype, cudaStream_t st) {
+  if (n) k_gather_types<<<(n + 255) / 256, 256, 0, st>>>(types, perm, n, stype);
+}
+
 void launch_gather_track(int track, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
                          SPos* spos, double* bpos, const DevPbc& pbc, unsigned long long* disp2, cudaStream_t st) {
   const unsigned blocks = (n + 255) / 256;

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     const unsigned far_off = a.row_far_off[k - a.row_begin];
     const bool row_is_b = (k >= a.n_a);
     const double qi = (K == K_DH) ? __ldg(a.sq + k) : 1.0;
+    const uint32_t ti = (K == K_GHB) ? __ldg(a.stype + k) : 0u;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     bool near = false;
     // Two pairs per lane and trip, evaluated as two independent straight-line chains: one pair is a ~25-deep
@@ -63,13 +64,21 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       for (unsigned e0 = 0; e0 < cnt; e0 += 64, e += 64) {  // warp-uniform trip count: the far part votes
         const RecBuf ca = pa, cb = pb;
         double qqa = 1.0, qqb = 1.0;
-        if (K == K_DH) {
+        if (K == K_DH || K == K_GHB) {
           if (e0 == 0u) {
             ia = (e < cnt) ? __ldg(row + e) : 0u;
             ib = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
           }
-          qqa = qi * __ldg(a.sq + ia);
-          qqb = qi * __ldg(a.sq + ib);
+          if (K == K_DH) {
+            qqa = qi * __ldg(a.sq + ia);
+            qqb = qi * __ldg(a.sq + ib);
+          } else {  // eta[type of the pair's first atom][type of its second atom], GHBFIX.cpp:189-197
+            const uint32_t ta = __ldg(a.stype + ia), tb = __ldg(a.stype + ib);
+            const bool fa = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(ca.w));
+            const bool fb = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(cb.w));
+            qqa = __ldg(a.etas + (fa ? ta * a.ntypes + ti : ti * a.ntypes + ta));
+            qqb = __ldg(a.etas + (fb ? tb * a.ntypes + ti : ti * a.ntypes + tb));
+          }
           ia = ja;
           ib = jb;
         }
@@ -150,6 +159,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     int c[3];
     cell_coords(g, (int)a.scell[k], c);
     const double qi = (K == K_DH) ? __ldg(a.sq + k) : 1.0;
+    const uint32_t ti = (K == K_GHB) ? __ldg(a.stype + k) : 0u;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     unsigned cnt = 0;
     bool unused_near = false;
@@ -161,9 +171,15 @@ __global__ void __launch_bounds__(kSweepThreads)
         const SPos pj = load_spos(a.spos + j);
         const bool valid = (j != k) && (!a.check_abs || pj.abs_index != pi.abs_index);
         const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
-        if (valid)
-          pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc,
-                                       (K == K_DH) ? qi * __ldg(a.sq + j) : 1.0);
+        if (valid) {
+          double qq = 1.0;
+          if (K == K_DH) qq = qi * __ldg(a.sq + j);
+          if (K == K_GHB) {
+            const uint32_t tj = __ldg(a.stype + j);
+            qq = __ldg(a.etas + (flip ? tj * a.ntypes + ti : ti * a.ntypes + tj));
+          }
+          pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc, qq);
+        }
       }
     });
     fx = warp_sum(fx);
@@ -197,7 +213,8 @@ __global__ void __launch_bounds__(kSweepThreads)
 // PAIR style: pair k = (k, k+n_a) (NeighborList.cpp:150-152); each atom slot occurs in exactly one pair
 template <int K, int PBC>
 __global__ void __launch_bounds__(kSweepThreads)
-    k_sweep_pairs(const double* __restrict__ pos, const double* __restrict__ charges, const uint32_t* __restrict__ abs_index, const uint8_t* __restrict__ active,
+    k_sweep_pairs(const double* __restrict__ pos, const double* __restrict__ charges, const uint32_t* __restrict__ types,
+                  const double* __restrict__ etas, unsigned ntypes, const uint32_t* __restrict__ abs_index, const uint8_t* __restrict__ active,
                   unsigned n_a, unsigned pair_begin, unsigned pair_end, DevPbc pbc, DevSwitch sw, double* __restrict__ out,
                   double* partials, unsigned long long* evals_out) {
   LaneAcc acc = {0, 0, 0, 0, 0, 0, 0};
@@ -217,8 +234,8 @@ __global__ void __launch_bounds__(kSweepThreads)
       double s, df;
       const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
       eval_switch<K>(sw, r2, s, df);
-      if (K == K_DH) {
-        const double qq = charges[k] * charges[k + n_a];
+      if (K == K_DH || K == K_GHB) {
+        const double qq = (K == K_DH) ? charges[k] * charges[k + n_a] : etas[types[k] * ntypes + types[k + n_a]];
         s *= qq;
         df *= qq;
       }
@@ -299,7 +316,8 @@ static unsigned pick_rows_per_block(unsigned rows) {
   unsigned rpb = rows / (148u * 4u);
   rpb = (rpb / kSweepWarps) * kSweepWarps;
   if (rpb < (unsigned)kSweepWarps) rpb = kSweepWarps;
-  if (rpb > 64u) rpb = 64u;
+  static const unsigned cap = getenv("B200COORD_RPB") ? (unsigned)atoi(getenv("B200COORD_RPB")) : 64u;  // EXPERIMENT
+  if (rpb > cap) rpb = cap;
   return rpb;
 }
 
@@ -355,6 +373,7 @@ static int run_sweep_kind(const SweepArgs& a, const DevPbc& pbc, const DevSwitch
     case K_COS: return run_sweep_pbc<K_COS, LIST>(a, pbc, sw, st);
     case K_NATIVEQ: return run_sweep_pbc<K_NATIVEQ, LIST>(a, pbc, sw, st);
     case K_DH: return run_sweep_pbc<K_DH, LIST>(a, pbc, sw, st);
+    case K_GHB: return run_sweep_pbc<K_GHB, LIST>(a, pbc, sw, st);
     default: return -1;
   }
 }
@@ -367,24 +386,26 @@ int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& s
 }
 
 template <int K>
-static int run_pairs(const double* pos, const double* charges, const uint32_t* abs_index, const uint8_t* active, unsigned n_a, unsigned pb,
+static int run_pairs(const double* pos, const double* charges, const uint32_t* types, const double* etas, unsigned ntypes,
+                     const uint32_t* abs_index, const uint8_t* active, unsigned n_a, unsigned pb,
                      unsigned pe, const DevPbc& pbc, const DevSwitch& sw, double* out, double* partials,
                      unsigned long long* evals, cudaStream_t st) {
   const int nblocks = (int)((pe - pb + kSweepThreads - 1) / kSweepThreads);
   if (nblocks == 0) return 0;
   switch (pbc.type) {
-    case 0: k_sweep_pairs<K, 0><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
-    case 1: k_sweep_pairs<K, 1><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
-    default: k_sweep_pairs<K, 2><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    case 0: k_sweep_pairs<K, 0><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, types, etas, ntypes, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    case 1: k_sweep_pairs<K, 1><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, types, etas, ntypes, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
+    default: k_sweep_pairs<K, 2><<<nblocks, kSweepThreads, 0, st>>>(pos, charges, types, etas, ntypes, abs_index, active, n_a, pb, pe, pbc, sw, out, partials, evals); break;
   }
   return nblocks;
 }
 
-int launch_sweep_pairs(const double* pos, const double* charges, const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
+int launch_sweep_pairs(const double* pos, const double* charges, const uint32_t* types, const double* etas, unsigned ntypes,
+                       const uint32_t* abs_index, const uint8_t* active, unsigned n_a,
                        unsigned pair_begin, unsigned pair_end, const DevPbc& pbc, const DevSwitch& sw, double* out,
                        double* partials, unsigned long long* evals, cudaStream_t st) {
 #define B200_PAIR_CASE(KK) \
-  case KK: return run_pairs<KK>(pos, charges, abs_index, active, n_a, pair_begin, pair_end, pbc, sw, out, partials, evals, st);
+  case KK: return run_pairs<KK>(pos, charges, types, etas, ntypes, abs_index, active, n_a, pair_begin, pair_end, pbc, sw, out, partials, evals, st);
   switch (kind_of(sw.type)) {
     B200_PAIR_CASE(K_FIX6)
     B200_PAIR_CASE(K_FIXN)
@@ -399,6 +420,7 @@ int launch_sweep_pairs(const double* pos, const double* charges, const uint32_t*
     B200_PAIR_CASE(K_COS)
     B200_PAIR_CASE(K_NATIVEQ)
     B200_PAIR_CASE(K_DH)
+    B200_PAIR_CASE(K_GHB)
     default: return -1;
   }
 #undef B200_PAIR_CASE

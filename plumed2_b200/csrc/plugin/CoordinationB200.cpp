@@ -12,12 +12,16 @@
 #include "core/Colvar.h"
 #include "core/PlumedMain.h"
 #include "tools/Communicator.h"
+#include "tools/IFile.h"
+#include "tools/Units.h"
 #include "tools/OpenMP.h"
 #include "tools/Pbc.h"
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -66,6 +70,14 @@ public:
 };
 PLUMED_REGISTER_ACTION(DHEnergyB200, "DHENERGY")
 
+// GHBFIX (src/colvar/GHBFIX.cpp): typed piecewise-polynomial interaction energy between the two groups
+class GHBFIXB200 : public CoordinationBaseB200 {
+public:
+  explicit GHBFIXB200(const ActionOptions&);
+  static void registerKeywords(Keywords& keys);
+};
+PLUMED_REGISTER_ACTION(GHBFIXB200, "GHBFIX")
+
 void CoordinationBaseB200::registerKeywords(Keywords& keys) {
   Colvar::registerKeywords(keys);
   keys.addFlag("SERIAL", false, "Perform the calculation in serial - for debug purpose");
@@ -97,6 +109,17 @@ void DHEnergyB200::registerKeywords(Keywords& keys) {  // DHEnergy.cpp:76-83
   keys.add("compulsory", "TEMP", "300.0", "Simulation temperature (K)");
   keys.add("compulsory", "EPSILON", "80.0", "Dielectric constant of solvent");
   keys.setValueDescription("scalar", "the value of the DHENERGY");
+}
+
+void GHBFIXB200::registerKeywords(Keywords& keys) {  // GHBFIX.cpp:91-103
+  CoordinationBaseB200::registerKeywords(keys);
+  keys.add("optional", "ENERGY_UNITS", "the value of ENERGY_UNITS in the switching function");
+  keys.add("compulsory", "TYPES", "the value of TYPES in the switching function");
+  keys.add("compulsory", "PARAMS", "the value of PARAMS in the switching function");
+  keys.add("compulsory", "D_MAX", "the value of D_MAX in the switching function");
+  keys.add("compulsory", "D_0", "the value of D_0 in the switching function");
+  keys.add("compulsory", "C", "the value of C in the switching function");
+  keys.setValueDescription("scalar", "the GHBFIX interaction energy between the atoms in GROUPA and GROUPB");
 }
 
 void CoordinationBaseB200::check(int rc, const char* what) {
@@ -159,6 +182,77 @@ DHEnergyB200::DHEnergyB200(const ActionOptions& ao) : Action(ao), CoordinationBa
   log << "  at temperature " << T << " K\n";
   log << "  at ionic strength " << I << "M\n";
   log << "  Bibliography " << plumed.cite("Do, Carloni, Varani and Bussi, J. Chem. Theory Comput. 9, 1720 (2013)") << " \n";
+}
+
+GHBFIXB200::GHBFIXB200(const ActionOptions& ao) : Action(ao), CoordinationBaseB200(ao) {  // GHBFIX.cpp:94-172
+  double dmax = 0.0, d0 = 0.0, c = 0.0;
+  std::string types, params, energy_units = "plumed";
+  parse("D_MAX", dmax);
+  parse("D_0", d0);
+  parse("C", c);
+  parse("TYPES", types);
+  parse("PARAMS", params);
+  parse("ENERGY_UNITS", energy_units);
+  b200coord_switch sw;
+  if (b200coord_pairing_ghbfix(dmax, d0, c, &sw) != B200COORD_OK) {
+    error(b200coord_last_error(nullptr));
+  }
+  // the two tables, read exactly as the reference reads them (std::map::operator[] makes a type name that only the
+  // parameter file knows read as index 0)
+  std::map<std::string, unsigned> table;
+  std::vector<unsigned> typesTable;
+  {
+    IFile typesfile;
+    typesfile.link(*this);
+    typesfile.open(types);
+    std::string itype;
+    while (typesfile.scanField("itype", itype).scanField()) {
+      plumed_assert(itype.empty() == false) << "itype is empty";
+      if (table.empty()) {
+        table.insert({itype, 0});
+      } else if (table.count(itype) == 0) {
+        unsigned currentMax = 0;
+        for (const auto& kv : table) {
+          currentMax = std::max(currentMax, kv.second);
+        }
+        table.insert({itype, currentMax + 1});
+      }
+      typesTable.push_back(table[itype]);
+    }
+  }
+  plumed_assert(!typesTable.empty()) << "the TYPES file is empty";
+  const unsigned nt = *std::max_element(typesTable.begin(), typesTable.end()) + 1;
+  std::vector<double> etas(static_cast<std::size_t>(nt) * nt, 0.0);
+  {
+    IFile etafile;
+    etafile.open(params);
+    std::string it, jt;
+    double eta;
+    while (etafile.scanField("itype", it).scanField("jtype", jt).scanField("eta", eta).scanField()) {
+      plumed_assert(it.empty() == false) << "itype is empty";
+      plumed_assert(jt.empty() == false) << "jtype is empty";
+      etas[nt * table[it] + table[jt]] = eta;
+    }
+  }
+  if (energy_units != "plumed") {
+    Units units;
+    units.setEnergy(energy_units);
+    for (auto& e : etas) {
+      e *= units.getEnergy() / getUnits().getEnergy();
+    }
+  }
+  setup(sw, "GHBFIX");
+  // typesTable is indexed by absolute atom index (GHBFIX.cpp:188-196)
+  const unsigned n = getNumberOfAtoms();
+  std::vector<unsigned> mine(n);
+  for (unsigned i = 0; i < n; ++i) {
+    const auto a = getAbsoluteIndex(i).index();
+    plumed_assert(a < typesTable.size()) << "your types table only covers " << typesTable.size()
+                                         << " atoms, but you are trying to access atom number " << (a + 1);
+    mine[i] = typesTable[a];
+  }
+  check(b200coord_set_types(ctx, mine.data(), nt, etas.data()), "set_types");
+  log.printf("  %u interaction types from %s, scaling parameters from %s\n", nt, types.c_str(), params.c_str());
 }
 
 void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {

@@ -19,6 +19,7 @@ enum SwKind {
   K_TANH,
   K_COS,
   K_NATIVEQ,
+  K_GHB,        // GHBFIX pairing (src/colvar/GHBFIX.cpp:186-220): piecewise polynomial, scaled by eta(type,type)
   K_DH,         // DHENERGY pairing (src/colvar/DHEnergy.cpp:130-143): screened Coulomb, scaled by q_i q_j
   K_COUNT
 };
@@ -38,6 +39,7 @@ static inline int kind_of(int type) {
     case 16: return K_COS;
     case 17: return K_NATIVEQ;
     case 32: return K_DH;  // B200COORD_PAIR_DHENERGY
+    case 33: return K_GHB;  // B200COORD_PAIR_GHBFIX
     default: return -1;
   }
 }
@@ -109,7 +111,19 @@ __device__ __forceinline__ void eval_switch(const DevSwitch& p, double r2, doubl
       rinv = (r2 > 0.0) ? fast_rsqrt(r2) : 0.0;
       r = r2 * rinv;
     }
-    if (K == K_DH) {  // DHEnergy::pairing: tmp = exp(-k r)/r * constant/epsilon [* q_i q_j: caller]; dfunc = -(k+1/r) tmp / r
+    if (K == K_GHB) {  // GHBFIX::pairing [* eta: caller]; C1 at D_0, at the joint and at D_MAX: no boundary patch needed
+      if (!(r2 > p.dmax_2)) {
+        const double rdist = r - p.d0;
+        s = -1.0;
+        if (rdist > p.c) {
+          s += p.preRes + rdist * (p.preDfunc + p.preSecDev * rdist);
+          df = (p.preDfunc + 2.0 * p.preSecDev * rdist) * rinv;
+        } else if (rdist > 0.0) {
+          s += p.d * (rdist * rdist);
+          df = 2.0 * p.d * rdist * rinv;
+        }
+      }
+    } else if (K == K_DH) {  // DHEnergy::pairing: tmp = exp(-k r)/r * constant/epsilon [* q_i q_j: caller]; dfunc = -(k+1/r) tmp / r
       const double tmp = exp(-p.beta * r) * rinv * p.lambda;
       s = tmp;
       df = -(p.beta + rinv) * tmp * rinv;
@@ -226,7 +240,7 @@ __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw
   const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
   double s, df;
   eval_switch<K>(sw, r2, s, df);
-  if (K == K_DH) {  // product of the two charges (DHENERGY only; no D_MAX / D_0 boundaries there)
+  if (K == K_DH || K == K_GHB) {  // q_i q_j (DHENERGY) / eta of the two types (GHBFIX); neither has boundary patches
     s *= qq;
     df *= qq;
   }
@@ -295,7 +309,7 @@ __device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitch& s
   double sa, dfa, sb, dfb;
   eval_switch<K>(sw, ra, sa, dfa);
   eval_switch<K>(sw, rb, sb, dfb);
-  if (K == K_DH) {
+  if (K == K_DH || K == K_GHB) {
     sa *= qqa;
     dfa *= qqa;
     sb *= qqb;

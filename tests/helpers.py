@@ -23,7 +23,7 @@ def water_box(n, density=100.0, seed=SEED, triclinic=False, jitter=None):
 
 
 def oracle_eval(pos, box, style, n_a, n_b, switch, do_pbc=True, nl_mode="none", cutoff=1e30, stride=0,
-                abs_index=None, nthreads=4, list_pos=None, fast_list=False, list_box=None, charges=None):
+                abs_index=None, nthreads=4, list_pos=None, fast_list=False, list_box=None, charges=None, types=None):
     """value, deriv, virial, pairs from the C oracle for one frame; list built on list_pos (default pos)"""
     pbc = O.make_pbc(np.zeros(9) if box is None else box)
     st = {"pair": O.NL_PAIR, "two": O.NL_TWOLIST, "single": O.NL_SINGLELIST}[style]
@@ -33,7 +33,7 @@ def oracle_eval(pos, box, style, n_a, n_b, switch, do_pbc=True, nl_mode="none", 
     if nl_mode != "none":
         lpbc = pbc if list_box is None else O.make_pbc(list_box)  # the box of the step the list was built at
         nl.update(lpbc, pos if list_pos is None else list_pos, fast=(fast_list and nl_mode == "classic"))
-    v, d, vir, npairs = O.coordination(nl, pbc, do_pbc, switch, pos, abs_index, nthreads=nthreads, charges=charges)
+    v, d, vir, npairs = O.coordination(nl, pbc, do_pbc, switch, pos, abs_index, nthreads=nthreads, charges=charges, types=types)
     pairs = nl.pairs() if nl_mode != "none" else None
     return v, d, vir, pairs, npairs
 
@@ -56,19 +56,22 @@ def oracle_switch_from_kv(kv):
 
 
 def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast_list=False, list_box=None,
-                     charges=None):
+                     charges=None, types=None):
     """evaluate a `c: COORDINATION ...` (or `c: DHENERGY ...`, with system `charges`) input line with the C oracle on
     full-system positions.  Returns dict(value, deriv (n,3) per requested atom, virial, pairs, atoms)"""
     from plumed2_b200.coordination import parse_atom_list, split_input_line
     _, action, kv, flags = split_input_line(line)
-    assert action in ("COORDINATION", "DHENERGY")
+    assert action in ("COORDINATION", "DHENERGY", "GHBFIX")
     ga = parse_atom_list(kv["GROUPA"])
     gb = parse_atom_list(kv.get("GROUPB"))
     atoms = np.concatenate([ga, gb]).astype(np.uint32)
     style = "single" if gb.size == 0 else ("pair" if "PAIR" in flags else "two")
     mode = "classic" if "NLIST" in flags else ("cells" if "NLISTCELLS" in flags else "none")
-    q = None
-    if action == "DHENERGY":  # keyword defaults of DHEnergy::registerKeywords, DHEnergy.cpp:77-80
+    q, tt = None, None
+    if action == "GHBFIX":  # types = (type per SYSTEM atom, ntypes, etas), e.g. from O.read_ghbfix_tables
+        sw = O.make_ghbfix(float(kv["D_MAX"]), float(kv["D_0"]), float(kv["C"]))
+        tt = (np.ascontiguousarray(np.asarray(types[0], dtype=np.uint32)[atoms]), types[1], types[2])
+    elif action == "DHENERGY":  # keyword defaults of DHEnergy::registerKeywords, DHEnergy.cpp:77-80
         sw = O.make_dhenergy(float(kv.get("I", 1.0)), float(kv.get("TEMP", 300.0)), float(kv.get("EPSILON", 80.0)))
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64)[atoms])
     else:
@@ -78,7 +81,7 @@ def oracle_from_line(line, positions, box, list_positions=None, nthreads=1, fast
     v, d, vir, pairs, npairs = oracle_eval(pos, box, style, int(ga.size), int(gb.size), sw, do_pbc="NOPBC" not in flags,
                                            nl_mode=mode, cutoff=float(kv.get("NL_CUTOFF", 1e30)),
                                            stride=int(kv.get("NL_STRIDE", 0)), abs_index=atoms, nthreads=nthreads,
-                                           list_pos=lpos, fast_list=fast_list, list_box=list_box, charges=q)
+                                           list_pos=lpos, fast_list=fast_list, list_box=list_box, charges=q, types=tt)
     return dict(value=v, deriv=d, virial=vir, pairs=pairs, atoms=atoms, npairs=npairs)
 
 

@@ -96,6 +96,26 @@ def test_dhenergy_sibling_action(body):
     compare(cpu, gpu)
 
 
+@pytest.mark.parametrize("body", [
+    "GROUPA=1-300 GROUPB=301-2000 D_0=0.2 D_MAX=0.5 C=0.8",
+    "GROUPA=1-2000 D_0=0.15 D_MAX=0.5 C=0.6 NLIST NL_CUTOFF=0.7 NL_STRIDE=3 ENERGY_UNITS=kcal/mol",
+    "GROUPA=1-1000 GROUPB=1001-2000 D_0=0.2 D_MAX=0.9 C=0.4 PAIR",
+])
+def test_ghbfix_sibling_action(body, tmp_path):
+    """GHBFIX (src/colvar/GHBFIX.cpp) answered by the plugin: the TYPES / PARAMS files are read by the action itself"""
+    _need()
+    frames, box = trajectory(2000, 5, seed=19, triclinic=True)
+    rng = np.random.default_rng(6)
+    names = ["a", "b", "c"]
+    (tmp_path / "types.dat").write_text("#! FIELDS itype\n" + "\n".join(names[t] for t in rng.integers(0, 3, 2000)) + "\n")
+    (tmp_path / "params.dat").write_text("#! FIELDS itype jtype eta\n" + "\n".join(
+        "%s %s %r" % (i, j, float(rng.standard_normal())) for i in names for j in names if (i, j) != ("c", "c")) + "\nzz a 0.5\n")
+    lines = ["c: GHBFIX %s TYPES=%s PARAMS=%s" % (body, tmp_path / "types.dat", tmp_path / "params.dat"),
+             "RESTRAINT ARG=c AT=1 KAPPA=0.01 SLOPE=0.5"]
+    cpu, gpu = run_both(2000, lines, frames, box, key="GHBFIX")
+    compare(cpu, gpu)
+
+
 def test_metad_with_grid_bias():
     """configs[3] in miniature: COORDINATION driving METAD with a GRID bias through plumed_cmd; forces and
     virial returned every step (hills are deposited, so the bias history must stay identical too)"""
