@@ -36,12 +36,48 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   const unsigned last = min(first + rows_per_block, seg_end);
   unsigned fixmask = 0u;  // rows of this warp with a pair on a D_MAX / D_0 boundary (rows_per_block <= 32 warps' worth)
   const bool far_on = a.force_far || !(__longlong_as_double((long long)*a.disp2_bits) < a.far_disp2_max);
-  for (unsigned k = first + wid; k < last; k += kSweepWarps) {
+  // Row lookahead: a row's first list entries sit behind its metadata, both in HBM, and a near part is only ~4 loop
+  // trips long -- so the metadata is requested two rows ahead and the first four entries one row ahead.
+  const unsigned k0 = first + wid;
+  unsigned long long base1 = 0ull, base2 = 0ull;  // row k, row k + kSweepWarps
+  unsigned cnt1 = 0u, cnt2 = 0u;
+  uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;  // entries lane, lane+32, lane+64, lane+96 of row k's near part
+  if (k0 < last) {
+    base1 = a.row_start[k0 - a.row_begin];
+    cnt1 = a.row_count[k0 - a.row_begin];
+    if (k0 + kSweepWarps < last) {
+      base2 = a.row_start[k0 + kSweepWarps - a.row_begin];
+      cnt2 = a.row_count[k0 + kSweepWarps - a.row_begin];
+    }
+    const uint32_t* __restrict__ r = a.nbr + base1 + lane;
+    h0 = (lane < cnt1) ? __ldg(r) : 0u;
+    h1 = (lane + 32 < cnt1) ? __ldg(r + 32) : 0u;
+    h2 = (lane + 64 < cnt1) ? __ldg(r + 64) : 0u;
+    h3 = (lane + 96 < cnt1) ? __ldg(r + 96) : 0u;
+  }
+  for (unsigned k = k0; k < last; k += kSweepWarps) {
     const SPos pi = load_spos(a.spos + k);
     const unsigned long long wi = ((unsigned long long)pi.slot << 32) | pi.abs_index;
-    const unsigned long long base = a.row_start[k - a.row_begin];
-    const unsigned cnt_near = a.row_count[k - a.row_begin], cnt_far = a.row_far_cnt[k - a.row_begin];
+    const unsigned long long base = base1;
+    const unsigned cnt_near = cnt1, cnt_far = a.row_far_cnt[k - a.row_begin];
     const unsigned far_off = a.row_far_off[k - a.row_begin];
+    const uint32_t j0 = h0, j1 = h1, j2 = h2, j3 = h3;
+    {  // next row: its entries now (metadata is here), the metadata of the row after it
+      const unsigned kn = k + kSweepWarps, knn = k + 2 * kSweepWarps;
+      base1 = base2;
+      cnt1 = cnt2;
+      if (kn < last) {
+        const uint32_t* __restrict__ r = a.nbr + base1 + lane;
+        h0 = (lane < cnt1) ? __ldg(r) : 0u;
+        h1 = (lane + 32 < cnt1) ? __ldg(r + 32) : 0u;
+        h2 = (lane + 64 < cnt1) ? __ldg(r + 64) : 0u;
+        h3 = (lane + 96 < cnt1) ? __ldg(r + 96) : 0u;
+      }
+      if (knn < last) {
+        base2 = a.row_start[knn - a.row_begin];
+        cnt2 = a.row_count[knn - a.row_begin];
+      }
+    }
     const bool row_is_b = (k >= a.n_a);
     const double qi = (K == K_DH) ? __ldg(a.sq + k) : 1.0;
     const uint32_t ti = (K == K_GHB) ? __ldg(a.stype + k) : 0u;
@@ -51,24 +87,20 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     // chain of dependent FP64 operations, so a single chain per warp leaves the FP64 pipe half idle.  Indices
     // are fetched two trips ahead, the two 32-byte records one trip ahead.
     auto part = [&](const uint32_t* __restrict__ row, unsigned cnt, auto far_tag) {
-      constexpr bool FAR = decltype(far_tag)::value;
+      constexpr bool FAR = decltype(far_tag)::value;  // the near part's first four entries were prefetched (j0..j3)
       unsigned e = lane;
-      uint32_t ja = (e < cnt) ? __ldg(row + e) : 0u;
-      uint32_t jb = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
+      uint32_t ja = FAR ? ((e < cnt) ? __ldg(row + e) : 0u) : j0;
+      uint32_t jb = FAR ? ((e + 32 < cnt) ? __ldg(row + e + 32) : 0u) : j1;
       RecBuf pa, pb;
       load_rec(a.spos + ja, pa);
       load_rec(a.spos + jb, pb);
-      ja = (e + 64 < cnt) ? __ldg(row + e + 64) : 0u;
-      jb = (e + 96 < cnt) ? __ldg(row + e + 96) : 0u;
-      uint32_t ia = 0u, ib = 0u;  // entries of the records in flight (DHENERGY looks their charges up)
+      uint32_t ia = ja, ib = jb;  // entries of the records in flight (DHENERGY / GHBFIX look charges / types up)
+      ja = FAR ? ((e + 64 < cnt) ? __ldg(row + e + 64) : 0u) : j2;
+      jb = FAR ? ((e + 96 < cnt) ? __ldg(row + e + 96) : 0u) : j3;
       for (unsigned e0 = 0; e0 < cnt; e0 += 64, e += 64) {  // warp-uniform trip count: the far part votes
         const RecBuf ca = pa, cb = pb;
         double qqa = 1.0, qqb = 1.0;
         if (K == K_DH || K == K_GHB) {
-          if (e0 == 0u) {
-            ia = (e < cnt) ? __ldg(row + e) : 0u;
-            ib = (e + 32 < cnt) ? __ldg(row + e + 32) : 0u;
-          }
           if (K == K_DH) {
             qqa = qi * __ldg(a.sq + ia);
             qqb = qi * __ldg(a.sq + ib);
