@@ -114,6 +114,8 @@ typedef struct b200coord_stats {
   float build_ms_sum;                /* same for list rebuilds */
   unsigned build_count;
   int f32_search;                    /* 1: the last rebuild used the FP32 candidate search (+ exact FP64 band) */
+  unsigned long long super_builds;   /* rebuilds that (re)built the super-list (cutoff + 10 %) from the cells */
+  unsigned long long filter_rebuilds;/* rebuilds that only filtered the super-list (displacement bound held) */
 } b200coord_stats;
 
 typedef struct b200coord_ctx b200coord_ctx;

@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("rebuilds", C.c_ulonglong), ("last_sweep_ms", C.c_float), ("last_build_ms", C.c_float),
                 ("last_h2d_ms", C.c_float), ("last_d2h_ms", C.c_float), ("ncells", C.c_uint * 3),
                 ("pbc_type", C.c_int), ("sweep_ms_sum", C.c_float), ("sweep_count", C.c_uint),
-                ("build_ms_sum", C.c_float), ("build_count", C.c_uint), ("f32_search", C.c_int)]
+                ("build_ms_sum", C.c_float), ("build_count", C.c_uint), ("f32_search", C.c_int),
+                ("super_builds", C.c_ulonglong), ("filter_rebuilds", C.c_ulonglong)]
 
 
 _lib = None

@@ -118,7 +118,8 @@ struct b200coord_ctx {
 
   DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small;
   DevBuf<uint32_t> d_abs, d_perm, d_scell, d_cell_of_slot, d_tmp, d_ccount, d_cstart, d_cursor, d_rowcount, d_nbr;
-  DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch, [10] max displacement^2 (bits)
+  DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch, [10] max displacement^2 since the list build (bits),
+                                                          // [11] the same since the super-list build
   DevBuf<SPos> d_spos;
   DevBuf<uint8_t> d_active;
   DevBuf<unsigned char> d_params;  // [DevPbc | DevSwitch] in global memory for the out-of-line row patch
@@ -134,6 +135,17 @@ struct b200coord_ctx {
   DevBuf<double> d_etas;
   unsigned ntypes = 0;
   bool have_types = false, stype_valid = false;
+  // super-list (kernels.cuh): rows with cutoff NL_CUTOFF + super_delta, the candidate sets of later rebuilds
+  DevBuf<unsigned long long> d_srowstart;
+  DevBuf<uint32_t> d_srowcount, d_snbr;
+  DevBuf<double> d_wpos, d_braw;  // wrapped / raw positions at the super-list build (sorted order)
+  bool super_on = true;          // B200COORD_NO_SUPERLIST=1 turns it off
+  bool super_off = false;        // given up at run time (box or displacements change too fast for it to pay)
+  bool super_valid = false;
+  int super_streak = 0;          // consecutive rebuilds that had to rebuild the super-list as well
+  double super_delta = 0.0, search_cutoff = 0.0;
+  unsigned long super_box_epoch = 0;
+  unsigned long long super_builds = 0, filter_rebuilds = 0;
   DevBuf<double> d_bpos;       // positions the list was built from (sorted order), for the displacement bound
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
@@ -243,7 +255,7 @@ int setup_grid(b200coord_ctx* c, const double* d_pos) {
   DevGrid& g = c->grid;
   std::memset(&g, 0, sizeof(g));
   const bool cells_mode = (c->cfg.nl_mode == B200COORD_NL_CELLS);
-  const double cut = cells_mode ? c->cfg.nl_cutoff : c->cfg.nl_cutoff * (1.0 + 1e-6);
+  const double cut = cells_mode ? c->cfg.nl_cutoff : c->search_cutoff * (1.0 + 1e-6);
   bool use_bbox;
   if (cells_mode) {
     use_bbox = box_is_zero(c->hpbc.box);
@@ -374,25 +386,20 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     return B200COORD_OK;
   }
   CU(c, cudaEventRecord(c->ev[4], c->st));
-  int rc = setup_grid(c, d_pos);
-  if (rc) return rc;
-  rc = ensure_cell_arrays(c);
-  if (rc) return rc;
-  launch_sort(d_pos, c->n, c->n_a, c->two_groups ? 2 : 1, c->grid, c->d_cell_of_slot.p, c->d_ccount.p, c->d_cstart.p,
-              c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->d_bsum.p, c->st);
-  c->stats.kernel_launches += 4;
-  c->sorted_valid = true;
-  c->sq_valid = false;  // new permutation
-  c->stype_valid = false;
+  const unsigned rows = c->row_end - c->row_begin;
+  const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
+  // super-list: wanted for the FP32-search NLIST path of systems whose sorted indices fit 26 bits
+  const bool super_wanted = (mode == B200COORD_NL_CLASSIC) && c->super_on && !c->super_off && c->n <= kSuperIndexMask;
+  c->super_delta = 0.1 * c->cfg.nl_cutoff;
+  c->search_cutoff = c->cfg.nl_cutoff + (super_wanted ? c->super_delta : 0.0);
+  float far2 = INFINITY;
   if (mode == B200COORD_NL_CLASSIC) {
-    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
-    const unsigned rows = c->row_end - c->row_begin;
     CU(c, c->d_rowcount.reserve(rows + 1));
     CU(c, c->d_rowstart.reserve(rows + 1));
     CU(c, c->d_rowfar.reserve(2 * (size_t)rows + 2));
+    CU(c, c->d_bsum.reserve(rows / 1024 + 2));
     c->far_rows = rows;
     // near/far split of the rows: partners beyond D_MAX + a skin of a quarter of the list's buffer go to the far part
-    float far2 = INFINITY;
     if (c->far_split && c->sw.dmax > 0.0 && c->sw.dmax < c->cfg.nl_cutoff) {
       const double rf = c->sw.dmax + 0.25 * (c->cfg.nl_cutoff - c->sw.dmax);
       far2 = (float)(rf * rf);
@@ -400,21 +407,13 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     } else {
       c->far_skin = 0.0;
     }
-    CU(c, c->d_bsum.reserve(rows / 1024 + 2));
-    const double cut2 = c->cfg.nl_cutoff * c->cfg.nl_cutoff;  // NeighborList.cpp:238
+  }
+  // The working list from a candidate source (`launch(mode)`: 0 count, 1 fill, 2 single pass into fixed-capacity rows):
+  // single pass when a capacity is known (1.2 x the longest row of the previous rebuild; an overflow is detected on
+  // the device and answered with the exact two-pass build), else count + scan + fill.
+  auto build_rows = [&](auto&& launch, bool cappable) -> int {
     auto two_pass = [&]() -> int {
-      auto rows_pass = [&](bool fill) {
-        if (c->f32_search)
-          launch_nl_rows_f32(fill ? 1 : 0, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid,
-                             c->dpbc, c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end,
-                             c->d_rowcount.p, c->d_rowstart.p, fill ? c->d_nbr.p : nullptr, 0u, c->d_capinfo.p, far2,
-                             c->d_rowfar.p, c->d_rowfar.p + rows, c->st);
-        else
-          launch_nl_rows(fill, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
-                         c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, fill ? c->d_rowstart.p : nullptr,
-                         fill ? c->d_nbr.p : nullptr, c->st);
-      };
-      rows_pass(false);
+      launch(0);
       launch_scan_rows(c->d_rowcount.p, rows, 3u, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
       CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
@@ -422,33 +421,22 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       CU_LAST(c, "neighbour list count");
       c->nbr_total = c->h_u64[0];
       {
-        // the following rebuilds use fixed-capacity rows (below): size the buffer for that layout now, so that the
-        // second rebuild does not have to free and allocate gigabytes
+        // the following rebuilds use fixed-capacity rows: size the buffer for that layout now, so that the second
+        // rebuild does not have to free and allocate gigabytes
         size_t need = (size_t)c->nbr_total;
-        if (c->f32_search) need = std::max(need, (size_t)rows * next_row_cap(c->h_capinfo[0], 0u));
+        if (cappable) need = std::max(need, (size_t)rows * next_row_cap(c->h_capinfo[0], 0u));
         CU(c, c->d_nbr.reserve(need + 4));
       }
-      rows_pass(true);
+      launch(1);
       c->stats.kernel_launches += 5;
       return B200COORD_OK;
     };
-    if (c->f32_search) {
-      CU(c, c->d_lpos.reserve(c->n));
-      launch_make_local(c->d_spos.p, c->n, c->grid, c->dbox, c->d_lpos.p, c->st);
-      c->stats.kernel_launches += 1;
-    }
     CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
-    if (!c->f32_search) CU(c, cudaMemsetAsync(c->d_rowfar.p, 0, 2 * (size_t)rows * sizeof(uint32_t), c->st));
     bool done = false;
-    if (c->f32_search && c->row_cap > 0) {
-      // single pass into fixed-capacity rows (capacity = 1.2 x the longest row of the previous rebuild);
-      // an overflow is detected on the device and answered with the exact two-pass build
+    if (cappable && c->row_cap > 0) {
       c->nbr_total = (unsigned long long)rows * c->row_cap;
       CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 4));
-      launch_nl_rows_f32(2, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, c->dbox,
-                         cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
-                         c->d_rowstart.p, c->d_nbr.p, c->row_cap, c->d_capinfo.p, far2, c->d_rowfar.p, c->d_rowfar.p + rows,
-                         c->st);
+      launch(2);
       CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
       CU_LAST(c, "neighbour list single-pass build");
@@ -460,7 +448,112 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       int rc2 = two_pass();
       if (rc2) return rc2;
     }
-    if (c->f32_search) c->row_cap = next_row_cap(c->h_capinfo[0], c->row_cap);
+    if (cappable) c->row_cap = next_row_cap(c->h_capinfo[0], c->row_cap);
+    return B200COORD_OK;
+  };
+  auto filter_launch = [&](int m) {
+    launch_nl_filter(m, c->d_spos.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, c->dpbc, c->dbox, cut2,
+                     c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p,
+                     m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2, c->d_rowfar.p,
+                     c->d_rowfar.p + rows, c->st);
+  };
+  bool list_done = false;
+  if (super_wanted && c->super_valid) {
+    // is the super-list still a superset?  same box, and nobody moved by delta/2 since it was built
+    bool ok = (c->box_epoch == c->super_box_epoch);
+    if (ok) {
+      launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);  // frozen permutation
+      CU(c, cudaMemsetAsync(c->d_u64.p + 11, 0, sizeof(unsigned long long), c->st));
+      launch_local_rel(c->d_spos.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_lpos.p, c->d_u64.p + 11, c->st);
+      CU(c, cudaMemcpyAsync(c->h_u64 + 2, c->d_u64.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+      CU(c, cudaStreamSynchronize(c->st));
+      c->stats.kernel_launches += 2;
+      double d2;
+      std::memcpy(&d2, c->h_u64 + 2, sizeof(double));
+      const double lim = 0.5 * c->super_delta * (1.0 - 1e-3);  // margin: FP32 search, rounding of the displacement
+      ok = (d2 < lim * lim);
+    }
+    if (ok) {
+      int rcf = build_rows(filter_launch, true);
+      if (rcf) return rcf;
+      c->super_streak = 0;
+      c->filter_rebuilds++;
+      list_done = true;
+    } else {
+      c->super_valid = false;
+      if (++c->super_streak >= 2) {  // twice in a row: this run changes too fast for a super-list to pay
+        c->super_off = true;
+        c->search_cutoff = c->cfg.nl_cutoff;
+      }
+    }
+  }
+  if (!list_done) {
+  int rc = setup_grid(c, d_pos);
+  if (rc) return rc;
+  rc = ensure_cell_arrays(c);
+  if (rc) return rc;
+  launch_sort(d_pos, c->n, c->n_a, c->two_groups ? 2 : 1, c->grid, c->d_cell_of_slot.p, c->d_ccount.p, c->d_cstart.p,
+              c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->d_bsum.p, c->st);
+  c->stats.kernel_launches += 4;
+  c->sorted_valid = true;
+  c->sq_valid = false;  // new permutation
+  c->stype_valid = false;
+  c->super_valid = false;
+  if (mode == B200COORD_NL_CLASSIC) {
+    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+    const bool build_super = super_wanted && !c->super_off && c->f32_search;
+    if (c->f32_search) {
+      CU(c, c->d_lpos.reserve(c->n));
+      if (build_super) {
+        CU(c, c->d_wpos.reserve(3 * (size_t)c->n));
+        CU(c, c->d_braw.reserve(3 * (size_t)c->n));
+      }
+      launch_make_local(c->d_spos.p, c->n, c->grid, c->dbox, c->d_lpos.p, build_super ? c->d_wpos.p : nullptr,
+                        build_super ? c->d_braw.p : nullptr, c->st);
+      c->stats.kernel_launches += 1;
+    }
+    if (!c->f32_search) CU(c, cudaMemsetAsync(c->d_rowfar.p, 0, 2 * (size_t)rows * sizeof(uint32_t), c->st));
+    if (build_super) {
+      // the super-list itself: two passes (count, scan, fill) over the cells with the extended cutoff
+      const double sc2 = c->search_cutoff * c->search_cutoff;
+      CU(c, c->d_srowcount.reserve(rows + 1));
+      CU(c, c->d_srowstart.reserve(rows + 1));
+      CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
+      auto super_pass = [&](int m) {
+        launch_nl_rows_f32(m, true, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+                           c->dbox, sc2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_srowcount.p,
+                           c->d_srowstart.p, m ? c->d_snbr.p : nullptr, 0u, c->d_capinfo.p, INFINITY, nullptr, nullptr, c->st);
+      };
+      super_pass(0);
+      launch_scan_rows(c->d_srowcount.p, rows, 3u, c->d_bsum.p, c->d_srowstart.p, c->d_u64.p, c->st);
+      CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+      CU(c, cudaStreamSynchronize(c->st));
+      CU_LAST(c, "super-list count");
+      CU(c, c->d_snbr.reserve((size_t)c->h_u64[0] + 4));
+      super_pass(1);
+      c->stats.kernel_launches += 5;
+      c->super_valid = true;
+      c->super_box_epoch = c->box_epoch;
+      c->super_builds++;
+      int rcf = build_rows(filter_launch, true);  // d_lpos of make_local = wrapped position + zero displacement
+      if (rcf) return rcf;
+    } else if (c->f32_search) {
+      int rcf = build_rows([&](int m) {
+        launch_nl_rows_f32(m, false, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+                           c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
+                           c->d_rowstart.p, m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2,
+                           c->d_rowfar.p, c->d_rowfar.p + rows, c->st);
+      }, true);
+      if (rcf) return rcf;
+    } else {
+      int rcf = build_rows([&](int m) {
+        launch_nl_rows(m != 0, c->d_spos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc, cut2, c->n_a,
+                       c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, m ? c->d_rowstart.p : nullptr,
+                       m ? c->d_nbr.p : nullptr, c->st);
+      }, false);
+      if (rcf) return rcf;
+    }
+  }
   }
   CU(c, cudaEventRecord(c->ev[5], c->st));
   c->ev_valid[2] = true;
@@ -670,6 +763,8 @@ void refresh_stats(b200coord_ctx* c) {
   }
   c->stats.pbc_type = c->hpbc.type;
   c->stats.f32_search = c->f32_search ? 1 : 0;
+  c->stats.super_builds = c->super_builds;
+  c->stats.filter_rebuilds = c->filter_rebuilds;
 }
 
 }  // namespace
@@ -853,6 +948,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   to_dev_pbc(c->hpbc, false, c->dpbc);
   if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
   if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   *out = c;
   return B200COORD_OK;
 }
@@ -895,7 +991,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_srowstart.release(); c->d_srowcount.release(); c->d_snbr.release(); c->d_wpos.release(); c->d_braw.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
   if (c->peer_mode)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)

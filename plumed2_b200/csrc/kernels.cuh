@@ -98,10 +98,26 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
                     const DevGrid& g, const DevPbc& pbc, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                     unsigned row_end, uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr,
                     cudaStream_t st);
-// float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits)
-void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st);
+// float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits);
+// wpos/braw (3 doubles per atom, or null): the wrapped and the raw positions, kept for later filter rebuilds
+void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, double* wpos,
+                       double* braw, cudaStream_t st);
+// ---- super-list: a list with cutoff NL_CUTOFF + delta whose rows are the candidate sets of the following rebuilds
+// (k_nl_filter) while 2 * max displacement since its build stays below delta.  An entry = sorted index | image << 26.
+constexpr uint32_t kSuperIndexMask = 0x03ffffffu;
+__host__ __device__ __forceinline__ uint32_t super_image(int wx, int wy, int wz) {
+  return ((uint32_t)(wx + 1) | ((uint32_t)(wy + 1) << 2) | ((uint32_t)(wz + 1) << 4)) << 26;
+}
+// lpos = wpos + minimum-image displacement since the super-list build; *disp2 = max squared displacement (bits)
+void launch_local_rel(const SPos* spos, unsigned n, const double* wpos, const double* braw, const DevPbc& pbc, float4* lpos,
+                      unsigned long long* disp2, cudaStream_t st);
+void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
+                      const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
+                      unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
+                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super /*super-list rows*/, const SPos* spos,
                         const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,

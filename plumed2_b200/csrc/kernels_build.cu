@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(256)
 // cutoff.  FP32 rounding moves r^2 by < band_rel*cutoff^2; candidates inside that band -- a ~1e-5 fraction
 // -- are decided by the reference's exact FP64 operation sequence on the original positions, so the kept
 // SET is the reference's bit for bit.
-__global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid g, DevPbc box, float4* __restrict__ lpos) {
+__global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid g, DevPbc box, float4* __restrict__ lpos,
+                             double* __restrict__ wpos, double* __restrict__ braw) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const SPos p = load_spos(spos + k);
@@ -321,6 +322,45 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
     for (int a = 0; a < 3; ++a) out[a] = fw[0] * box.box[a] + fw[1] * box.box[3 + a] + fw[2] * box.box[6 + a];
   }
   lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
+  if (wpos) {  // super-list build: remember the wrapped and the raw position (k_local_rel continues from them)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      wpos[3 * (size_t)k + a] = out[a];
+      braw[3 * (size_t)k + a] = q[a];
+    }
+  }
+}
+
+// Local copy for a rebuild that FILTERS the super-list: the atom's wrapped position at the super-list build plus its
+// minimum-image displacement since then, so that the periodic image stored with every super-list entry stays the
+// right one even when the MD engine re-wraps the atom.  Also the largest squared displacement (validity of the
+// super-list: 2 * max displacement < its extra cutoff).
+template <int PBC>
+__global__ void __launch_bounds__(256)
+    k_local_rel(const SPos* __restrict__ spos, unsigned n, const double* __restrict__ wpos, const double* __restrict__ braw,
+                DevPbc pbc, float4* __restrict__ lpos, unsigned long long* __restrict__ disp2) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (k < n) {
+    const SPos p = load_spos(spos + k);
+    double dx = p.x - braw[3 * (size_t)k], dy = p.y - braw[3 * (size_t)k + 1], dz = p.z - braw[3 * (size_t)k + 2];
+    min_image_fast<PBC>(pbc, dx, dy, dz);
+    d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    if (!(d2 >= 0.0)) d2 = INFINITY;
+    lpos[k] = make_float4((float)(wpos[3 * (size_t)k] + dx), (float)(wpos[3 * (size_t)k + 1] + dy),
+                          (float)(wpos[3 * (size_t)k + 2] + dz), __uint_as_float(p.abs_index));
+  }
+  __shared__ double sm[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmax(m, sm[w]);
+    if (m > 0.0) atomicMax(disp2, (unsigned long long)__double_as_longlong(m));
+  }
 }
 
 // FP32 constants of the candidate search
@@ -329,7 +369,9 @@ struct SearchF32 {
   float c2_hi, c2_lo;  // cutoff^2 * (1 +- band): outside -> decided in FP32, inside -> exact FP64 test
 };
 
-template <bool FILL, bool CAPPED>
+// SUPER: the rows of the super-list (cutoff + delta, kernels.cuh): entries carry the periodic image they were found
+// through in their top 6 bits, no near/far split.
+template <bool FILL, bool CAPPED, bool SUPER>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
@@ -415,7 +457,122 @@ __global__ void __launch_bounds__(256, 4)
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     bool keep = (j != k) && (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
     if (keep && r2 > c2_lo) keep = exact_keep(j);
-    far = r2 > far2;  // only orders the row: any classification gives the same results
+    far = !SUPER && (r2 > far2);  // only orders the row: any classification gives the same results
+    return keep;
+  };
+  auto emit = [&](bool keep, bool far, uint32_t j, uint32_t img) {
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned mn = __ballot_sync(0xffffffffu, keep && !far), mf = __ballot_sync(0xffffffffu, keep && far);
+    if (FILL && keep) {
+      const unsigned at = far ? total_far + __popc(mf & below) : total + __popc(mn & below);
+      if (at < alloc) nbr[base + (far ? alloc - 1u - at : at)] = j | img;
+    }
+    total += __popc(mn);
+    total_far += __popc(mf);
+  };
+  // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
+  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
+    const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
+    const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
+    const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
+    const uint32_t img = SUPER ? super_image(wx, wyy, wzz) : 0u;
+    for (uint32_t e0 = 0; e0 < m; e0 += 64) {
+      const uint32_t e1 = e0 + lane, e2 = e1 + 32;
+      const bool in1 = e1 < m, in2 = e2 < m;
+      const uint32_t j1 = s + e1, j2 = s + e2;
+      const float4 l1 = __ldg(lpos + (in1 ? j1 : k));
+      const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
+      bool f1, f2;
+      const bool k1 = in1 && test(j1, l1, ox, oy, oz, f1);
+      const bool k2 = in2 && test(j2, l2, ox, oy, oz, f2);
+      emit(k1, f1, j1, img);
+      if (e0 + 32 < m) emit(k2, f2, j2, img);
+    }
+  };
+  for (int col = 0; col < ncol; ++col) {
+    const uint32_t s1 = __shfl_sync(0xffffffffu, sA, col), m1 = __shfl_sync(0xffffffffu, mA, col);
+    const uint32_t s2 = __shfl_sync(0xffffffffu, sB, col), m2 = __shfl_sync(0xffffffffu, mB, col);
+    const int w1 = __shfl_sync(0xffffffffu, wxA, col), w2 = __shfl_sync(0xffffffffu, wxB, col);
+    const int wyy = __shfl_sync(0xffffffffu, wy, col), wzz = __shfl_sync(0xffffffffu, wz, col);
+    if (m1) scan_range(s1, m1, w1, wyy, wzz);
+    if (m2) scan_range(s2, m2, w2, wyy, wzz);
+  }
+  const unsigned all = total + total_far;
+  if (lane == 0) {
+    if (FILL) {
+      row_count[k - row_begin] = min(total, alloc);
+      if (!SUPER) {
+        row_far_cnt[k - row_begin] = min(total_far, alloc);
+        row_far_off[k - row_begin] = alloc - min(total_far, alloc);
+      }
+    } else {
+      row_count[k - row_begin] = all;
+    }
+    if (CAPPED || !FILL) {
+      if (all > cap_info[0]) atomicMax(&cap_info[0], all);
+    }
+    if (CAPPED && all > row_cap) atomicExch(&cap_info[1], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rebuild by FILTERING the super-list: the candidates of row k are the entries of its super-list row (every atom that
+// was within NL_CUTOFF + delta when the super-list was built; valid while 2 * max displacement < delta, checked by
+// the host), seen through the periodic image stored with each entry.  Same FP32 test, same exact FP64 decision
+// inside the rounding band and the same two-ended near/far rows as k_nl_rows_f32 -- ~1/3 of its candidates, no
+// cell tables, no re-sort.
+template <bool FILL, bool CAPPED>
+__global__ void __launch_bounds__(256, 4)
+    k_nl_filter(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const unsigned long long* __restrict__ srow_start,
+                const uint32_t* __restrict__ srow_count, const uint32_t* __restrict__ snbr, DevPbc pbc, SearchF32 f,
+                double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
+                uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr,
+                unsigned row_cap, unsigned* __restrict__ cap_info, float far2, uint32_t* __restrict__ row_far_off,
+                uint32_t* __restrict__ row_far_cnt) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned k = row_begin + warp;
+  if (k >= row_end) return;
+  const float4 li = lpos[k];
+  const unsigned my_abs = __float_as_uint(li.w);
+  const unsigned my_grp = (k < n_a) ? 0u : 1u;
+  const float c2_hi = f.c2_hi, c2_lo = f.c2_lo;
+  const unsigned long long sbase = srow_start[k - row_begin];
+  const unsigned m = srow_count[k - row_begin];
+  unsigned total = 0, total_far = 0;
+  const unsigned long long base = CAPPED ? (unsigned long long)(k - row_begin) * row_cap : (FILL ? row_start[k - row_begin] : 0ull);
+  const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
+  auto exact_keep = [&](uint32_t j) -> bool {  // NeighborList.cpp:246-259 on the unmodified positions
+    const SPos pi = load_spos(spos + k);
+    const SPos pj = load_spos(spos + j);
+    const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
+    double d[3];
+    if (i_first) {
+      d[0] = xsub(pj.x, pi.x);
+      d[1] = xsub(pj.y, pi.y);
+      d[2] = xsub(pj.z, pi.z);
+    } else {
+      d[0] = xsub(pi.x, pj.x);
+      d[1] = xsub(pi.y, pj.y);
+      d[2] = xsub(pi.z, pj.z);
+    }
+    min_image_exact(pbc, d);
+    return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
+  };
+  auto test = [&](bool in, uint32_t entry, bool& far) -> bool {
+    far = false;
+    if (!in) return false;
+    const uint32_t j = entry & kSuperIndexMask;
+    const float wx = (float)((int)((entry >> 26) & 3u) - 1), wy = (float)((int)((entry >> 28) & 3u) - 1),
+                wz = (float)((int)((entry >> 30) & 3u) - 1);
+    const float4 lj = __ldg(lpos + j);
+    const float dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
+    const float dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
+    const float dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    bool keep = (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);  // j != k already holds in the super-list
+    if (keep && r2 > c2_lo) keep = exact_keep(j);
+    far = r2 > far2;
     return keep;
   };
   auto emit = [&](bool keep, bool far, uint32_t j) {
@@ -428,31 +585,16 @@ __global__ void __launch_bounds__(256, 4)
     total += __popc(mn);
     total_far += __popc(mf);
   };
-  // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
-  auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
-    const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
-    const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
-    const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
-    for (uint32_t e0 = 0; e0 < m; e0 += 64) {
-      const uint32_t e1 = e0 + lane, e2 = e1 + 32;
-      const bool in1 = e1 < m, in2 = e2 < m;
-      const uint32_t j1 = s + e1, j2 = s + e2;
-      const float4 l1 = __ldg(lpos + (in1 ? j1 : k));
-      const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
-      bool f1, f2;
-      const bool k1 = in1 && test(j1, l1, ox, oy, oz, f1);
-      const bool k2 = in2 && test(j2, l2, ox, oy, oz, f2);
-      emit(k1, f1, j1);
-      if (e0 + 32 < m) emit(k2, f2, j2);
-    }
-  };
-  for (int col = 0; col < ncol; ++col) {
-    const uint32_t s1 = __shfl_sync(0xffffffffu, sA, col), m1 = __shfl_sync(0xffffffffu, mA, col);
-    const uint32_t s2 = __shfl_sync(0xffffffffu, sB, col), m2 = __shfl_sync(0xffffffffu, mB, col);
-    const int w1 = __shfl_sync(0xffffffffu, wxA, col), w2 = __shfl_sync(0xffffffffu, wxB, col);
-    const int wyy = __shfl_sync(0xffffffffu, wy, col), wzz = __shfl_sync(0xffffffffu, wz, col);
-    if (m1) scan_range(s1, m1, w1, wyy, wzz);
-    if (m2) scan_range(s2, m2, w2, wyy, wzz);
+  const uint32_t* __restrict__ srow = snbr + sbase;
+  for (uint32_t e0 = 0; e0 < m; e0 += 64) {  // two 32-candidate batches per trip: two loads in flight per lane
+    const uint32_t e1 = e0 + lane, e2 = e1 + 32;
+    const bool in1 = e1 < m, in2 = e2 < m;
+    const uint32_t c1 = in1 ? __ldg(srow + e1) : 0u, c2 = in2 ? __ldg(srow + e2) : 0u;
+    bool f1, f2;
+    const bool k1 = test(in1, c1, f1);
+    const bool k2 = test(in2, c2, f2);
+    emit(k1, f1, c1 & kSuperIndexMask);
+    if (e0 + 32 < m) emit(k2, f2, c2 & kSuperIndexMask);
   }
   const unsigned all = total + total_far;
   if (lane == 0) {
@@ -655,11 +797,22 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 #undef B200_NL_LAUNCH
 }
 
-void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, cudaStream_t st) {
-  if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos);
+void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, double* wpos,
+                       double* braw, cudaStream_t st) {
+  if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos, wpos, braw);
+}
+void launch_local_rel(const SPos* spos, unsigned n, const double* wpos, const double* braw, const DevPbc& pbc, float4* lpos,
+                      unsigned long long* disp2, cudaStream_t st) {
+  if (!n) return;
+  const unsigned blocks = (n + 255) / 256;
+  switch (pbc.type) {
+    case 0: k_local_rel<0><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
+    case 1: k_local_rel<1><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
+    default: k_local_rel<2><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
+  }
 }
 
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super, const SPos* spos,
                         const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
@@ -675,10 +828,34 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, cons
 #define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (mode == 0) k_nl_rows_f32<false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  else if (mode == 1) k_nl_rows_f32<true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  else k_nl_rows_f32<true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  if (super) {  // super-list rows: two passes only
+    if (mode == 0) k_nl_rows_f32<false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  } else if (mode == 0) k_nl_rows_f32<false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  else if (mode == 1) k_nl_rows_f32<true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  else k_nl_rows_f32<true, true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
 #undef B200_F32_ARGS
+}
+
+void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
+                      const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
+                      unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
+                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st) {
+  const unsigned rows = row_end - row_begin;
+  if (!rows) return;
+  const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
+  SearchF32 f;
+  for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
+  f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
+  f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
+#define B200_FLT_ARGS spos, lpos, srow_start, srow_count, snbr, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+                      row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
+  if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
+  if (mode == 0) k_nl_filter<false, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  else if (mode == 1) k_nl_filter<true, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  else k_nl_filter<true, true><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+#undef B200_FLT_ARGS
 }
 
 void launch_pair_mask(const double* pos, unsigned n_a, const DevPbc& pbc, double cutoff2, uint8_t* active, cudaStream_t st) {

@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   unsigned fixmask = 0u;  // rows of this warp with a pair on a D_MAX / D_0 boundary (rows_per_block <= 32 warps' worth)
   const bool far_on = a.force_far || !(__longlong_as_double((long long)*a.disp2_bits) < a.far_disp2_max);
   // Row lookahead: a row's first list entries sit behind its metadata, both in HBM, and a near part is only ~4 loop
-  // trips long -- so the metadata is requested two rows ahead and the first four entries one row ahead.
+  // trips long -- so the metadata is requested two rows ahead and the first six entries per lane one row ahead.
   const unsigned k0 = first + wid;
   unsigned long long base1 = 0ull, base2 = 0ull;  // row k, row k + kSweepWarps
   unsigned cnt1 = 0u, cnt2 = 0u;
-  uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;  // entries lane, lane+32, lane+64, lane+96 of row k's near part
+  uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u, h4 = 0u, h5 = 0u;  // entries lane + 32 i of row k's near part
   if (k0 < last) {
     base1 = a.row_start[k0 - a.row_begin];
     cnt1 = a.row_count[k0 - a.row_begin];
@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     h1 = (lane + 32 < cnt1) ? __ldg(r + 32) : 0u;
     h2 = (lane + 64 < cnt1) ? __ldg(r + 64) : 0u;
     h3 = (lane + 96 < cnt1) ? __ldg(r + 96) : 0u;
+    h4 = (lane + 128 < cnt1) ? __ldg(r + 128) : 0u;
+    h5 = (lane + 160 < cnt1) ? __ldg(r + 160) : 0u;
   }
   for (unsigned k = k0; k < last; k += kSweepWarps) {
     const SPos pi = load_spos(a.spos + k);
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     const unsigned long long base = base1;
     const unsigned cnt_near = cnt1, cnt_far = a.row_far_cnt[k - a.row_begin];
     const unsigned far_off = a.row_far_off[k - a.row_begin];
-    const uint32_t j0 = h0, j1 = h1, j2 = h2, j3 = h3;
+    const uint32_t j0 = h0, j1 = h1, j2 = h2, j3 = h3, j4 = h4, j5 = h5;
     {  // next row: its entries now (metadata is here), the metadata of the row after it
       const unsigned kn = k + kSweepWarps, knn = k + 2 * kSweepWarps;
       base1 = base2;
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
         h1 = (lane + 32 < cnt1) ? __ldg(r + 32) : 0u;
         h2 = (lane + 64 < cnt1) ? __ldg(r + 64) : 0u;
         h3 = (lane + 96 < cnt1) ? __ldg(r + 96) : 0u;
+        h4 = (lane + 128 < cnt1) ? __ldg(r + 128) : 0u;
+        h5 = (lane + 160 < cnt1) ? __ldg(r + 160) : 0u;
       }
       if (knn < last) {
         base2 = a.row_start[knn - a.row_begin];
@@ -84,10 +88,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     double fx = 0.0, fy = 0.0, fz = 0.0;
     bool near = false;
     // Two pairs per lane and trip, evaluated as two independent straight-line chains: one pair is a ~25-deep
-    // chain of dependent FP64 operations, so a single chain per warp leaves the FP64 pipe half idle.  Indices
-    // are fetched two trips ahead, the two 32-byte records one trip ahead.
+    // chain of dependent FP64 operations, so a single chain per warp leaves the FP64 pipe half idle.
     auto part = [&](const uint32_t* __restrict__ row, unsigned cnt, auto far_tag) {
-      constexpr bool FAR = decltype(far_tag)::value;  // the near part's first four entries were prefetched (j0..j3)
+      constexpr bool FAR = decltype(far_tag)::value;  // the near part's first six entries were prefetched (j0..j5)
       unsigned e = lane;
       uint32_t ja = FAR ? ((e < cnt) ? __ldg(row + e) : 0u) : j0;
       uint32_t jb = FAR ? ((e + 32 < cnt) ? __ldg(row + e + 32) : 0u) : j1;
@@ -95,8 +98,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       load_rec(a.spos + ja, pa);
       load_rec(a.spos + jb, pb);
       uint32_t ia = ja, ib = jb;  // entries of the records in flight (DHENERGY / GHBFIX look charges / types up)
+      // list entries run two loop trips ahead of the records (HBM latency), the records one trip ahead of the math
       ja = FAR ? ((e + 64 < cnt) ? __ldg(row + e + 64) : 0u) : j2;
       jb = FAR ? ((e + 96 < cnt) ? __ldg(row + e + 96) : 0u) : j3;
+      uint32_t na = FAR ? ((e + 128 < cnt) ? __ldg(row + e + 128) : 0u) : j4;
+      uint32_t nb = FAR ? ((e + 160 < cnt) ? __ldg(row + e + 160) : 0u) : j5;
       for (unsigned e0 = 0; e0 < cnt; e0 += 64, e += 64) {  // warp-uniform trip count: the far part votes
         const RecBuf ca = pa, cb = pb;
         double qqa = 1.0, qqb = 1.0;
@@ -116,8 +122,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
         }
         load_rec(a.spos + ja, pa);
         load_rec(a.spos + jb, pb);
-        ja = (e + 128 < cnt) ? __ldg(row + e + 128) : 0u;
-        jb = (e + 160 < cnt) ? __ldg(row + e + 160) : 0u;
+        ja = na;
+        jb = nb;
+        na = (e + 192 < cnt) ? __ldg(row + e + 192) : 0u;
+        nb = (e + 224 < cnt) ? __ldg(row + e + 224) : 0u;
         pair_term2<K, PBC, ACC, FAR>(pbc, sw, near, pi.x, pi.y, pi.z, wi, a.two_groups, row_is_b, ca, cb, e < cnt,
                                      e + 32 < cnt, a.far_skip2, fx, fy, fz, acc, qqa, qqb);
       }
@@ -348,8 +356,7 @@ static unsigned pick_rows_per_block(unsigned rows) {
   unsigned rpb = rows / (148u * 4u);
   rpb = (rpb / kSweepWarps) * kSweepWarps;
   if (rpb < (unsigned)kSweepWarps) rpb = kSweepWarps;
-  static const unsigned cap = getenv("B200COORD_RPB") ? (unsigned)atoi(getenv("B200COORD_RPB")) : 64u;  // EXPERIMENT
-  if (rpb > cap) rpb = cap;
+  if (rpb > 128u) rpb = 128u;  // 16 rows per warp: 3 % faster than 64 (fewer block tails), no gain beyond
   return rpb;
 }
 

@@ -223,6 +223,44 @@ def test_far_parts_of_rows_and_displacement_bound(sw, tri):
     c.close()
 
 
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("groups", ["GROUPA=1-6000", "GROUPA=1-1500 GROUPB=1201-6000"])
+def test_rebuilds_that_filter_the_super_list(groups, tri):
+    """NLIST rebuilds normally FILTER a super-list (cutoff + 10 %) instead of scanning the cells, as long as nobody has
+    moved by 5 % of the cutoff since it was built.  Slow drift, atoms re-wrapped by box vectors, a jump that invalidates
+    the super-list, a box change and finally motion fast enough to switch the mechanism off: the pair SET of every
+    rebuild must be the reference's, and value / derivatives / virial the frozen-list numbers."""
+    n = 6000
+    pos0, box = water_box(n, 100.0, seed=41, triclinic=tri)
+    rng = np.random.default_rng(7)
+    line = "c: COORDINATION %s SWITCH={RATIONAL R_0=0.3 D_MAX=0.55} NLIST NL_CUTOFF=0.7 NL_STRIDE=2" % groups
+    c = P.Coordination.from_input(line)
+    pos, cur_box, list_pos, list_box = pos0.copy(), box, None, None
+    plan = [0.004] * 6 + ["wrap"] + [0.004] * 3 + [0.06] + [0.004] * 4 + ["box"] + [0.004] * 3 + [0.05] * 5 + [0.004] * 2
+    for step, what in enumerate(plan):
+        if what == "wrap":  # the MD engine re-wraps atoms: jumps by box vectors are not displacements
+            pos = pos.copy()
+            pos[::5] += cur_box[1]
+            pos[::9] -= cur_box[0] + cur_box[2]
+        elif what == "box":
+            cur_box = cur_box * 1.003
+            pos = pos * 1.003
+        else:
+            pos = pos + what * rng.standard_normal(pos.shape) / np.sqrt(3.0)
+        if c.prepare(step):
+            list_pos, list_box = pos.copy(), cur_box
+        c.calculate(pos, cur_box)
+        ref = oracle_from_line(line, pos, cur_box, list_positions=list_pos, list_box=list_box, nthreads=8, fast_list=True)
+        assert_parity(c, ref, "step %d (%s)" % (step, what))
+        if step % 2 == 0:
+            np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]), err_msg="step %d" % step)
+    st = c.stats()
+    assert st["f32_search"] == 1
+    assert st["filter_rebuilds"] >= 4 and st["super_builds"] >= 3, st
+    assert st["filter_rebuilds"] + st["super_builds"] < st["rebuilds"], st  # the fast stretch switched it off
+    c.close()
+
+
 def test_exchange_step_rules():
     c = P.Coordination.from_input("c: COORDINATION GROUPA=1-50 R_0=0.3 NLIST NL_CUTOFF=1.0 NL_STRIDE=5")
     assert c.prepare(0) is True
