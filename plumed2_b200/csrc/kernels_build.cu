@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256, 4)
 // inside the rounding band and the same two-ended near/far rows as k_nl_rows_f32 -- ~1/3 of its candidates, no
 // cell tables, no re-sort.
 template <bool FILL, bool CAPPED>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
     k_nl_filter(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const unsigned long long* __restrict__ srow_start,
                 const uint32_t* __restrict__ srow_count, const uint32_t* __restrict__ snbr, DevPbc pbc, SearchF32 f,
                 double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
@@ -559,19 +559,21 @@ __global__ void __launch_bounds__(256, 4)
     min_image_exact(pbc, d);
     return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
   };
-  auto test = [&](bool in, uint32_t entry, bool& far) -> bool {
+  // `shifted`: some entry of this trip is seen through a periodic image (warp-uniform; rare away from the box faces)
+  auto test = [&](bool in, uint32_t entry, const float4 lj, bool shifted, bool& far) -> bool {
     far = false;
     if (!in) return false;
-    const uint32_t j = entry & kSuperIndexMask;
-    const float wx = (float)((int)((entry >> 26) & 3u) - 1), wy = (float)((int)((entry >> 28) & 3u) - 1),
-                wz = (float)((int)((entry >> 30) & 3u) - 1);
-    const float4 lj = __ldg(lpos + j);
-    const float dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
-    const float dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
-    const float dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+    float dx = lj.x - li.x, dy = lj.y - li.y, dz = lj.z - li.z;
+    if (shifted) {
+      const float wx = (float)((int)((entry >> 26) & 3u) - 1), wy = (float)((int)((entry >> 28) & 3u) - 1),
+                  wz = (float)((int)((entry >> 30) & 3u) - 1);
+      dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
+      dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
+      dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+    }
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     bool keep = (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);  // j != k already holds in the super-list
-    if (keep && r2 > c2_lo) keep = exact_keep(j);
+    if (keep && r2 > c2_lo) keep = exact_keep(entry & kSuperIndexMask);
     far = r2 > far2;
     return keep;
   };
@@ -585,16 +587,30 @@ __global__ void __launch_bounds__(256, 4)
     total += __popc(mn);
     total_far += __popc(mf);
   };
-  const uint32_t* __restrict__ srow = snbr + sbase;
-  for (uint32_t e0 = 0; e0 < m; e0 += 64) {  // two 32-candidate batches per trip: two loads in flight per lane
-    const uint32_t e1 = e0 + lane, e2 = e1 + 32;
-    const bool in1 = e1 < m, in2 = e2 < m;
-    const uint32_t c1 = in1 ? __ldg(srow + e1) : 0u, c2 = in2 ? __ldg(srow + e2) : 0u;
+  // Two 32-candidate batches per trip, software-pipelined: the super-list entries (streamed from HBM) run two trips
+  // ahead, the float4 records they point to (L1/L2 gather) one trip ahead of the test.
+  const uint32_t* __restrict__ srow = snbr + sbase + lane;
+  const uint32_t centre = super_image(0, 0, 0);
+  auto entry_at = [&](uint32_t e) -> uint32_t { return (e + lane < m) ? __ldg(srow + e) : centre; };
+  uint32_t c1 = entry_at(0), c2 = entry_at(32);
+  float4 l1 = __ldg(lpos + (c1 & kSuperIndexMask)), l2 = __ldg(lpos + (c2 & kSuperIndexMask));
+  uint32_t n1 = entry_at(64), n2 = entry_at(96);
+  for (uint32_t e0 = 0; e0 < m; e0 += 64) {
+    const uint32_t a1 = c1, a2 = c2;
+    const float4 p1 = l1, p2 = l2;
+    c1 = n1;
+    c2 = n2;
+    l1 = __ldg(lpos + (c1 & kSuperIndexMask));  // entry 0 (a valid atom) when past the end of the row
+    l2 = __ldg(lpos + (c2 & kSuperIndexMask));
+    n1 = entry_at(e0 + 128);
+    n2 = entry_at(e0 + 160);
+    const bool in1 = e0 + lane < m, in2 = e0 + 32 + lane < m;
+    const bool shifted = __any_sync(0xffffffffu, ((a1 & ~kSuperIndexMask) != centre) || ((a2 & ~kSuperIndexMask) != centre));
     bool f1, f2;
-    const bool k1 = test(in1, c1, f1);
-    const bool k2 = test(in2, c2, f2);
-    emit(k1, f1, c1 & kSuperIndexMask);
-    if (e0 + 32 < m) emit(k2, f2, c2 & kSuperIndexMask);
+    const bool k1 = test(in1, a1, p1, shifted, f1);
+    const bool k2 = test(in2, a2, p2, shifted, f2);
+    emit(k1, f1, a1 & kSuperIndexMask);
+    if (e0 + 32 < m) emit(k2, f2, a2 & kSuperIndexMask);
   }
   const unsigned all = total + total_far;
   if (lane == 0) {
