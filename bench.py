@@ -364,6 +364,8 @@ def run_b200(args):
                             "hbm": {"achieved_gbs": list_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
                                     "peak_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
                "rebuild_ms": build_ms, "rebuilds_in_timed_region": int(st1["build_count"]),
+               "rebuild_kinds": {"super_list_builds_total": int(st1["super_builds"]),
+                                 "filter_rebuilds_total": int(st1["filter_rebuilds"]), "rebuilds_total": int(st1["rebuilds"])},
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                        "h2d_bytes_per_step": int(cnt * 24), "d2h_bytes_per_step": int(cnt * 24 + 80),

@@ -261,6 +261,37 @@ def test_rebuilds_that_filter_the_super_list(groups, tri):
     c.close()
 
 
+def test_switching_the_shortcuts_off_changes_nothing():
+    """B200COORD_NO_SUPERLIST / B200COORD_NO_FAR_SPLIT (A/B switches): same pair sets, same numbers"""
+    n = 8000
+    pos0, box = water_box(n, 100.0, seed=52)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.6} NLIST NL_CUTOFF=0.8 NL_STRIDE=3" % n
+    runs = []
+    for env in ({}, {"B200COORD_NO_SUPERLIST": "1"}, {"B200COORD_NO_FAR_SPLIT": "1"}):
+        os.environ.update(env)
+        try:
+            c = P.Coordination.from_input(line)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        rng = np.random.default_rng(11)
+        pos, out = pos0.copy(), []
+        for step in range(8):
+            pos = pos + 0.006 * rng.standard_normal(pos.shape)
+            c.prepare(step)
+            c.calculate(pos, box)
+            out.append((c.value, c.derivatives.copy(), c.virial.copy(), c.neighbor_pairs() if step % 3 == 0 else None))
+        runs.append((out, c.stats()))
+        c.close()
+    assert runs[0][1]["filter_rebuilds"] >= 2 and runs[1][1]["filter_rebuilds"] == 0 and runs[1][1]["super_builds"] == 0
+    for other, _ in runs[1:]:
+        for (v0, d0, w0, p0), (v1, d1, w1, p1) in zip(runs[0][0], other):
+            assert abs(v0 - v1) <= 1e-12 * abs(v0)
+            assert rel_err(d1, d0) <= 1e-11 and rel_err(w1, w0) <= 1e-11
+            if p0 is not None:
+                np.testing.assert_array_equal(p0, p1)
+
+
 def test_exchange_step_rules():
     c = P.Coordination.from_input("c: COORDINATION GROUPA=1-50 R_0=0.3 NLIST NL_CUTOFF=1.0 NL_STRIDE=5")
     assert c.prepare(0) is True
