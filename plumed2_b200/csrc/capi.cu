@@ -599,7 +599,10 @@ int combine_ranks(b200coord_ctx* c) {
 }
 
 // the whole per-step device pipeline on c->st; d_pos device positions, result left in c->d_out
-int run_device(b200coord_ctx* c, const double* d_pos) {
+// out: where the 3n derivatives go (null = c->d_out; the 10 tail doubles always land in c->d_out);
+// [slot_lo, slot_lo+slot_cnt): the slots of the derivative array the caller is going to read
+int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, unsigned slot_lo = 0u,
+               unsigned slot_cnt = 0xffffffffu) {
   if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
   if (c->dsw.type == B200COORD_PAIR_DHENERGY && !c->have_charges)
     return fail(c, B200COORD_ERR_STATE, "b200coord_set_charges must be called before calculate (DHENERGY)");
@@ -723,8 +726,8 @@ int run_device(b200coord_ctx* c, const double* d_pos) {
     if (rc) return rc;
   }
   if (c->cfg.style != B200COORD_STYLE_PAIR) {
-    launch_unsort_derivs(c->peer_mode ? c->peer_rows[c->parity][c->cfg.rank] : c->d_sderiv.p, c->d_spos.p, c->n, c->d_out.p,
-                         c->st);
+    launch_unsort_derivs(c->peer_mode ? c->peer_rows[c->parity][c->cfg.rank] : c->d_sderiv.p, c->d_perm.p, c->n,
+                         out ? out : c->d_out.p, slot_lo, slot_cnt, c->st);
     c->stats.kernel_launches += 1;
   }
   CU(c, cudaMemcpyAsync(c->h_u64 + 1, c->d_u64.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
@@ -1081,9 +1084,13 @@ int b200coord_calculate(b200coord_ctx* c, const double* pos, double* value, doub
 int b200coord_calculate_device(b200coord_ctx* c, const double* d_pos, double* d_out) {
   if (!c || !d_pos || !d_out) return fail(c, B200COORD_ERR_INVALID, "null argument");
   CU(c, cudaSetDevice(c->device));
-  int rc = run_device(c, d_pos);
+  const bool direct = (c->cfg.style != B200COORD_STYLE_PAIR);  // the un-sort writes the caller's buffer itself
+  int rc = run_device(c, d_pos, direct ? d_out : nullptr);
   if (rc) return rc;
-  CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
+  if (direct)
+    CU(c, cudaMemcpyAsync(d_out + 3 * (size_t)c->n, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToDevice, c->st));
+  else
+    CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
   CU(c, cudaStreamSynchronize(c->st));
   refresh_stats(c);
   return B200COORD_OK;
@@ -1092,9 +1099,13 @@ int b200coord_calculate_device(b200coord_ctx* c, const double* d_pos, double* d_
 int b200coord_enqueue_device(b200coord_ctx* c, const double* d_pos, double* d_out) {
   if (!c || !d_pos || !d_out) return fail(c, B200COORD_ERR_INVALID, "null argument");
   CU(c, cudaSetDevice(c->device));
-  int rc = run_device(c, d_pos);
+  const bool direct = (c->cfg.style != B200COORD_STYLE_PAIR);  // the un-sort writes the caller's buffer itself
+  int rc = run_device(c, d_pos, direct ? d_out : nullptr);
   if (rc) return rc;
-  CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
+  if (direct)
+    CU(c, cudaMemcpyAsync(d_out + 3 * (size_t)c->n, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToDevice, c->st));
+  else
+    CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
   return B200COORD_OK;
 }
 
@@ -1141,7 +1152,8 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
                                    ncclDouble, c->comm, c->st);
     if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
   }
-  int rc = run_device(c, c->d_pos.p);
+  int rc = run_device(c, c->d_pos.p, nullptr, c->cfg.style != B200COORD_STYLE_PAIR ? c->slot_begin : 0u,
+                      c->cfg.style != B200COORD_STYLE_PAIR ? c->slot_count : 0xffffffffu);
   if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[6], c->st));
   if (cnt) CU(c, cudaMemcpyAsync(deriv_slice, c->d_out.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->st));

@@ -187,8 +187,9 @@ int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DH
 // sum the per-block partials in a fixed order and write virial (9) + value behind the 3n derivatives;
 // weight = 0.5 when every pair was visited from both sides (SingleList), 1 otherwise
 void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail /*[10]*/, cudaStream_t st);
-// out[3*slot+c] = sderiv[3*k+c] for all sorted rows k in [0,n)
-void launch_unsort_derivs(const double* sderiv, const SPos* spos, unsigned n, double* out, cudaStream_t st);
+// out[3*slot+c] = sderiv[3*k+c] for the sorted rows k in [0,n) whose slot lies in [slot_lo, slot_lo+slot_cnt)
+void launch_unsort_derivs(const double* sderiv, const uint32_t* perm /*sorted -> slot*/, unsigned n, double* out,
+                          unsigned slot_lo, unsigned slot_cnt /*slots to write*/, cudaStream_t st);
 
 // ---- util
 double measure_dfma_tflops(cudaStream_t st, int sm_count, int reps);

@@ -339,11 +339,14 @@ __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ pa
   }
 }
 
-__global__ void k_unsort_derivs(const double* __restrict__ sderiv, const SPos* __restrict__ spos, unsigned n,
-                                double* __restrict__ out) {
+// only the slots [slot_lo, slot_lo + slot_cnt) are written (a rank that returns just its slice to the host)
+__global__ void k_unsort_derivs(const double* __restrict__ sderiv, const uint32_t* __restrict__ perm, unsigned n,
+                                double* __restrict__ out, unsigned slot_lo, unsigned slot_cnt) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const size_t o = 3 * (size_t)spos[k].slot;
+  const uint32_t slot = perm[k];
+  if (slot - slot_lo >= slot_cnt) return;
+  const size_t o = 3 * (size_t)slot;
   out[o] = sderiv[3 * (size_t)k];
   out[o + 1] = sderiv[3 * (size_t)k + 1];
   out[o + 2] = sderiv[3 * (size_t)k + 2];
@@ -469,8 +472,9 @@ void launch_finalize(const double* partials, int nblocks, double weight, double*
   k_finalize<<<1, 1024, 0, st>>>(partials, nblocks, weight, out_tail);
 }
 
-void launch_unsort_derivs(const double* sderiv, const SPos* spos, unsigned n, double* out, cudaStream_t st) {
-  if (n) k_unsort_derivs<<<(n + 255) / 256, 256, 0, st>>>(sderiv, spos, n, out);
+void launch_unsort_derivs(const double* sderiv, const uint32_t* perm, unsigned n, double* out, unsigned slot_lo,
+                          unsigned slot_cnt, cudaStream_t st) {
+  if (n) k_unsort_derivs<<<(n + 255) / 256, 256, 0, st>>>(sderiv, perm, n, out, slot_lo, slot_cnt);
 }
 
 }  // namespace b200
