@@ -99,6 +99,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(local):
+    """Multi-GPU runs: keep this rank's threads (and therefore its page-locked staging buffers, which are placed by
+    first touch) on the NUMA node its GPU hangs off, so that eight ranks do not push their PCIe traffic through one
+    socket.  Best effort: returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def pinned_array(L, shape):
     """numpy view of page-locked host memory from the library's allocator"""
     nbytes = int(np.prod(shape)) * 8
@@ -199,6 +223,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -369,7 +394,8 @@ def run_b200(args):
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                        "h2d_bytes_per_step": int(cnt * 24), "d2h_bytes_per_step": int(cnt * 24 + 80),
-                       "api": "b200coord_calculate_distributed" if world > 1 else "b200coord_calculate"}}
+                       "api": "b200coord_calculate_distributed" if world > 1 else "b200coord_calculate",
+                       "numa_node_of_rank0": numa_node}}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = reference_cpu(args.ref_sample_atoms, NL_STRIDE, 0, threads)
