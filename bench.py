@@ -255,7 +255,8 @@ def run_b200(args):
     K, W, F = args.steps, args.warmup, args.frames
     frames, box = make_frames(n, F)
     line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
-    c = P.Coordination.from_input(line, device=local, rank=rank, nranks=world)
+    c = P.Coordination.from_input(line, device=local, rank=rank, nranks=world,
+                                  precision=capi.FP32 if args.fp32 else capi.FP64)
     if world > 1:
         ids = [P.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -378,9 +379,11 @@ def run_b200(args):
         list_bytes = 2.0 * my_pairs * 4 + 32.0 * n + 24.0 * rows_mine
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+               "dtype": "f32 pair arithmetic, f64 minimum image and accumulation (opt-in, 1e-5)" if args.fp32 else "f64",
+               "data": "synthetic", "config": workload_config(args, world),
                "pairs_per_step": pairs_per_step, "cv_value": value_cv,
-               "roofline": {"kernel": "k_sweep_list<rationalfix6, orthorhombic>", "bound": "fp64",
+               "roofline": {"kernel": "k_sweep_list<rationalfix6, orthorhombic, %s>" % ("float" if args.fp32 else "double"),
+                            "bound": "fp64",
                             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                             "frac": (achieved / peak.value) if achieved else None, "traffic": traffic,
                             "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -426,6 +429,8 @@ def main():
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--ref-sample-atoms", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32", action="store_true",
+                    help="opt-in FP32 sweep (B200COORD_FP32); the default and the headline number are FP64")
     ap.add_argument("--no-peer", action="store_true", help="combine with NCCL all-gather instead of in-kernel peer stores")
     args = ap.parse_args()
     if args.warmup < 3:

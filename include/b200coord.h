@@ -49,8 +49,10 @@ enum { B200COORD_STYLE_PAIR = 0, B200COORD_STYLE_TWOLIST = 1, B200COORD_STYLE_SI
 /* neighbour-list mode: none (all pairs, NL off), NLIST (distance filtered), NLISTCELLS (27-cell superset) */
 enum { B200COORD_NL_NONE = 0, B200COORD_NL_CLASSIC = 1, B200COORD_NL_CELLS = 2 };
 
-/* arithmetic of the pair sweep: FP64 (default, 1e-10 parity) or the opt-in FP32 mode (1e-5 parity;
- * positions relative to the cell, FP32 pair math, FP64 accumulation) */
+/* arithmetic of the pair sweep: FP64 (default, 1e-10 parity) or the opt-in FP32 mode (1e-5 parity): coordinate
+ * difference and minimum image in FP64, then r^2, switching function, dd and the sums over one row in FP32, rows
+ * added to FP64 accumulators; no exact patch for pairs within rounding of D_MAX / D_0.  The neighbour list is the
+ * same bit-exact list in both modes.  PAIR style always runs its FP64 kernel. */
 enum { B200COORD_FP64 = 0, B200COORD_FP32 = 1 };
 
 /* switching-function kinds, same order as switchContainers::switchType (src/tools/SwitchingFunction.h:36-57) */

@@ -222,6 +222,8 @@ void to_dev_switch(const b200coord_switch& s, DevSwitch& d) {
     default: break;
   }
   d.fix_df = -(double)d.nnf * d.pre_df;
+  d.dmax_2_f64 = d.dmax_2;
+  d.d0_2_f64 = d.d0_2;
 }
 
 void to_dev_pbc(const HostPbc& h, bool use_pbc, DevPbc& d) {
@@ -681,6 +683,8 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.row_far_cnt = c->d_rowfar.p + c->far_rows;
     // a pair with r^2 above this is beyond D_MAX and outside the band in which the exact patch decides (sweep_math.cuh)
     a.far_skip2 = (c->dsw.band_dmax >= 0.0) ? c->dsw.dmax_2 + c->dsw.band_dmax : INFINITY;
+    a.f32 = (c->cfg.precision == B200COORD_FP32) ? 1 : 0;
+    if (a.f32 && c->dsw.band_dmax >= 0.0) a.far_skip2 = c->dsw.dmax_2 * (1.0 + 1e-6);  // above D_MAX^2 after rounding to float
     a.disp2_bits = c->d_u64.p + 10;
     {
       const double half = 0.5 * c->far_skin * (1.0 - 1e-3);  // margin: the split itself was decided in FP32
@@ -839,8 +843,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if ((sw->type < 0 || sw->type >= B200COORD_SW_LEPTON) && sw->type != B200COORD_PAIR_DHENERGY &&
       sw->type != B200COORD_PAIR_GHBFIX)
     return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "switching function is not available on the GPU");
-  if (cfg->precision != B200COORD_FP64)
-    return fail(nullptr, B200COORD_ERR_UNSUPPORTED, "only the FP64 sweep is built in this version");
+  if (cfg->precision != B200COORD_FP64 && cfg->precision != B200COORD_FP32)
+    return fail(nullptr, B200COORD_ERR_INVALID, "precision must be B200COORD_FP64 or B200COORD_FP32");
   const unsigned long long ntot = (unsigned long long)cfg->n_group_a + cfg->n_group_b;
   if (ntot == 0 || ntot > 0x7fffffffull) return fail(nullptr, B200COORD_ERR_INVALID, "atom count out of range");
 

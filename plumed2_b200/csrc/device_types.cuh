@@ -27,24 +27,55 @@ struct DevGrid {
   double origin[3];
 };
 
-// ---- switching function (mirrors b200coord_switch / switchContainers::Data)
-struct DevSwitch {
+// ---- switching function (mirrors b200coord_switch / switchContainers::Data).  T = double, or float for the
+// opt-in FP32 sweep (B200COORD_FP32), whose copy is rounded once on the host (to_f32).
+template <typename T>
+struct DevSwitchT {
   int type;
-  double d0, dmax, dmax_2, invr0, invr0_2, stretch, shift;
+  T d0, dmax, dmax_2, invr0, invr0_2, stretch, shift;
   int nn, mm;
-  double preRes, preDfunc, preSecDev;
+  T preRes, preDfunc, preSecDev;
   int nnf, mmf;
-  double preDfuncF, preSecDevF;
+  T preDfuncF, preSecDevF;
   int a, b;
-  double c, d;
-  double beta, lambda, ref;
+  T c, d;
+  T beta, lambda, ref;
   // derived on the host (to_dev_switch): constant factors of the r^2 fast paths
-  double d0_2;       // d0^2
-  double band_dmax;  // |r^2 - dmax^2| below this -> exact re-evaluation (0 when there is no D_MAX)
-  double band_d0;    // same around d0^2 (negative when d0 == 0: never)
-  double pre_df;   // 2*invr0_2*stretch
-  double fix_df;   // -(N/2)*pre_df for rationalfixN
+  T d0_2;       // d0^2
+  T band_dmax;  // |r^2 - dmax^2| below this -> exact re-evaluation (0 when there is no D_MAX)
+  T band_d0;    // same around d0^2 (negative when d0 == 0: never)
+  T pre_df;   // 2*invr0_2*stretch
+  T fix_df;   // -(N/2)*pre_df for rationalfixN
+  // FP32 sweep only: D_MAX^2 and D_0^2 in double -- which side of a jump a pair is on is decided on the FP64 r^2
+  double dmax_2_f64, d0_2_f64;
 };
+using DevSwitch = DevSwitchT<double>;
+
+static inline float clamp_f32(double v) {  // "infinite" D_MAX (DBL_MAX) and friends stay finite-comparable in float
+  if (v > 3.0e38) return 3.0e38f;
+  if (v < -3.0e38) return -3.0e38f;
+  return (float)v;
+}
+static inline DevSwitchT<float> to_f32(const DevSwitch& s) {
+  DevSwitchT<float> f;
+  f.type = s.type;
+  f.d0 = clamp_f32(s.d0); f.dmax = clamp_f32(s.dmax); f.dmax_2 = clamp_f32(s.dmax_2); f.invr0 = clamp_f32(s.invr0);
+  f.invr0_2 = clamp_f32(s.invr0_2); f.stretch = clamp_f32(s.stretch); f.shift = clamp_f32(s.shift);
+  f.nn = s.nn; f.mm = s.mm;
+  f.preRes = clamp_f32(s.preRes); f.preDfunc = clamp_f32(s.preDfunc); f.preSecDev = clamp_f32(s.preSecDev);
+  f.nnf = s.nnf; f.mmf = s.mmf;
+  f.preDfuncF = clamp_f32(s.preDfuncF); f.preSecDevF = clamp_f32(s.preSecDevF);
+  f.a = s.a; f.b = s.b;
+  f.c = clamp_f32(s.c); f.d = clamp_f32(s.d);
+  f.beta = clamp_f32(s.beta); f.lambda = clamp_f32(s.lambda); f.ref = clamp_f32(s.ref);
+  f.d0_2 = clamp_f32(s.d0_2);
+  f.band_dmax = -1.0f;  // no boundary patch in FP32 mode
+  f.band_d0 = -1.0f;
+  f.pre_df = clamp_f32(s.pre_df); f.fix_df = clamp_f32(s.fix_df);
+  f.dmax_2_f64 = s.dmax_2;
+  f.d0_2_f64 = s.d0_2;
+  return f;
+}
 
 // sorted atom record: position + slot bookkeeping in one 32-byte sector
 struct __align__(32) SPos {
@@ -138,6 +169,10 @@ __device__ __forceinline__ double flip_sign(double x, unsigned sign_mask /*0 or 
   return __hiloint2double(__double2hiint(x) ^ (int)sign_mask, __double2loint(x));
 }
 
+__device__ __forceinline__ float flip_sign(float x, unsigned sign_mask /*0 or 0x80000000*/) {
+  return __int_as_float(__float_as_int(x) ^ (int)sign_mask);
+}
+
 // ------------------------------------------------------------------ fast arithmetic for the sweep
 // floor(x) with two FP64 adds: the first add rounds toward -inf onto the integer grid of the magic constant
 // (valid for |x| < 2^51).  Callers pass x = t + 0.5 (folded into an FMA) to get the round-half-up of
@@ -170,12 +205,27 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
   return x;
 }
 
-__device__ __forceinline__ double ipow_dev(double base, int e) {  // Tools::fastpow (Tools.h:581-595)
+// FP32 sweep: MUFU seed + one Newton step (~1 ulp)
+__device__ __forceinline__ float fast_rcp(float a) {
+  float x;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+  const float e = fmaf(-a, x, 1.0f);
+  return fmaf(x, e, x);
+}
+__device__ __forceinline__ float fast_rsqrt(float a) {
+  float x;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+  const float e = fmaf(-0.5f * a * x, x, 0.5f);
+  return fmaf(x, e, x);
+}
+
+template <typename T>
+__device__ __forceinline__ T ipow_dev(T base, int e) {  // Tools::fastpow (Tools.h:581-595)
   if (e < 0) {
     e = -e;
     base = fast_rcp(base);
   }
-  double r = 1.0;
+  T r = T(1.0);
   while (e) {
     if (e & 1) r *= base;
     e >>= 1;

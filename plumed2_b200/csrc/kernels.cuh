@@ -158,6 +158,7 @@ struct SweepArgs {
   const unsigned long long* disp2_bits;  // largest squared displacement since the rebuild (bits of a double)
   double far_disp2_max;                  // visit the far parts unless disp2 < this
   int force_far;                         // box changed since the rebuild: always visit them
+  int f32;                               // B200COORD_FP32: FP32 pair arithmetic (kernels_sweep_f32.cu)
   // implicit ranges (no NL / NLISTCELLS)
   const uint32_t* scell;
   const uint32_t* cstart;

@@ -89,6 +89,7 @@ void CoordinationBaseB200::registerKeywords(Keywords& keys) {
   keys.add("atoms", "GROUPA", "First list of atoms");
   keys.add("atoms", "GROUPB", "Second list of atoms (if empty, N*(N-1)/2 pairs in GROUPA are counted)");
   keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
+  keys.addFlag("GPU_FP32", false, "opt-in FP32 pair arithmetic (1e-5 relative instead of 1e-10; FP64 minimum image and accumulation). Also switched on by the B200COORD_FP32=1 environment variable");
 }
 
 void CoordinationB200::registerKeywords(Keywords& keys) {
@@ -291,6 +292,15 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
     device = std::atoi(env);
   }
   parse("GPU_DEVICE", device);
+  bool fp32 = false;
+  if (const char* env = std::getenv("B200COORD_FP32")) {
+    fp32 = std::atoi(env) != 0;
+  }
+  {
+    bool flag = false;
+    parseFlag("GPU_FP32", flag);
+    fp32 = fp32 || flag;
+  }
   checkRead();
 
   addValueWithDerivatives();
@@ -306,7 +316,7 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   b200coord_config cfg;
   cfg.abi_version = B200COORD_ABI_VERSION;
   cfg.device = device;
-  cfg.precision = B200COORD_FP64;
+  cfg.precision = fp32 ? B200COORD_FP32 : B200COORD_FP64;
   cfg.style = gb.empty() ? B200COORD_STYLE_SINGLELIST : (dopair ? B200COORD_STYLE_PAIR : B200COORD_STYLE_TWOLIST);
   cfg.n_group_a = ga.size();
   cfg.n_group_b = gb.size();
@@ -333,6 +343,9 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   char desc[512];
   b200coord_switch_describe(&sw, desc, sizeof(desc));
   log.printf("  B200-native %s (libb200coord, sm_100a kernels)\n", what);
+  if (fp32) {
+    log.printf("  FP32 pair arithmetic (opt-in): results within 1e-5 of the FP64 path\n");
+  }
   log.printf("  between two groups of %u and %u atoms\n", static_cast<unsigned>(ga.size()), static_cast<unsigned>(gb.size()));
   log.printf(pbc ? "  using periodic boundary conditions\n" : "  without periodic boundary conditions\n");
   if (dopair) {

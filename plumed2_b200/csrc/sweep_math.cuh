@@ -44,46 +44,77 @@ static inline int kind_of(int type) {
   }
 }
 
+// overloads so that the switching functions below are written once for double and float
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double exp_t(double x) { return exp(x); }
+__device__ __forceinline__ float exp_t(float x) { return expf(x); }
+__device__ __forceinline__ double pow_t(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ float pow_t(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double tanh_t(double x) { return tanh(x); }
+__device__ __forceinline__ float tanh_t(float x) { return tanhf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ void sincospi_t(double x, double* s, double* c) { sincospi(x, s, c); }
+__device__ __forceinline__ void sincospi_t(float x, float* s, float* c) { sincospif(x, s, c); }
 // rational<>::doRational (SwitchingFunction.cpp:258-283); res/dfn preset to preRes/preDfunc(F)
-__device__ __forceinline__ void rational_generic(bool simplified, double x, double secdev, int N, int M, double& res,
-                                                 double& dfn) {
+template <typename T>
+__device__ __forceinline__ void rational_generic(bool simplified, T x, T secdev, int N, int M, T& res, T& dfn) {
   if (simplified) {
-    const double t = ipow_dev(x, N - 1);
-    res = fast_rcp(fma(t, x, 1.0));
-    dfn = -(double)N * t * res * res;
+    const T t = ipow_dev(x, N - 1);
+    res = fast_rcp(fma_t(t, x, T(1.0)));
+    dfn = -(T)N * t * res * res;
   } else {
-    const double hi = 1.0 + 5.0e10 * 2.220446049250313e-16, lo = 1.0 - 5.0e10 * 2.220446049250313e-16;
+    const T hi = T(1.0 + 5.0e10 * 2.220446049250313e-16), lo = T(1.0 - 5.0e10 * 2.220446049250313e-16);
     if (!((x > lo) && (x < hi))) {
-      const double tn = ipow_dev(x, N - 1);
-      const double tm = ipow_dev(x, M - 1);
-      const double num = fma(-tn, x, 1.0);
-      const double iden = fast_rcp(fma(-tm, x, 1.0));
+      const T tn = ipow_dev(x, N - 1);
+      const T tm = ipow_dev(x, M - 1);
+      const T num = fma_t(-tn, x, T(1.0));
+      const T iden = fast_rcp(fma_t(-tm, x, T(1.0)));
       res = num * iden;
-      dfn = (((double)M * res * tm) - ((double)N * tn)) * iden;
+      dfn = (((T)M * res * tm) - ((T)N * tn)) * iden;
     } else {
-      const double dx = x - 1.0;
-      res = res + dx * (dfn + 0.5 * dx * secdev);
+      const T dx = x - T(1.0);
+      res = res + dx * (dfn + T(0.5) * dx * secdev);
       dfn = dfn + dx * secdev;
     }
   }
 }
 
+// FP32 sweep: the general quotient (1-x^n)/(1-x^m) and its derivative cancel around x = 1 (1e-4 relative in float
+// at |x-1| = 1e-3, and no Taylor window is both wide and accurate enough), so this rarely used kind (MM != 2 NN)
+// evaluates its quotient in FP64; the simplified form 1/(1+x^n) has no cancellation and stays in FP32.
+__device__ __forceinline__ void rational_generic(bool simplified, float x, float secdev, int N, int M, float& res,
+                                                 float& dfn) {
+  if (simplified) {
+    rational_generic<float>(true, x, secdev, N, M, res, dfn);
+  } else {
+    double r = (double)res, d = (double)dfn;
+    rational_generic<double>(false, (double)x, (double)secdev, N, M, r, d);
+    res = (float)r;
+    dfn = (float)d;
+  }
+}
+
 // (s, df=(1/r) ds/dr) of SwitchingFunction::calculateSqr for kind K, stretch/shift and D_MAX applied
-template <int K, bool XS = false>
-__device__ __forceinline__ void eval_switch(const DevSwitch& p, double r2, double& s, double& df) {
-  s = 0.0;
-  df = 0.0;
+// in_dmax / above_d0 (FP32 sweep): 0 / 1 = the side of D_MAX resp. D_0 the pair is on, decided by the caller on the
+// FP64 r^2 (the value or the derivative jumps there); -1 = decide here.
+template <int K, bool XS = false, typename T = double>
+__device__ __forceinline__ void eval_switch(const DevSwitchT<T>& p, T r2, T& s, T& df, int in_dmax = -1,
+                                            int above_d0 = -1) {
+  s = T(0.0);
+  df = T(0.0);
   if (K == K_FIX6 || K == K_FIXN || K == K_RAT_R2) {
-    if (r2 <= p.dmax_2) {  // fixedRational<N>::calculateSqr :203-215, rational<fast>::calculateSqr :289-303
-      const double y = r2 * p.invr0_2;
-      double res, d;
+    if ((in_dmax >= 0) ? (in_dmax != 0) : (r2 <= p.dmax_2)) {  // fixedRational<N>::calculateSqr :203-215, rational<fast>::calculateSqr :289-303
+      const T y = r2 * p.invr0_2;
+      T res, d;
       if (K == K_FIX6) {
-        const double t = y * y;
-        res = fast_rcp(fma(t, y, 1.0));
+        const T t = y * y;
+        res = fast_rcp(fma_t(t, y, T(1.0)));
         df = (t * res) * (res * p.fix_df);
       } else if (K == K_FIXN) {
-        const double t = ipow_dev(y, p.nnf - 1);
-        res = fast_rcp(fma(t, y, 1.0));
+        const T t = ipow_dev(y, p.nnf - 1);
+        res = fast_rcp(fma_t(t, y, T(1.0)));
         df = (t * res) * (res * p.fix_df);
       } else {
         res = p.preRes;
@@ -91,89 +122,90 @@ __device__ __forceinline__ void eval_switch(const DevSwitch& p, double r2, doubl
         rational_generic(p.type == 9, y, p.preSecDevF, p.nnf, p.mmf, res, d);
         df = d * p.pre_df;
       }
-      s = fma(res, p.stretch, p.shift);
+      s = fma_t(res, p.stretch, p.shift);
     }
   } else if (K == K_FASTGAUSS) {  // fastgaussianSwitch::calculateSqr :414-431
-    if (r2 < p.dmax_2) {
-      s = 1.0;
-      if (r2 > 0.0) {
-        const double res = exp(-0.5 * r2);
+    if ((in_dmax >= 0) ? (in_dmax != 0) : (r2 < p.dmax_2)) {
+      s = T(1.0);
+      if (r2 > T(0.0)) {
+        const T res = exp_t(T(-0.5) * r2);
         df = -res * p.stretch;
-        s = fma(res, p.stretch, p.shift);
+        s = fma_t(res, p.stretch, p.shift);
       }
     }
   } else {  // baseSwitch::calculateSqr -> calculate(sqrt(r2)) :135-149, :181-183
-    double rinv, r;
+    T rinv, r;
     if (XS) {  // correctly rounded sqrt: comparisons of r with D_0 / D_MAX match the reference bit for bit
-      r = sqrt(r2);
-      rinv = (r2 > 0.0) ? 1.0 / r : 0.0;
+      r = sqrt_t(r2);
+      rinv = (r2 > T(0.0)) ? T(1.0) / r : T(0.0);
     } else {
-      rinv = (r2 > 0.0) ? fast_rsqrt(r2) : 0.0;
+      rinv = (r2 > T(0.0)) ? fast_rsqrt(r2) : T(0.0);
       r = r2 * rinv;
     }
     if (K == K_GHB) {  // GHBFIX::pairing [* eta: caller]; C1 at D_0, at the joint and at D_MAX: no boundary patch needed
-      if (!(r2 > p.dmax_2)) {
-        const double rdist = r - p.d0;
-        s = -1.0;
+      if ((in_dmax >= 0) ? (in_dmax != 0) : !(r2 > p.dmax_2)) {
+        const T rdist = r - p.d0;
+        s = T(-1.0);
         if (rdist > p.c) {
           s += p.preRes + rdist * (p.preDfunc + p.preSecDev * rdist);
-          df = (p.preDfunc + 2.0 * p.preSecDev * rdist) * rinv;
-        } else if (rdist > 0.0) {
+          df = (p.preDfunc + T(2.0) * p.preSecDev * rdist) * rinv;
+        } else if (rdist > T(0.0)) {
           s += p.d * (rdist * rdist);
-          df = 2.0 * p.d * rdist * rinv;
+          df = T(2.0) * p.d * rdist * rinv;
         }
       }
     } else if (K == K_DH) {  // DHEnergy::pairing: tmp = exp(-k r)/r * constant/epsilon [* q_i q_j: caller]; dfunc = -(k+1/r) tmp / r
-      const double tmp = exp(-p.beta * r) * rinv * p.lambda;
+      const T tmp = exp_t(-p.beta * r) * rinv * p.lambda;
       s = tmp;
       df = -(p.beta + rinv) * tmp * rinv;
     } else if (K == K_NATIVEQ) {  // nativeqSwitch::calculate :524-549
-      if (r <= p.dmax) {
-        double res = 1.0;
-        if (r > p.d0) {
-          const double e = exp(p.beta * (r - p.lambda * p.ref));
-          res = fast_rcp(1.0 + e);
-          df = -p.beta * fast_rcp(e + 2.0 + fast_rcp(e)) * rinv * p.stretch;
+      if ((in_dmax >= 0) ? (in_dmax != 0) : (r <= p.dmax)) {
+        T res = T(1.0);
+        if ((above_d0 >= 0) ? (above_d0 != 0) : (r > p.d0)) {
+          const T e = exp_t(p.beta * (r - p.lambda * p.ref));
+          res = fast_rcp(T(1.0) + e);
+          df = -p.beta * fast_rcp(e + T(2.0) + fast_rcp(e)) * rinv * p.stretch;
         }
-        s = fma(res, p.stretch, p.shift);
+        s = fma_t(res, p.stretch, p.shift);
       }
-    } else if (!(r > p.dmax)) {
-      const double x = (r - p.d0) * p.invr0;
-      if (x > 0.0) {
-        double f, fp;
+    } else if ((in_dmax >= 0) ? (in_dmax != 0) : !(r > p.dmax)) {
+      T x = (r - p.d0) * p.invr0;
+      if (above_d0 > 0) x = (x > T(1e-30)) ? x : T(1e-30);  // FP64 says beyond D_0: keep the float x on that side
+      if ((above_d0 >= 0) ? (above_d0 != 0) : (x > T(0.0))) {
+        T f, fp;
         if (K == K_RAT_R) {
           f = p.preRes;
           fp = p.preDfunc;
           rational_generic(p.type == 8, x, p.preSecDev, p.nn, p.mm, f, fp);
         } else if (K == K_EXP) {  // :375-387
-          f = exp(-x);
+          f = exp_t(-x);
           fp = -f;
         } else if (K == K_GAUSS) {  // :389-401
-          f = exp(-0.5 * x * x);
+          f = exp_t(T(-0.5) * x * x);
           fp = -x * f;
         } else if (K == K_SMAP) {  // :434-455
-          const double sx = p.c * ipow_dev(x, p.a);
-          f = pow(1.0 + sx, p.d);
-          fp = -(double)p.b * sx * fast_rcp(x) * f * fast_rcp(1.0 + sx);
+          const T sx = p.c * ipow_dev(x, p.a);
+          f = pow_t(T(1.0) + sx, p.d);
+          fp = -(T)p.b * sx * fast_rcp(x) * f * fast_rcp(T(1.0) + sx);
         } else if (K == K_CUBIC) {  // :457-469
-          const double t1 = x - 1.0, t2 = fma(2.0, x, 1.0);
-          fp = 2.0 * t1 * t2 + 2.0 * t1 * t1;
+          const T t1 = x - T(1.0), t2 = fma_t(T(2.0), x, T(1.0));
+          fp = T(2.0) * t1 * t2 + T(2.0) * t1 * t1;
           f = t1 * t1 * t2;
         } else if (K == K_TANH) {  // :471-486
-          const double t1 = tanh(x);
-          fp = fma(t1, t1, -1.0);
-          f = 1.0 - t1;
+          const T t1 = tanh_t(x);
+          fp = fma_t(t1, t1, T(-1.0));
+          f = T(1.0) - t1;
         } else {  // K_COS :488-507
-          f = 0.0;
-          fp = 0.0;
-          if (x <= 1.0) {
-            double sn, cs;
-            sincospi(x, &sn, &cs);
-            f = 0.5 * (cs + 1.0);
-            fp = -0.5 * 3.141592653589793238462643383279502884 * sn;
+          f = T(0.0);
+          fp = T(0.0);
+          if (x <= T(1.0)) {
+            T sn, cs;
+            sincospi_t(x, &sn, &cs);
+            f = T(0.5) * (cs + T(1.0));
+            fp = T(-0.5 * 3.141592653589793238462643383279502884) * sn;
           }
         }
-        s = fma(f, p.stretch, p.shift);
+        s = fma_t(f, p.stretch, p.shift);
         df = fp * p.stretch * p.invr0 * rinv;  // applystretch :124-130
       } else {
         s = p.stretch + p.shift;
@@ -218,9 +250,12 @@ __device__ __forceinline__ ExactPair exact_pair(const DevPbc& pbc, const DevSwit
   return o;
 }
 
-struct LaneAcc {
-  double val, vxx, vxy, vxz, vyy, vyz, vzz;
+template <typename T>
+struct LaneAccT {
+  T val, vxx, vxy, vxz, vyy, vyz, vzz;
 };
+using LaneAcc = LaneAccT<double>;
+using LaneAccF = LaneAccT<float>;
 
 // one pair seen from atom i.  The reference evaluates every pair once, as distance = pos[i1]-pos[i0] with
 // (i0,i1) = (GROUPA atom, GROUPB atom) resp. (lower, higher index) (NeighborList.cpp:147-166), and gives
@@ -269,6 +304,49 @@ __device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitch& sw
     acc.vyy = fma(gy, dy, acc.vyy);
     acc.vyz = fma(gy, dz, acc.vyz);
     acc.vzz = fma(gz, dz, acc.vzz);
+  }
+}
+
+// ---- opt-in FP32 sweep (B200COORD_FP32, 1e-5 parity).  The coordinate difference and the minimum image stay in
+// FP64 -- a difference of box-sized coordinates rounded to float would carry ~1e-6 nm of absolute error, 1e-5 of a
+// contact distance -- and the image vector is then rounded once (6e-8 relative).  r^2, the switching function, dd and
+// the sums over one row run on the FP32 pipe; rows are added to the FP64 block accumulators.  Which side of D_MAX and
+// D_0 a pair is on -- the derivative (without stretch also the value) jumps there, and among 1e8 pairs a few always lie
+// within FP32 rounding of the jump -- is decided on the FP64 r^2 (3 more FP64 operations per pair); the 1e-10 exact
+// patch of the FP64 sweep is not applied.
+template <int K>
+__device__ __forceinline__ bool inside_dmax(const DevSwitchT<float>& sw, double r2d) {
+  return (K == K_FASTGAUSS) ? (r2d < sw.dmax_2_f64) : (r2d <= sw.dmax_2_f64);  // fastgaussian: strict (:414)
+}
+template <int K, int PBC, bool ACC, bool INLINE_EXACT = false>
+__device__ __forceinline__ void pair_term(const DevPbc& pbc, const DevSwitchT<float>& sw, bool&, double xi, double yi,
+                                          double zi, const SPos& pj, bool flip, float& fx, float& fy, float& fz,
+                                          LaneAccF& acc, float qq = 1.0f) {
+  const unsigned sgn = flip ? 0x80000000u : 0u;
+  double ex = flip_sign(pj.x - xi, sgn), ey = flip_sign(pj.y - yi, sgn), ez = flip_sign(pj.z - zi, sgn);
+  min_image_fast<PBC>(pbc, ex, ey, ez);
+  const float dx = (float)ex, dy = (float)ey, dz = (float)ez;
+  const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
+  float s, df;
+  eval_switch<K>(sw, r2, s, df, inside_dmax<K>(sw, r2d), r2d > sw.d0_2_f64);
+  if (K == K_DH || K == K_GHB) {
+    s *= qq;
+    df *= qq;
+  }
+  const float dfs = flip_sign(df, sgn);
+  fx = fmaf(-dfs, dx, fx);
+  fy = fmaf(-dfs, dy, fy);
+  fz = fmaf(-dfs, dz, fz);
+  if (ACC) {
+    const float gx = df * dx, gy = df * dy, gz = df * dz;
+    acc.val += s;
+    acc.vxx = fmaf(gx, dx, acc.vxx);
+    acc.vxy = fmaf(gx, dy, acc.vxy);
+    acc.vxz = fmaf(gx, dz, acc.vxz);
+    acc.vyy = fmaf(gy, dy, acc.vyy);
+    acc.vyz = fmaf(gy, dz, acc.vyz);
+    acc.vzz = fmaf(gz, dz, acc.vzz);
   }
 }
 
@@ -342,6 +420,79 @@ __device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitch& s
   return true;
 }
 
+// FP32 flavour of pair_term2 (see the FP32 pair_term above)
+template <int K, int PBC, bool ACC, bool FAR>
+__device__ __forceinline__ bool pair_term2(const DevPbc& pbc, const DevSwitchT<float>& sw, bool&, double xi, double yi,
+                                           double zi, unsigned long long wi, int two_groups, bool row_is_b,
+                                           const RecBuf& pa, const RecBuf& pb, bool va, bool vb, float far_skip2,
+                                           float& fx, float& fy, float& fz, LaneAccF& acc, float qqa = 1.0f,
+                                           float qqb = 1.0f) {
+  const bool flipa = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pa.w));
+  const bool flipb = two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(pb.w));
+  const unsigned sga = flipa ? 0x80000000u : 0u, sgb = flipb ? 0x80000000u : 0u;
+  double eax = flip_sign(pa.x - xi, sga), eay = flip_sign(pa.y - yi, sga), eaz = flip_sign(pa.z - zi, sga);
+  double ebx = flip_sign(pb.x - xi, sgb), eby = flip_sign(pb.y - yi, sgb), ebz = flip_sign(pb.z - zi, sgb);
+  min_image_fast<PBC>(pbc, eax, eay, eaz);
+  min_image_fast<PBC>(pbc, ebx, eby, ebz);
+  const float ax = (float)eax, ay = (float)eay, az = (float)eaz;
+  const float bx = (float)ebx, by = (float)eby, bz = (float)ebz;
+  const float ra = fmaf(az, az, fmaf(ay, ay, ax * ax));
+  const float rb = fmaf(bz, bz, fmaf(by, by, bx * bx));
+  if (FAR) {
+    if (__all_sync(0xffffffffu, (!va || ra > far_skip2) && (!vb || rb > far_skip2))) return false;
+  }
+  const double rad = fma(eaz, eaz, fma(eay, eay, eax * eax));
+  const double rbd = fma(ebz, ebz, fma(eby, eby, ebx * ebx));
+  float sa, dfa, sb, dfb;
+  eval_switch<K>(sw, ra, sa, dfa, inside_dmax<K>(sw, rad), rad > sw.d0_2_f64);
+  eval_switch<K>(sw, rb, sb, dfb, inside_dmax<K>(sw, rbd), rbd > sw.d0_2_f64);
+  if (K == K_DH || K == K_GHB) {
+    sa *= qqa;
+    dfa *= qqa;
+    sb *= qqb;
+    dfb *= qqb;
+  }
+  if (!va) {
+    sa = 0.0f;
+    dfa = 0.0f;
+  }
+  if (!vb) {
+    sb = 0.0f;
+    dfb = 0.0f;
+  }
+  const float da = flip_sign(dfa, sga), db = flip_sign(dfb, sgb);
+  fx = fmaf(-da, ax, fmaf(-db, bx, fx));
+  fy = fmaf(-da, ay, fmaf(-db, by, fy));
+  fz = fmaf(-da, az, fmaf(-db, bz, fz));
+  if (ACC) {
+    const float gax = dfa * ax, gay = dfa * ay, gaz = dfa * az;
+    const float gbx = dfb * bx, gby = dfb * by, gbz = dfb * bz;
+    acc.val += sa + sb;
+    acc.vxx = fmaf(gax, ax, fmaf(gbx, bx, acc.vxx));
+    acc.vxy = fmaf(gax, ay, fmaf(gbx, by, acc.vxy));
+    acc.vxz = fmaf(gax, az, fmaf(gbx, bz, acc.vxz));
+    acc.vyy = fmaf(gay, ay, fmaf(gby, by, acc.vyy));
+    acc.vyz = fmaf(gay, az, fmaf(gby, bz, acc.vyz));
+    acc.vzz = fmaf(gaz, az, fmaf(gbz, bz, acc.vzz));
+  }
+  return true;
+}
+
+// the accumulator a row's pair terms go to: the block's FP64 lane accumulators, or in FP32 mode a per-row FP32
+// set that is added to them when the row is done
+__device__ __forceinline__ LaneAcc& row_acc(LaneAcc& block, LaneAcc&) { return block; }
+__device__ __forceinline__ LaneAccF& row_acc(LaneAcc&, LaneAccF& row) { return row; }
+__device__ __forceinline__ void flush_row_acc(LaneAcc&, const LaneAcc&) {}
+__device__ __forceinline__ void flush_row_acc(LaneAcc& block, const LaneAccF& row) {
+  block.val += (double)row.val;
+  block.vxx += (double)row.vxx;
+  block.vxy += (double)row.vxy;
+  block.vxz += (double)row.vxz;
+  block.vyy += (double)row.vyy;
+  block.vyz += (double)row.vyz;
+  block.vzz += (double)row.vzz;
+}
+
 // Patch of one row in which some lane saw a boundary pair (rare: constructed inputs).  Walks the row again, and for
 // every pair on a boundary returns (exact contribution - fast contribution).  Out of line and by value so that the
 // hot loop keeps its registers; parameters come from global memory.
@@ -400,6 +551,12 @@ __device__ __forceinline__ void apply_fix(const RowFix& f, bool accumulate, doub
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
