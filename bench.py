@@ -67,6 +67,19 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+        self.windows = []  # [t0, t1] of the timed regions (time.time()); samples are stamped on receipt
+
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi takes a moment to start: do not enter a timed region before it delivers"""
+        t_end = time.time() + timeout
+        while not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+
+    def open_window(self):
+        self.windows.append([time.time(), None])
+
+    def close_window(self):
+        self.windows[-1][1] = time.time()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -79,7 +92,7 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self._stop_evt.is_set():
                     break
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
         except Exception:
             pass
 
@@ -87,16 +100,20 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        inside = [r for r in self.rows if any(w[0] <= r[-1] <= (w[1] or r[-1]) for w in self.windows)]
+        which = "timed regions (value + e2e)"
+        if not inside:  # regions shorter than the sampling period: fall back to everything sampled under load
+            inside, which = self.rows, "whole run (timed regions shorter than the 20 ms sampling period)"
+        sm = [float(r[0]) for r in inside if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
+        for r in inside:
+            if len(r) >= 8:
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
 def pin_to_gpu_numa_node(local):
@@ -292,8 +309,9 @@ def run_b200(args):
     st0 = c.stats()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    sampler.wait_first()
     barrier()
+    sampler.open_window()
     capi.check(L.b200coord_stream_mark(ctx, 0), ctx)
     for _ in range(K):
         c.prepare(step)
@@ -302,8 +320,8 @@ def run_b200(args):
     capi.check(L.b200coord_stream_mark(ctx, 1), ctx)
     ms = C.c_float(0)
     capi.check(L.b200coord_stream_elapsed_ms(ctx, C.byref(ms)), ctx)
+    sampler.close_window()
     barrier()
-    clocks = sampler.stop()
     st1 = c.stats()
     value_ms = allmax(float(ms.value))
     pairs_per_step = allsum(float(st1["nl_size"]))
@@ -343,6 +361,7 @@ def run_b200(args):
         e2e_step(step)
         step += 1
     barrier()
+    sampler.open_window()
     capi.check(L.b200coord_stream_mark(ctx, 0), ctx)
     t0 = time.perf_counter()
     for _ in range(K):
@@ -351,6 +370,8 @@ def run_b200(args):
     capi.check(L.b200coord_stream_mark(ctx, 1), ctx)
     capi.check(L.b200coord_stream_elapsed_ms(ctx, C.byref(ms)), ctx)
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.close_window()
+    clocks = sampler.stop()
     barrier()
     e2e_ms = allmax(max(float(ms.value), wall_ms))
     st2 = c.stats()
