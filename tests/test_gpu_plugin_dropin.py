@@ -64,6 +64,32 @@ def trajectory(n, nframes, seed, triclinic=False, step=0.01):
     return frames, box
 
 
+def test_fp32_mode_through_the_plugin(monkeypatch):
+    """the opt-in FP32 sweep, switched on by the environment (same plumed.dat for both arms) and by the plugin's
+    additive GPU_FP32 flag; 1e-5 against the reference's CPU action"""
+    _need()
+    frames, box = trajectory(2000, 5, seed=14)
+    body = "GROUPA=1-2000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3"
+    lines = ["c: COORDINATION " + body, "RESTRAINT ARG=c AT=100 KAPPA=0.01 SLOPE=0.5"]
+    monkeypatch.setenv("B200COORD_FP32", "1")
+    cpu, gpu = run_both(2000, lines, frames, box)
+    assert "FP32 pair arithmetic" in open("/tmp/plumed_gpu.log").read()
+    compare(cpu, gpu, tol=1e-5)
+    assert any(np.any(a["forces"] != b["forces"]) for a, b in zip(cpu, gpu))  # a different arithmetic did run
+    monkeypatch.delenv("B200COORD_FP32")
+    p = R.Plumed(2000, ["LOAD FILE=" + PLUGIN, lines[0] + " GPU_FP32", lines[1]], watch=("c",), log="/tmp/plumed_gpu32.log")
+    flagged = []
+    for step, pos in enumerate(frames):
+        r = p.calc(step, pos, box)
+        r["values"] = {"c": p.value("c")}
+        flagged.append(r)
+    p.close()
+    assert "FP32 pair arithmetic" in open("/tmp/plumed_gpu32.log").read()
+    compare(cpu, flagged, tol=1e-5)
+    for a, b in zip(gpu, flagged):  # same mode either way: identical results
+        assert a["values"]["c"] == b["values"]["c"] and np.array_equal(a["forces"], b["forces"])
+
+
 @pytest.mark.parametrize("body", [
     "GROUPA=1-2000 R_0=0.3",
     "GROUPA=1-2000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",

@@ -148,7 +148,8 @@ def test_create_rejects_bad_configs():
         return capi.Config(*[base[k] for k, _ in capi.Config._fields_])
     for bad in [cfg(abi_version=99), cfg(style=7), cfg(nl_mode=2, style=0, n_group_a=5, n_group_b=5, nl_cutoff=1.0, nl_stride=1),
                 cfg(nl_mode=1, nl_cutoff=0.0, nl_stride=1), cfg(nl_mode=1, nl_cutoff=1.0, nl_stride=0),
-                cfg(style=0, n_group_a=4, n_group_b=6), cfg(n_group_a=0), cfg(style=2, n_group_b=3)]:
+                cfg(style=0, n_group_a=4, n_group_b=6), cfg(n_group_a=0), cfg(style=2, n_group_b=3),
+                cfg(precision=2), cfg(precision=-1)]:  # B200COORD_FP64 = 0 and B200COORD_FP32 = 1 are the two modes
         rc = L.b200coord_create(C.byref(bad), C.byref(sw), ap, C.byref(out))
         assert rc == capi.ERR_INVALID and not out.value
         assert len(L.b200coord_last_error(None)) > 0
