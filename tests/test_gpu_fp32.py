@@ -138,6 +138,27 @@ def test_fp32_dhenergy_typed_sibling():
     c.close()
 
 
+@pytest.mark.parametrize("mode", ["", "NLIST NL_CUTOFF=0.8 NL_STRIDE=3", "NLISTCELLS NL_CUTOFF=0.8 NL_STRIDE=3"])
+def test_fp32_ghbfix_typed_sibling(mode):
+    n = 4000
+    pos, box = water_box(n, 100.0, seed=9, triclinic=True)
+    rng = np.random.default_rng(4)
+    ntypes = 5
+    types = rng.integers(0, ntypes, n).astype(np.uint32)
+    etas = rng.standard_normal((ntypes, ntypes))  # asymmetric on purpose
+    line = "c: GHBFIX GROUPA=1-%d D_0=0.2 D_MAX=0.6 C=0.7 TYPES=x PARAMS=y %s" % (n, mode)
+    c = P.Coordination.from_input(line, precision=capi.FP32)
+    c.set_types(types, ntypes, etas)
+    c.prepare(0)
+    c.calculate(pos, box)
+    ref = oracle_from_line(line, pos, box, types=(types, ntypes, etas.ravel()), nthreads=8)
+    # mixed-sign scaling parameters: the sum cancels, compare on the scale of its largest derivative
+    assert abs(c.value - ref["value"]) <= TOL32 * max(abs(ref["value"]), np.abs(ref["deriv"]).max()), (c.value, ref["value"])
+    assert rel_err(c.derivatives, ref["deriv"]) <= TOL32, rel_err(c.derivatives, ref["deriv"])
+    assert rel_err(c.virial, ref["virial"]) <= TOL32
+    c.close()
+
+
 def test_precision_outside_the_enum_is_refused():
     with pytest.raises(capi.B200CoordError):
         P.Coordination.from_input("c: COORDINATION GROUPA=1-10 R_0=0.3", precision=7)
