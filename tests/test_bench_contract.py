@@ -35,3 +35,35 @@ def test_non_root_ranks_of_reference_arm_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3",
                           "--warmup", "3"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_clock_sampler_counts_only_samples_inside_the_timed_regions(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler: samples are stamped on receipt, the report covers the timed regions, and a
+    region shorter than the sampling period falls back to everything sampled (and says so)"""
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nwhile true; do echo '1965, 1965, 400.5, Not Active, Not Active, Not Active, Active'; sleep 0.02; done\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    s.wait_first()
+    assert s.rows, "the sampler must have delivered before a timed region opens"
+    time.sleep(0.1)
+    before = len(s.rows)
+    s.open_window()
+    time.sleep(0.15)
+    s.close_window()
+    time.sleep(0.1)
+    r = s.stop()
+    assert r["window"].startswith("timed regions") and 1 <= r["samples"] < len(s.rows) - before + 3
+    assert r["samples"] < len(s.rows) and r["sm_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.start()
+    s.wait_first()
+    s.open_window()
+    s.close_window()
+    r = s.stop()
+    assert r["window"].startswith("whole run") and r["samples"] >= 1
