@@ -147,6 +147,15 @@ struct b200coord_ctx {
   unsigned long super_box_epoch = 0;
   unsigned long long super_builds = 0, filter_rebuilds = 0;
   DevBuf<double> d_bpos;       // positions the list was built from (sorted order), for the displacement bound
+                               // (continuous coordinates u in u_mode)
+  // u_mode (FP32-search lists): the sorted records hold continuous coordinates u = wrapped position at the sort +
+  // minimum-image displacement since (kernels_build.cu: k_sort_init / k_gather_u); img_list: the list entries carry
+  // the periodic image their partner was found through, and k_sweep_img (sweep_img.cuh) may take the step
+  bool u_mode = false, img_list = false;
+  unsigned long sort_box_epoch = 0;   // box at the last re-sort (wpos / braw / images refer to it)
+  DevBuf<uint4> d_meta;               // per row {start / 4, near count, far offset, far count}
+  int img_variant = 2;                // resident blocks per SM the image sweep is compiled for (B200COORD_IMG_VARIANT)
+  bool img_on = true;                 // B200COORD_NO_IMG_SWEEP=1: always the general kernel
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
   unsigned* h_capinfo = nullptr;
@@ -454,7 +463,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     return B200COORD_OK;
   };
   auto filter_launch = [&](int m) {
-    launch_nl_filter(m, c->d_spos.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, c->dpbc, c->dbox, cut2,
+    launch_nl_filter(m, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, c->dpbc, c->dbox, cut2,
                      c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p,
                      m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2, c->d_rowfar.p,
                      c->d_rowfar.p + rows, c->st);
@@ -464,12 +473,13 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     // is the super-list still a superset?  same box, and nobody moved by delta/2 since it was built
     bool ok = (c->box_epoch == c->super_box_epoch);
     if (ok) {
-      launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);  // frozen permutation
+      // frozen permutation: continuous coordinates, their float copy, and the largest displacement since the sort
       CU(c, cudaMemsetAsync(c->d_u64.p + 11, 0, sizeof(unsigned long long), c->st));
-      launch_local_rel(c->d_spos.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_lpos.p, c->d_u64.p + 11, c->st);
+      launch_gather_u(true, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_spos.p,
+                      c->d_bpos.p, c->d_lpos.p, c->d_u64.p + 11, c->st);
       CU(c, cudaMemcpyAsync(c->h_u64 + 2, c->d_u64.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
-      c->stats.kernel_launches += 2;
+      c->stats.kernel_launches += 1;
       double d2;
       std::memcpy(&d2, c->h_u64 + 2, sizeof(double));
       const double lim = 0.5 * c->super_delta * (1.0 - 1e-3);  // margin: FP32 search, rounding of the displacement
@@ -502,18 +512,21 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   c->stype_valid = false;
   c->super_valid = false;
   if (mode == B200COORD_NL_CLASSIC) {
-    launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
     const bool build_super = super_wanted && !c->super_off && c->f32_search;
+    c->u_mode = c->f32_search;
+    c->img_list = c->f32_search && c->n <= kSuperIndexMask;
+    c->sort_box_epoch = c->box_epoch;
+    CU(c, c->d_bpos.reserve(3 * (size_t)c->n));
     if (c->f32_search) {
       CU(c, c->d_lpos.reserve(c->n));
-      if (build_super) {
-        CU(c, c->d_wpos.reserve(3 * (size_t)c->n));
-        CU(c, c->d_braw.reserve(3 * (size_t)c->n));
-      }
-      launch_make_local(c->d_spos.p, c->n, c->grid, c->dbox, c->d_lpos.p, build_super ? c->d_wpos.p : nullptr,
-                        build_super ? c->d_braw.p : nullptr, c->st);
-      c->stats.kernel_launches += 1;
+      CU(c, c->d_wpos.reserve(3 * (size_t)c->n));
+      CU(c, c->d_braw.reserve(3 * (size_t)c->n));
+      launch_sort_init(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->grid, c->dbox, c->dpbc.type != 0, c->d_lpos.p, c->d_wpos.p,
+                       c->d_braw.p, c->d_spos.p, c->d_bpos.p, c->st);
+    } else {  // tiny boxes: FP64 search on the caller's positions, general sweep
+      launch_gather_track(1, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->d_bpos.p, c->dpbc, c->d_u64.p + 10, c->st);
     }
+    c->stats.kernel_launches += 1;
     if (!c->f32_search) CU(c, cudaMemsetAsync(c->d_rowfar.p, 0, 2 * (size_t)rows * sizeof(uint32_t), c->st));
     if (build_super) {
       // the super-list itself: two passes (count, scan, fill) over the cells with the extended cutoff
@@ -522,7 +535,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       CU(c, c->d_srowstart.reserve(rows + 1));
       CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
       auto super_pass = [&](int m) {
-        launch_nl_rows_f32(m, true, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+        launch_nl_rows_f32(m, true, true, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
                            c->dbox, sc2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_srowcount.p,
                            c->d_srowstart.p, m ? c->d_snbr.p : nullptr, 0u, c->d_capinfo.p, INFINITY, nullptr, nullptr, c->st);
       };
@@ -541,7 +554,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       if (rcf) return rcf;
     } else if (c->f32_search) {
       int rcf = build_rows([&](int m) {
-        launch_nl_rows_f32(m, false, c->d_spos.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+        launch_nl_rows_f32(m, false, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
                            c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
                            c->d_rowstart.p, m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2,
                            c->d_rowfar.p, c->d_rowfar.p + rows, c->st);
@@ -556,6 +569,14 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       if (rcf) return rcf;
     }
   }
+  }
+  if (mode == B200COORD_NL_CLASSIC) {
+    c->build_box_epoch = c->box_epoch;
+    if (c->img_list) {
+      CU(c, c->d_meta.reserve(rows + 1));
+      launch_pack_meta(rows, c->d_rowstart.p, c->d_rowcount.p, c->d_rowfar.p, c->d_rowfar.p + rows, c->d_meta.p, c->d_u64.p + 13, c->st);
+      c->stats.kernel_launches += 1;
+    }
   }
   CU(c, cudaEventRecord(c->ev[5], c->st));
   c->ev_valid[2] = true;
@@ -625,6 +646,7 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
   const DevPbc* pbc_g = reinterpret_cast<const DevPbc*>(c->d_params.p);
   const DevSwitch* sw_g = reinterpret_cast<const DevSwitch*>(c->d_params.p + sizeof(DevPbc));
   CU(c, cudaMemsetAsync(c->d_u64.p + 1, 0, sizeof(unsigned long long), c->st));
+  CU(c, cudaMemsetAsync(c->d_u64.p + 12, 0, sizeof(unsigned long long), c->st));
   int nblocks;
   double weight;
   if (c->cfg.style == B200COORD_STYLE_PAIR) {
@@ -640,13 +662,22 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     weight = 1.0;
     c->stats.kernel_launches += 1;
   } else {
-    const bool track = (c->cfg.nl_mode == B200COORD_NL_CLASSIC);
-    if (track) {
-      CU(c, c->d_bpos.reserve(3 * (size_t)c->n));
-      if (need_rebuild) c->build_box_epoch = c->box_epoch;
-      CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));  // this step's displacement
-      launch_gather_track(need_rebuild ? 1 : 2, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->d_bpos.p, c->dpbc,
-                          c->d_u64.p + 10, c->st);
+    const bool classic = (c->cfg.nl_mode == B200COORD_NL_CLASSIC);
+    // box changed since the sort: the continuous coordinates (and the images) no longer mean anything
+    const bool u_now = classic && c->u_mode && c->box_epoch == c->sort_box_epoch;
+    if (classic) {
+      if (need_rebuild) {  // rebuild() left records, displacement origin and a zero displacement behind
+        CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));
+      } else if (u_now) {
+        CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));
+        launch_gather_u(false, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_spos.p,
+                        c->d_bpos.p, nullptr, c->d_u64.p + 10, c->st);
+      } else if (c->u_mode) {  // far parts are visited anyway (force_far): no displacement needed
+        launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
+      } else {
+        CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));
+        launch_gather_track(2, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->d_bpos.p, c->dpbc, c->d_u64.p + 10, c->st);
+      }
     } else {
       launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
     }
@@ -687,10 +718,33 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     if (a.f32 && c->dsw.band_dmax >= 0.0) a.far_skip2 = c->dsw.dmax_2 * (1.0 + 1e-6);  // above D_MAX^2 after rounding to float
     a.disp2_bits = c->d_u64.p + 10;
     {
-      const double half = 0.5 * c->far_skin * (1.0 - 1e-3);  // margin: the split itself was decided in FP32
-      a.far_disp2_max = half * half;
+      // The near/far split was decided on the FP32 r^2 of the search, which is off by up to band_rel * cutoff^2,
+      // i.e. r by up to ~band_rel * cutoff: that much of the skin is not available to the atoms.
+      const double half = 0.5 * (c->far_skin - c->band_rel * c->cfg.nl_cutoff) * (1.0 - 1e-3);
+      a.far_disp2_max = (half > 0.0) ? half * half : 0.0;
     }
     a.force_far = (c->box_epoch != c->build_box_epoch) ? 1 : 0;
+    a.idx_mask = c->img_list ? kSuperIndexMask : 0xffffffffu;
+    a.row_meta = c->d_meta.p;
+    a.pos = d_pos;
+    a.executed = c->d_u64.p + 12;
+    // image sweep: valid while a listed pair cannot have a second image as close as the stored one, i.e. while
+    // NL_CUTOFF + 2 * displacement < half the smallest box height (any lattice vector is at least that long)
+    a.img_disp2_max = 0.0;
+    const bool img_now = classic && u_now && c->img_list && c->img_on && !a.f32;
+    if (img_now) {
+      if (c->dpbc.type == 0) {
+        a.img_disp2_max = INFINITY;
+      } else {
+        double hmin = INFINITY;
+        for (int k = 0; k < 3; ++k) {
+          const double* ib = c->hpbc.inv_box;
+          hmin = std::min(hmin, 1.0 / std::sqrt(ib[k] * ib[k] + ib[3 + k] * ib[3 + k] + ib[6 + k] * ib[6 + k]));
+        }
+        const double lim = 0.5 * (0.5 * hmin * (1.0 - 1e-3) - c->cfg.nl_cutoff);
+        a.img_disp2_max = (lim > 0.0) ? lim * lim : 0.0;
+      }
+    }
     a.scell = c->d_scell.p;
     a.cstart = c->d_cstart.p;
     a.ccount = c->d_ccount.p;
@@ -707,12 +761,27 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.evals = c->d_u64.p + 1;
     a.pbc_g = pbc_g;
     a.sw_g = sw_g;
-    CU(c, c->d_partials.reserve((size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 4)));
+    const size_t npart = (size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 8);
+    CU(c, c->d_partials.reserve(npart));
     a.partials = c->d_partials.p;
     CU(c, cudaEventRecord(c->ev[2], c->st));
     CU(c, cudaEventRecord(c->sweep_ev[2 * (c->sweep_n % b200coord_ctx::kRing)], c->st));
-    nblocks = (c->cfg.nl_mode == B200COORD_NL_CLASSIC) ? launch_sweep_list(a, c->dpbc, c->dsw, c->st)
-                                                        : launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
+    if (classic) {
+      if (a.img_disp2_max > 0.0) {
+        // Two kernels, one of which returns at once (device-side gate on the displacement): the image sweep skips
+        // empty rows and the general kernel only stores partials for GROUPA rows, so rows and partials start at zero.
+        CU(c, cudaMemsetAsync(c->d_partials.p, 0, npart * sizeof(double), c->st));
+        CU(c, cudaMemsetAsync(rows_now + 3 * (size_t)c->row_begin, 0, sizeof(double) * 3 * (size_t)(c->row_end - c->row_begin), c->st));
+        nblocks = launch_sweep_img(a, c->dbox, c->dsw, c->img_variant, c->st);
+        const int nb2 = launch_sweep_list(a, c->dpbc, c->dsw, c->st);
+        if (nb2 < 0) nblocks = nb2;
+        c->stats.kernel_launches += 1 + (c->two_groups ? 2 : 1);
+      } else {
+        nblocks = launch_sweep_list(a, c->dpbc, c->dsw, c->st);
+      }
+    } else {
+      nblocks = launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
+    }
     CU(c, cudaEventRecord(c->ev[3], c->st));
     weight = c->two_groups ? 1.0 : 0.5;
     c->stats.kernel_launches += 1 + (c->two_groups ? 2 : 1);
@@ -735,6 +804,7 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     c->stats.kernel_launches += 1;
   }
   CU(c, cudaMemcpyAsync(c->h_u64 + 1, c->d_u64.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaMemcpyAsync(c->h_u64 + 3, c->d_u64.p + 12, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
   CU_LAST(c, "finalize");
   return B200COORD_OK;
 }
@@ -754,11 +824,15 @@ void maybe_pin(b200coord_ctx* c, int which, const void* p, size_t bytes) {
 }
 
 void refresh_stats(b200coord_ctx* c) {
-  c->stats.pair_evals = c->h_u64[1];
+  // [1] entries of the rows the general / cell kernels swept, [3] entries actually evaluated, [4] entries of the
+  // image-mode list (counted when it was built)
+  const bool img = (c->cfg.nl_mode == B200COORD_NL_CLASSIC && c->img_list && c->cfg.style != B200COORD_STYLE_PAIR);
+  const unsigned long long listed = img ? c->h_u64[4] : c->h_u64[1];
+  c->stats.pair_evals = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : c->h_u64[3];
   const unsigned long long n = c->n;
   switch (c->cfg.nl_mode) {
     case B200COORD_NL_CLASSIC:
-      c->stats.nl_size = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : c->h_u64[1] / 2 + (c->cfg.rank == 0 ? c->n_self_pairs : 0);
+      c->stats.nl_size = (c->cfg.style == B200COORD_STYLE_PAIR) ? c->h_u64[1] : listed / 2 + (c->cfg.rank == 0 ? c->n_self_pairs : 0);
       break;
     case B200COORD_NL_CELLS:
       c->stats.nl_size = c->two_groups ? c->h_u64[1] / 2 : (c->h_u64[1] - (c->row_end - c->row_begin)) / 2;
@@ -956,6 +1030,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
   if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_IMG_VARIANT")) c->img_variant = std::atoi(e);
   *out = c;
   return B200COORD_OK;
 }
@@ -998,7 +1074,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
-  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_srowstart.release(); c->d_srowcount.release(); c->d_snbr.release(); c->d_wpos.release(); c->d_braw.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
+  c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_meta.release(); c->d_srowstart.release(); c->d_srowcount.release(); c->d_snbr.release(); c->d_wpos.release(); c->d_braw.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
   if (c->peer_mode)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
@@ -1246,9 +1322,10 @@ int b200coord_nl_pairs(b200coord_ctx* c, unsigned* pairs, unsigned long long cap
         CU(c, cudaMemcpy(nbr.data(), c->d_nbr.p, (size_t)c->nbr_total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
       std::vector<uint32_t> far(2 * (size_t)n);
       if (n) CU(c, cudaMemcpy(far.data(), c->d_rowfar.p, 2 * (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      const uint32_t mask = c->img_list ? kSuperIndexMask : 0xffffffffu;  // image-mode entries: index | image << 26
       for (unsigned k = 0; k < n; ++k) {
-        for (uint32_t e = 0; e < cnt[k]; ++e) emit(perm[k], perm[nbr[st[k] + e]]);
-        for (uint32_t e = 0; e < far[n + k]; ++e) emit(perm[k], perm[nbr[st[k] + far[k] + e]]);
+        for (uint32_t e = 0; e < cnt[k]; ++e) emit(perm[k], perm[nbr[st[k] + e] & mask]);
+        for (uint32_t e = 0; e < far[n + k]; ++e) emit(perm[k], perm[nbr[st[k] + far[k] + e] & mask]);
       }
       // pairs of one and the same atom are at distance 0 <= cutoff: the reference lists them
       if (c->n_self_pairs) {

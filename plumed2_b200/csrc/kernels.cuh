@@ -98,27 +98,34 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
                     const DevGrid& g, const DevPbc& pbc, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                     unsigned row_end, uint32_t* row_count, const unsigned long long* row_start, uint32_t* nbr,
                     cudaStream_t st);
-// float4 copy of the sorted atoms in wrapped coordinates relative to the box centre (w = absolute index bits);
-// wpos/braw (3 doubles per atom, or null): the wrapped and the raw positions, kept for later filter rebuilds
-void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, double* wpos,
-                       double* braw, cudaStream_t st);
+// image mode (sweep_img.cuh): see k_sort_init / k_gather_u / k_pack_meta in kernels_build.cu
+void launch_sort_init(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, const DevGrid& g,
+                      const DevPbc& box, bool use_wrapped, float4* lpos, double* wpos, double* braw, SPos* spos, double* ubuild,
+                      cudaStream_t st);
+void launch_gather_u(bool build, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+                     const double* wpos, const double* braw, const DevPbc& pbc, SPos* spos, double* ubuild, float4* lpos,
+                     unsigned long long* disp2, cudaStream_t st);
+void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
+                      const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st);
 // ---- super-list: a list with cutoff NL_CUTOFF + delta whose rows are the candidate sets of the following rebuilds
 // (k_nl_filter) while 2 * max displacement since its build stays below delta.  An entry = sorted index | image << 26.
 constexpr uint32_t kSuperIndexMask = 0x03ffffffu;
+// image code = (wx+1) | (wy+1)<<2 | (wz+1)<<4, stored XOR the code of the home cell (21): an entry that needs no
+// shift has zero top bits, so "does any entry of this trip need a shift" is one unsigned compare
+constexpr uint32_t kImageCentre = 21u;
 __host__ __device__ __forceinline__ uint32_t super_image(int wx, int wy, int wz) {
-  return ((uint32_t)(wx + 1) | ((uint32_t)(wy + 1) << 2) | ((uint32_t)(wz + 1) << 4)) << 26;
+  return ((((uint32_t)(wx + 1) | ((uint32_t)(wy + 1) << 2) | ((uint32_t)(wz + 1) << 4))) ^ kImageCentre) << 26;
 }
-// lpos = wpos + minimum-image displacement since the super-list build; *disp2 = max squared displacement (bits)
-void launch_local_rel(const SPos* spos, unsigned n, const double* wpos, const double* braw, const DevPbc& pbc, float4* lpos,
-                      unsigned long long* disp2, cudaStream_t st);
-void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool images /*entries keep their image bits*/,
+                      const double* pos /*caller's positions (exact band test)*/, const uint32_t* perm, const float4* lpos,
                       const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
                       const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
                       unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super /*super-list rows*/, const SPos* spos,
-                        const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super /*super-list rows*/,
+                        bool images /*entries carry the periodic image in their top 6 bits*/, const double* pos,
+                        const uint32_t* perm, const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
                         unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
@@ -130,7 +137,7 @@ void launch_scan_rows(const uint32_t* row_count, unsigned rows, unsigned padq /*
                       cudaStream_t st);
 
 // ---- sweep
-constexpr int kPartialStride = 8;  // value, vxx, vxy, vxz, vyy, vyz, vzz, (pad)
+constexpr int kPartialStride = 12;  // value, then the 3x3 sum c[a][b] (virial = -weight * c), (pad)
 
 struct SweepArgs {
   const SPos* spos;
@@ -146,6 +153,10 @@ struct SweepArgs {
   const unsigned long long* row_start;
   const uint32_t* row_count;
   const uint32_t* nbr;
+  uint32_t idx_mask;       // sorted index of an entry = entry & idx_mask (image-mode lists keep the image above bit 26)
+  const uint4* row_meta;   // image mode: {row start / 4, near count, far offset, far count} per row (k_pack_meta)
+  const double* pos;       // the caller's positions (slot order): exact boundary patch
+  double img_disp2_max;    // image mode is valid while the squared displacement since the rebuild is below this
   // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)
   // when the list was built, [row_start + row_far_off, +row_far_cnt) the rest (filled from the end of the row's
   // allocation).  A trip of the far part whose 32 pairs are all beyond D_MAX contributes exactly zero and stops
@@ -167,7 +178,8 @@ struct SweepArgs {
   // outputs
   double* sderiv;          // 3 doubles per sorted row (only rows of this rank are written)
   double* partials;        // kPartialStride doubles per block
-  unsigned long long* evals;  // pair evaluations executed (both directions)
+  unsigned long long* evals;  // list entries of the rows swept (both directions)
+  unsigned long long* executed;  // entries actually evaluated (far parts that were skipped do not count)
   // box and switch parameters in global memory, for the out-of-line row patch (sweep_math.cuh: row_fixup_*)
   const DevPbc* pbc_g;
   const DevSwitch* sw_g;
@@ -178,6 +190,10 @@ struct SweepArgs {
 
 // returns the number of blocks launched (= number of partial records), or -1 for an unsupported switch
 int launch_sweep_list(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
+// image mode (sweep_img.cuh): continuous coordinates + image in the list entry; box = the lattice vectors the
+// images refer to.  Runs only while the displacement bound holds (device-side gate), k_sweep_list otherwise:
+// launch both, exactly one of them does the step.
+int launch_sweep_img(const SweepArgs& a, const DevPbc& box, const DevSwitch& sw, int variant, cudaStream_t st);
 int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 // PAIR style: one thread per pair (k, k+n_a); writes derivatives straight into out (slot order)
 int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DHENERGY*/,

@@ -289,6 +289,30 @@ __global__ void __launch_bounds__(256)
 }
 
 
+// The reference's neighbour test on the caller's unmodified positions (NeighborList.cpp:246-259): the pair is
+// evaluated as (index0,index1) = (A atom, B atom) resp. (lower, higher slot), distance = pos[index1]-pos[index0],
+// kept iff modulo2(distance) <= cutoff^2, every operation as the reference's non-FMA build does it.
+// k, j: sorted indices; perm: sorted -> slot.
+__device__ __noinline__ bool exact_within(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const DevPbc& pbc,
+                                          uint32_t k, uint32_t j, int two_groups, bool k_in_a, double cutoff2) {
+  const uint32_t sk = perm[k], sj = perm[j];
+  const double* pk = pos + 3 * (size_t)sk;
+  const double* pj = pos + 3 * (size_t)sj;
+  const bool i_first = two_groups ? k_in_a : (sk < sj);
+  double d[3];
+  if (i_first) {
+    d[0] = xsub(pj[0], pk[0]);
+    d[1] = xsub(pj[1], pk[1]);
+    d[2] = xsub(pj[2], pk[2]);
+  } else {
+    d[0] = xsub(pk[0], pj[0]);
+    d[1] = xsub(pk[1], pj[1]);
+    d[2] = xsub(pk[2], pj[2]);
+  }
+  min_image_exact(pbc, d);
+  return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP32 candidate search.  The sorted atoms are copied once per rebuild into float4 records holding the
 // position WRAPPED into the cell the atom was binned to (relative to the box centre; bounding-box mode:
@@ -299,12 +323,20 @@ __global__ void __launch_bounds__(256)
 // cutoff.  FP32 rounding moves r^2 by < band_rel*cutoff^2; candidates inside that band -- a ~1e-5 fraction
 // -- are decided by the reference's exact FP64 operation sequence on the original positions, so the kept
 // SET is the reference's bit for bit.
-__global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid g, DevPbc box, float4* __restrict__ lpos,
-                             double* __restrict__ wpos, double* __restrict__ braw) {
+// After a re-sort (image mode, see sweep_img.cuh): everything the following steps continue from.
+//   braw  = the caller's position of sorted atom k now,
+//   wpos  = that position wrapped into the cell the atom was binned to (same arithmetic as cell_of()),
+//   lpos  = float4 copy of wpos for the FP32 search (w = absolute index bits),
+//   spos  = the record the sweep reads: u = wpos under PBC (the periodic images stored with the list entries refer
+//           to these coordinates), the caller's position otherwise; ubuild = u (displacement bound).
+__global__ void k_sort_init(const double* __restrict__ pos, const uint32_t* __restrict__ perm,
+                            const uint32_t* __restrict__ abs_index, unsigned n, DevGrid g, DevPbc box, int use_wrapped,
+                            float4* __restrict__ lpos, double* __restrict__ wpos, double* __restrict__ braw,
+                            SPos* __restrict__ spos, double* __restrict__ ubuild) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const SPos p = load_spos(spos + k);
-  double q[3] = {p.x, p.y, p.z};
+  const uint32_t slot = perm[k];
+  const double q[3] = {pos[3 * (size_t)slot], pos[3 * (size_t)slot + 1], pos[3 * (size_t)slot + 2]};
   double out[3];
   if (g.bbox) {
 #pragma unroll
@@ -321,34 +353,63 @@ __global__ void k_make_local(const SPos* __restrict__ spos, unsigned n, DevGrid 
 #pragma unroll
     for (int a = 0; a < 3; ++a) out[a] = fw[0] * box.box[a] + fw[1] * box.box[3 + a] + fw[2] * box.box[6 + a];
   }
-  lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(p.abs_index));
-  if (wpos) {  // super-list build: remember the wrapped and the raw position (k_local_rel continues from them)
+  const uint32_t ab = abs_index[slot];
+  lpos[k] = make_float4((float)out[0], (float)out[1], (float)out[2], __uint_as_float(ab));
+  SPos r;
+  r.x = use_wrapped ? out[0] : q[0];
+  r.y = use_wrapped ? out[1] : q[1];
+  r.z = use_wrapped ? out[2] : q[2];
+  r.abs_index = ab;
+  r.slot = slot;
+  spos[k] = r;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      wpos[3 * (size_t)k + a] = out[a];
-      braw[3 * (size_t)k + a] = q[a];
-    }
+  for (int a = 0; a < 3; ++a) {
+    wpos[3 * (size_t)k + a] = out[a];
+    braw[3 * (size_t)k + a] = q[a];
   }
+  ubuild[3 * (size_t)k] = r.x;
+  ubuild[3 * (size_t)k + 1] = r.y;
+  ubuild[3 * (size_t)k + 2] = r.z;
 }
 
-// Local copy for a rebuild that FILTERS the super-list: the atom's wrapped position at the super-list build plus its
-// minimum-image displacement since then, so that the periodic image stored with every super-list entry stays the
-// right one even when the MD engine re-wraps the atom.  Also the largest squared displacement (validity of the
-// super-list: 2 * max displacement < its extra cutoff).
-template <int PBC>
+// Per step in image mode: u = wpos + minimum-image displacement since the sort -- continuous coordinates: the MD
+// engine may re-wrap atoms at will, the periodic image stored with every list entry stays the right one.
+// BUILD (a rebuild that keeps the sort and filters the super-list): also the float4 copy for the FP32 test, the
+// largest squared displacement since the sort (validity of the super-list), and ubuild = u.
+// !BUILD: the largest squared displacement since the list was built (far-part skip, validity of the images).
+template <int PBC, bool BUILD>
 __global__ void __launch_bounds__(256)
-    k_local_rel(const SPos* __restrict__ spos, unsigned n, const double* __restrict__ wpos, const double* __restrict__ braw,
-                DevPbc pbc, float4* __restrict__ lpos, unsigned long long* __restrict__ disp2) {
+    k_gather_u(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ abs_index,
+               unsigned n, const double* __restrict__ wpos, const double* __restrict__ braw, DevPbc pbc,
+               SPos* __restrict__ spos, double* __restrict__ ubuild, float4* __restrict__ lpos,
+               unsigned long long* __restrict__ disp2) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   double d2 = 0.0;
   if (k < n) {
-    const SPos p = load_spos(spos + k);
-    double dx = p.x - braw[3 * (size_t)k], dy = p.y - braw[3 * (size_t)k + 1], dz = p.z - braw[3 * (size_t)k + 2];
+    const uint32_t slot = perm[k];
+    const double qx = pos[3 * (size_t)slot], qy = pos[3 * (size_t)slot + 1], qz = pos[3 * (size_t)slot + 2];
+    double dx = qx - braw[3 * (size_t)k], dy = qy - braw[3 * (size_t)k + 1], dz = qz - braw[3 * (size_t)k + 2];
     min_image_fast<PBC>(pbc, dx, dy, dz);
-    d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    if (!(d2 >= 0.0)) d2 = INFINITY;
-    lpos[k] = make_float4((float)(wpos[3 * (size_t)k] + dx), (float)(wpos[3 * (size_t)k + 1] + dy),
-                          (float)(wpos[3 * (size_t)k + 2] + dz), __uint_as_float(p.abs_index));
+    const double wx = wpos[3 * (size_t)k] + dx, wy = wpos[3 * (size_t)k + 1] + dy, wz = wpos[3 * (size_t)k + 2] + dz;
+    SPos r;
+    r.x = PBC ? wx : qx;
+    r.y = PBC ? wy : qy;
+    r.z = PBC ? wz : qz;
+    const uint32_t ab = abs_index[slot];
+    r.abs_index = ab;
+    r.slot = slot;
+    spos[k] = r;
+    if (BUILD) {
+      lpos[k] = make_float4((float)wx, (float)wy, (float)wz, __uint_as_float(ab));
+      ubuild[3 * (size_t)k] = r.x;
+      ubuild[3 * (size_t)k + 1] = r.y;
+      ubuild[3 * (size_t)k + 2] = r.z;
+      d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    } else {
+      const double ex = r.x - ubuild[3 * (size_t)k], ey = r.y - ubuild[3 * (size_t)k + 1], ez = r.z - ubuild[3 * (size_t)k + 2];
+      d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+    }
+    if (!(d2 >= 0.0)) d2 = INFINITY;  // NaN positions: never skip anything
   }
   __shared__ double sm[8];
 #pragma unroll
@@ -363,6 +424,32 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// one 16-byte record per row for the image sweep: {row start / 4, near count, far offset, far count}; *listed += all
+// entries of these rows (what the reference's list holds, counted from both ends)
+__global__ void __launch_bounds__(256)
+    k_pack_meta(unsigned rows, const unsigned long long* __restrict__ row_start, const uint32_t* __restrict__ row_count,
+                const uint32_t* __restrict__ far_off, const uint32_t* __restrict__ far_cnt, uint4* __restrict__ meta,
+                unsigned long long* __restrict__ listed) {
+  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned mine = 0u;
+  if (r < rows) {
+    const uint4 m = make_uint4((uint32_t)(row_start[r] >> 2), row_count[r], far_off[r], far_cnt[r]);
+    meta[r] = m;
+    mine = m.y + m.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  __shared__ unsigned sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    if (t) atomicAdd(listed, t);
+  }
+}
+
 // FP32 constants of the candidate search
 struct SearchF32 {
   float box[9];        // box rows
@@ -371,9 +458,10 @@ struct SearchF32 {
 
 // SUPER: the rows of the super-list (cutoff + delta, kernels.cuh): entries carry the periodic image they were found
 // through in their top 6 bits, no near/far split.
-template <bool FILL, bool CAPPED, bool SUPER>
+template <bool FILL, bool CAPPED, bool SUPER, bool IMAGES>
 __global__ void __launch_bounds__(256, 4)
-    k_nl_rows_f32(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const uint32_t* __restrict__ scell,
+    k_nl_rows_f32(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
+                  const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
                   SearchF32 f, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                   unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
@@ -435,23 +523,7 @@ __global__ void __launch_bounds__(256, 4)
   const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
 
   // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
-  auto exact_keep = [&](uint32_t j) -> bool {
-    const SPos pi = load_spos(spos + k);
-    const SPos pj = load_spos(spos + j);
-    const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
-    double d[3];
-    if (i_first) {
-      d[0] = xsub(pj.x, pi.x);
-      d[1] = xsub(pj.y, pi.y);
-      d[2] = xsub(pj.z, pi.z);
-    } else {
-      d[0] = xsub(pi.x, pj.x);
-      d[1] = xsub(pi.y, pj.y);
-      d[2] = xsub(pi.z, pj.z);
-    }
-    min_image_exact(pbc, d);
-    return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
-  };
+  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc, k, j, two_groups, my_grp == 0u, cutoff2); };
   auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz, bool& far) -> bool {
     const float dx = lj.x - ox, dy = lj.y - oy, dz = lj.z - oz;
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -475,7 +547,7 @@ __global__ void __launch_bounds__(256, 4)
     const float ox = li.x - ((float)wx * ax + (float)wyy * bx + (float)wzz * cx);
     const float oy = li.y - ((float)wx * ay + (float)wyy * by + (float)wzz * cy);
     const float oz = li.z - ((float)wx * az + (float)wyy * bz + (float)wzz * cz);
-    const uint32_t img = SUPER ? super_image(wx, wyy, wzz) : 0u;
+    const uint32_t img = IMAGES ? super_image(wx, wyy, wzz) : 0u;
     for (uint32_t e0 = 0; e0 < m; e0 += 64) {
       const uint32_t e1 = e0 + lane, e2 = e1 + 32;
       const bool in1 = e1 < m, in2 = e2 < m;
@@ -521,9 +593,10 @@ __global__ void __launch_bounds__(256, 4)
 // the host), seen through the periodic image stored with each entry.  Same FP32 test, same exact FP64 decision
 // inside the rounding band and the same two-ended near/far rows as k_nl_rows_f32 -- ~1/3 of its candidates, no
 // cell tables, no re-sort.
-template <bool FILL, bool CAPPED>
+template <bool FILL, bool CAPPED, bool IMAGES>
 __global__ void __launch_bounds__(256, 3)
-    k_nl_filter(const SPos* __restrict__ spos, const float4* __restrict__ lpos, const unsigned long long* __restrict__ srow_start,
+    k_nl_filter(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
+                const unsigned long long* __restrict__ srow_start,
                 const uint32_t* __restrict__ srow_count, const uint32_t* __restrict__ snbr, DevPbc pbc, SearchF32 f,
                 double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
                 uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr,
@@ -542,31 +615,16 @@ __global__ void __launch_bounds__(256, 3)
   unsigned total = 0, total_far = 0;
   const unsigned long long base = CAPPED ? (unsigned long long)(k - row_begin) * row_cap : (FILL ? row_start[k - row_begin] : 0ull);
   const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
-  auto exact_keep = [&](uint32_t j) -> bool {  // NeighborList.cpp:246-259 on the unmodified positions
-    const SPos pi = load_spos(spos + k);
-    const SPos pj = load_spos(spos + j);
-    const bool i_first = two_groups ? (my_grp == 0u) : (pi.slot < pj.slot);
-    double d[3];
-    if (i_first) {
-      d[0] = xsub(pj.x, pi.x);
-      d[1] = xsub(pj.y, pi.y);
-      d[2] = xsub(pj.z, pi.z);
-    } else {
-      d[0] = xsub(pi.x, pj.x);
-      d[1] = xsub(pi.y, pj.y);
-      d[2] = xsub(pi.z, pj.z);
-    }
-    min_image_exact(pbc, d);
-    return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
-  };
+  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc, k, j, two_groups, my_grp == 0u, cutoff2); };
   // `shifted`: some entry of this trip is seen through a periodic image (warp-uniform; rare away from the box faces)
   auto test = [&](bool in, uint32_t entry, const float4 lj, bool shifted, bool& far) -> bool {
     far = false;
     if (!in) return false;
     float dx = lj.x - li.x, dy = lj.y - li.y, dz = lj.z - li.z;
     if (shifted) {
-      const float wx = (float)((int)((entry >> 26) & 3u) - 1), wy = (float)((int)((entry >> 28) & 3u) - 1),
-                  wz = (float)((int)((entry >> 30) & 3u) - 1);
+      const uint32_t code = (entry >> 26) ^ kImageCentre;
+      const float wx = (float)((int)(code & 3u) - 1), wy = (float)((int)((code >> 2) & 3u) - 1),
+                  wz = (float)((int)((code >> 4) & 3u) - 1);
       dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
       dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
       dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
@@ -590,7 +648,7 @@ __global__ void __launch_bounds__(256, 3)
   // Two 32-candidate batches per trip, software-pipelined: the super-list entries (streamed from HBM) run two trips
   // ahead, the float4 records they point to (L1/L2 gather) one trip ahead of the test.
   const uint32_t* __restrict__ srow = snbr + sbase + lane;
-  const uint32_t centre = super_image(0, 0, 0);
+  const uint32_t centre = 0u;  // xor-encoded images: the home cell is code 0
   auto entry_at = [&](uint32_t e) -> uint32_t { return (e + lane < m) ? __ldg(srow + e) : centre; };
   uint32_t c1 = entry_at(0), c2 = entry_at(32);
   float4 l1 = __ldg(lpos + (c1 & kSuperIndexMask)), l2 = __ldg(lpos + (c2 & kSuperIndexMask));
@@ -609,8 +667,8 @@ __global__ void __launch_bounds__(256, 3)
     bool f1, f2;
     const bool k1 = test(in1, a1, p1, shifted, f1);
     const bool k2 = test(in2, a2, p2, shifted, f2);
-    emit(k1, f1, a1 & kSuperIndexMask);
-    if (e0 + 32 < m) emit(k2, f2, a2 & kSuperIndexMask);
+    emit(k1, f1, IMAGES ? a1 : (a1 & kSuperIndexMask));
+    if (e0 + 32 < m) emit(k2, f2, IMAGES ? a2 : (a2 & kSuperIndexMask));
   }
   const unsigned all = total + total_far;
   if (lane == 0) {
@@ -813,23 +871,42 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 #undef B200_NL_LAUNCH
 }
 
-void launch_make_local(const SPos* spos, unsigned n, const DevGrid& g, const DevPbc& box, float4* lpos, double* wpos,
-                       double* braw, cudaStream_t st) {
-  if (n) k_make_local<<<(n + 255) / 256, 256, 0, st>>>(spos, n, g, box, lpos, wpos, braw);
+void launch_sort_init(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, const DevGrid& g,
+                      const DevPbc& box, bool use_wrapped, float4* lpos, double* wpos, double* braw, SPos* spos, double* ubuild,
+                      cudaStream_t st) {
+  if (n)
+    k_sort_init<<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, g, box, use_wrapped ? 1 : 0, lpos, wpos, braw, spos,
+                                                  ubuild);
 }
-void launch_local_rel(const SPos* spos, unsigned n, const double* wpos, const double* braw, const DevPbc& pbc, float4* lpos,
-                      unsigned long long* disp2, cudaStream_t st) {
+void launch_gather_u(bool build, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+                     const double* wpos, const double* braw, const DevPbc& pbc, SPos* spos, double* ubuild, float4* lpos,
+                     unsigned long long* disp2, cudaStream_t st) {
   if (!n) return;
   const unsigned blocks = (n + 255) / 256;
-  switch (pbc.type) {
-    case 0: k_local_rel<0><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
-    case 1: k_local_rel<1><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
-    default: k_local_rel<2><<<blocks, 256, 0, st>>>(spos, n, wpos, braw, pbc, lpos, disp2); break;
+#define B200_GU(P, B) k_gather_u<P, B><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, wpos, braw, pbc, spos, ubuild, lpos, disp2)
+  if (build) {
+    switch (pbc.type) {
+      case 0: B200_GU(0, true); break;
+      case 1: B200_GU(1, true); break;
+      default: B200_GU(2, true); break;
+    }
+  } else {
+    switch (pbc.type) {
+      case 0: B200_GU(0, false); break;
+      case 1: B200_GU(1, false); break;
+      default: B200_GU(2, false); break;
+    }
   }
+#undef B200_GU
+}
+void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
+                      const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st) {
+  cudaMemsetAsync(listed, 0, sizeof(unsigned long long), st);
+  if (rows) k_pack_meta<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_start, row_count, far_off, far_cnt, meta, listed);
 }
 
-void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super, const SPos* spos,
-                        const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
+void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super, bool images, const double* pos,
+                        const uint32_t* perm, const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
                         const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
                         unsigned long long* row_start, uint32_t* nbr, unsigned row_cap, unsigned* cap_info, float far2,
@@ -841,19 +918,25 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
   for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
   f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
   f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
-#define B200_F32_ARGS spos, lpos, scell, cstart, ccount, g, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+#define B200_F32_ARGS pos, perm, lpos, scell, cstart, ccount, g, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (super) {  // super-list rows: two passes only
-    if (mode == 0) k_nl_rows_f32<false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  } else if (mode == 0) k_nl_rows_f32<false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  else if (mode == 1) k_nl_rows_f32<true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  else k_nl_rows_f32<true, true, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  if (super) {  // super-list rows: two passes only, always with images
+    if (mode == 0) k_nl_rows_f32<false, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  } else if (mode == 0) k_nl_rows_f32<false, false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  else if (images) {
+    if (mode == 1) k_nl_rows_f32<true, false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  } else {
+    if (mode == 1) k_nl_rows_f32<true, false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+  }
 #undef B200_F32_ARGS
 }
 
-void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, const SPos* spos, const float4* lpos,
+void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool images, const double* pos, const uint32_t* perm,
+                      const float4* lpos,
                       const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
                       const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
@@ -865,12 +948,17 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, const 
   for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
   f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
   f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
-#define B200_FLT_ARGS spos, lpos, srow_start, srow_count, snbr, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+#define B200_FLT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (mode == 0) k_nl_filter<false, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
-  else if (mode == 1) k_nl_filter<true, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
-  else k_nl_filter<true, true><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  if (mode == 0) k_nl_filter<false, false, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  else if (images) {
+    if (mode == 1) k_nl_filter<true, false, true><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+    else k_nl_filter<true, true, true><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  } else {
+    if (mode == 1) k_nl_filter<true, false, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+    else k_nl_filter<true, true, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);
+  }
 #undef B200_FLT_ARGS
 }
 

@@ -84,30 +84,23 @@ __global__ void __launch_bounds__(kSweepThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// fixed-order sum of the block partials; virial = -weight * sum(df d(x)d), value = weight * sum(s).
-// 1024 threads = 128 groups x 8 components; group g adds records g, g+128, ... and the 128 group sums are
+// fixed-order sum of the block partials; virial = -weight * sum(c), value = weight * sum(s).
+// 1024 threads = 64 groups x 16 components; group g adds records g, g+64, ... and the 64 group sums are
 // added in index order, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int nblocks, double weight,
                                                    double* __restrict__ tail) {
-  __shared__ double sm[128][kPartialStride];
-  const int comp = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  __shared__ double sm[64][16];
+  const int comp = threadIdx.x & 15, grp = threadIdx.x >> 4;
   double t = 0.0;
-  for (int b = grp; b < nblocks; b += 128) t += partials[(size_t)b * kPartialStride + comp];
+  if (comp < 10)
+    for (int b = grp; b < nblocks; b += 64) t += partials[(size_t)b * kPartialStride + comp];
   sm[grp][comp] = t;
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 10) {
     double r = 0.0;
-    for (int g2 = 0; g2 < 128; ++g2) r += sm[g2][threadIdx.x];
-    sm[0][threadIdx.x] = r * weight;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double val = sm[0][0], xx = -sm[0][1], xy = -sm[0][2], xz = -sm[0][3], yy = -sm[0][4], yz = -sm[0][5],
-                 zz = -sm[0][6];
-    tail[0] = xx; tail[1] = xy; tail[2] = xz;
-    tail[3] = xy; tail[4] = yy; tail[5] = yz;
-    tail[6] = xz; tail[7] = yz; tail[8] = zz;
-    tail[9] = val;
+    for (int g2 = 0; g2 < 64; ++g2) r += sm[g2][threadIdx.x];
+    if (threadIdx.x == 0) tail[9] = r * weight;
+    else tail[threadIdx.x - 1] = -(r * weight);
   }
 }
 

@@ -16,9 +16,11 @@ namespace b200 {
 template <int K, int PBC, bool ACC, typename T>
 __global__ void __launch_bounds__(kSweepThreads, 2)
     k_sweep_list(SweepArgs a, DevPbc pbc, DevSwitchT<T> sw, unsigned rows_per_block, unsigned seg_begin, unsigned seg_end) {
+  // image mode: k_sweep_img does the step while its displacement bound holds (img_disp2_max = 0: it never runs)
+  if (__longlong_as_double((long long)*a.disp2_bits) < a.img_disp2_max) return;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LaneAcc acc = {0, 0, 0, 0, 0, 0, 0};
-  unsigned long long evals = 0;
+  unsigned long long evals = 0, execd = 0;
   const unsigned first = seg_begin + blockIdx.x * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
   unsigned fixmask = 0u;  // rows of this warp with a pair on a D_MAX / D_0 boundary (rows_per_block <= 32 warps' worth)
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       uint32_t ja = FAR ? ((e < cnt) ? __ldg(row + e) : 0u) : j0;
       uint32_t jb = FAR ? ((e + 32 < cnt) ? __ldg(row + e + 32) : 0u) : j1;
       RecBuf pa, pb;
-      load_rec(a.spos + ja, pa);
-      load_rec(a.spos + jb, pb);
+      load_rec(a.spos + (ja & a.idx_mask), pa);
+      load_rec(a.spos + (jb & a.idx_mask), pb);
       uint32_t ia = ja, ib = jb;  // entries of the records in flight (DHENERGY / GHBFIX look charges / types up)
       // list entries run two loop trips ahead of the records (HBM latency), the records one trip ahead of the math
       ja = FAR ? ((e + 64 < cnt) ? __ldg(row + e + 64) : 0u) : j2;
@@ -97,10 +99,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
         T qqa = T(1.0), qqb = T(1.0);
         if (K == K_DH || K == K_GHB) {
           if (K == K_DH) {
-            qqa = qi * (T)__ldg(a.sq + ia);
-            qqb = qi * (T)__ldg(a.sq + ib);
+            qqa = qi * (T)__ldg(a.sq + (ia & a.idx_mask));
+            qqb = qi * (T)__ldg(a.sq + (ib & a.idx_mask));
           } else {  // eta[type of the pair's first atom][type of its second atom], GHBFIX.cpp:189-197
-            const uint32_t ta = __ldg(a.stype + ia), tb = __ldg(a.stype + ib);
+            const uint32_t ta = __ldg(a.stype + (ia & a.idx_mask)), tb = __ldg(a.stype + (ib & a.idx_mask));
             const bool fa = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(ca.w));
             const bool fb = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(cb.w));
             qqa = (T)__ldg(a.etas + (fa ? ta * a.ntypes + ti : ti * a.ntypes + ta));
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
           ia = ja;
           ib = jb;
         }
-        load_rec(a.spos + ja, pa);
-        load_rec(a.spos + jb, pb);
+        load_rec(a.spos + (ja & a.idx_mask), pa);
+        load_rec(a.spos + (jb & a.idx_mask), pb);
         ja = na;
         jb = nb;
         na = (e + 192 < cnt) ? __ldg(row + e + 192) : 0u;
@@ -133,15 +135,17 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       a.sderiv[3 * (size_t)k + 1] = (double)fy;
       a.sderiv[3 * (size_t)k + 2] = (double)fz;
       evals += cnt_near + cnt_far;
+      execd += cnt_near + (far_on ? cnt_far : 0u);
     }
   }
+  if (lane == 0 && execd) atomicAdd(a.executed, execd);
   if constexpr (std::is_same<T, double>::value)
   while (fixmask) {
     const unsigned m = (unsigned)__ffs((int)fixmask) - 1u;
     fixmask &= fixmask - 1u;
     const unsigned kf = first + wid + kSweepWarps * m;
     const uint32_t* __restrict__ row = a.nbr + a.row_start[kf - a.row_begin];
-    const RowFix f = row_fixup_list<K, PBC>(a.pbc_g, a.sw_g, a.spos, row, a.row_count[kf - a.row_begin],
+    const RowFix f = row_fixup_list<K, PBC>(a.pbc_g, a.sw_g, a.spos, a.pos, a.idx_mask, row, a.row_count[kf - a.row_begin],
                                             row + a.row_far_off[kf - a.row_begin], a.row_far_cnt[kf - a.row_begin], kf, lane,
                                             a.two_groups, kf >= a.n_a);
     double gx = 0.0, gy = 0.0, gz = 0.0;
@@ -225,6 +229,7 @@ __global__ void __launch_bounds__(kSweepThreads)
       evals += cnt;
     }
   }
+  if (lane == 0 && evals) atomicAdd(a.executed, evals);
   if (a.npeers) {
     // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
     // them over NVLink with coalesced stores while other blocks keep computing
@@ -244,15 +249,6 @@ __global__ void __launch_bounds__(kSweepThreads)
 
 // ------------------------------------------------------------------------------------------------
 // dispatch
-static unsigned pick_rows_per_block(unsigned rows) {
-  // aim for >= 4 resident blocks on each of the 148 SMs; a warp always owns whole rows
-  unsigned rpb = rows / (148u * 4u);
-  rpb = (rpb / kSweepWarps) * kSweepWarps;
-  if (rpb < (unsigned)kSweepWarps) rpb = kSweepWarps;
-  if (rpb > 128u) rpb = 128u;  // 16 rows per warp: 3 % faster than 64 (fewer block tails), no gain beyond
-  return rpb;
-}
-
 template <int K, int PBC, bool LIST, typename T>
 static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>& sw, cudaStream_t st) {
   // rows that accumulate value+virial: SingleList -> all; TwoList -> only the A rows

@@ -501,7 +501,8 @@ struct RowFix {
 };
 template <int K, int PBC>
 __device__ __forceinline__ void fix_one(const DevPbc& pbc, const DevSwitch& sw, double xi, double yi, double zi,
-                                        double xj, double yj, double zj, bool flip, RowFix& f) {
+                                        double xj, double yj, double zj, const double* __restrict__ ri,
+                                        const double* __restrict__ rj, bool flip, RowFix& f) {
   const unsigned sgn = flip ? 0x80000000u : 0u;
   double dx = flip_sign(xj - xi, sgn), dy = flip_sign(yj - yi, sgn), dz = flip_sign(zj - zi, sgn);
   min_image_fast<PBC>(pbc, dx, dy, dz);
@@ -509,7 +510,8 @@ __device__ __forceinline__ void fix_one(const DevPbc& pbc, const DevSwitch& sw, 
   if (!on_boundary(sw, r2)) return;
   double s, df;
   eval_switch<K>(sw, r2, s, df);
-  const ExactPair o = exact_pair<K>(pbc, sw, xi, yi, zi, xj, yj, zj, flip);
+  // the exact evaluation starts from the caller's own positions (the records may hold continuous coordinates)
+  const ExactPair o = exact_pair<K>(pbc, sw, ri[0], ri[1], ri[2], rj[0], rj[1], rj[2], flip);
   const double dfs = flip_sign(df, sgn), odfs = flip ? -o.df : o.df;
   f.fx += -odfs * o.dx + dfs * dx;
   f.fy += -odfs * o.dy + dfs * dy;
@@ -524,14 +526,16 @@ __device__ __forceinline__ void fix_one(const DevPbc& pbc, const DevSwitch& sw, 
 }
 template <int K, int PBC>
 __device__ __noinline__ RowFix row_fixup_list(const DevPbc* __restrict__ pbc_g, const DevSwitch* __restrict__ sw_g,
-                                              const SPos* __restrict__ spos, const uint32_t* __restrict__ row, unsigned cnt,
+                                              const SPos* __restrict__ spos, const double* __restrict__ pos,
+                                              uint32_t idx_mask, const uint32_t* __restrict__ row, unsigned cnt,
                                               const uint32_t* __restrict__ far_row, unsigned far_cnt, unsigned k,
                                               unsigned lane, int two_groups, bool row_is_b) {
   RowFix f = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const SPos pi = spos[k];
   for (unsigned e = lane; e < cnt + far_cnt; e += 32) {
-    const SPos pj = spos[e < cnt ? row[e] : far_row[e - cnt]];
-    fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, two_groups ? row_is_b : (pi.slot > pj.slot), f);
+    const SPos pj = spos[(e < cnt ? row[e] : far_row[e - cnt]) & idx_mask];
+    fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, pos + 3 * (size_t)pi.slot, pos + 3 * (size_t)pj.slot,
+                    two_groups ? row_is_b : (pi.slot > pj.slot), f);
   }
   return f;
 }
@@ -565,11 +569,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int kSweepThreads = 256;
 constexpr int kSweepWarps = kSweepThreads / 32;
 
+static inline unsigned pick_rows_per_block(unsigned rows) {
+  // aim for >= 4 resident blocks on each of the 148 SMs; a warp always owns whole rows
+  unsigned rpb = rows / (148u * 4u);
+  rpb = (rpb / kSweepWarps) * kSweepWarps;
+  if (rpb < (unsigned)kSweepWarps) rpb = kSweepWarps;
+  if (rpb > 128u) rpb = 128u;  // 16 rows per warp: 3 % faster than 64 (fewer block tails), no gain beyond
+  return rpb;
+}
+
 // block epilogue: reduce the lane accumulators of all warps and store one partial record
+// {value, c[3][3]} with c = sum df d (x) d (symmetric here; the image sweep stores a general 3x3 sum)
 __device__ __forceinline__ void block_store_partials(const LaneAcc& a, unsigned long long evals, double* partials,
                                                      unsigned long long* evals_out) {
   constexpr int kMaxWarps = 32;  // blocks of up to 1024 threads
-  __shared__ double sm[kMaxWarps][kPartialStride];
+  __shared__ double sm[kMaxWarps][8];
   __shared__ unsigned long long sev[kMaxWarps];
   const int nwarps = (int)(blockDim.x >> 5);
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -586,10 +600,13 @@ __device__ __forceinline__ void block_store_partials(const LaneAcc& a, unsigned 
     sev[wid] = evals;
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 10) {
+    // record slot -> symmetric component: value | xx xy xz | xy yy yz | xz yz zz
+    const int map[10] = {0, 1, 2, 3, 2, 4, 5, 3, 5, 6};
+    const int src = map[threadIdx.x];
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < nwarps; ++w) t += sm[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) t += sm[w][src];
     partials[(size_t)blockIdx.x * kPartialStride + threadIdx.x] = t;
   }
   if (threadIdx.x == 32) {

@@ -489,3 +489,68 @@ def test_rt20_switch_regtests_on_gpu():
                     bad.append((name, lab, fi, fr["pos"], float(c.value), float(col[fi, 1 + ci]), float(ed)))
             c.close()
     assert not bad, bad
+
+
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("body", ["GROUPA=1-5000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.6}",
+                                  "GROUPA=1-5000 SWITCH={RATIONAL R_0=0.3 NN=8 MM=16 D_MAX=0.6}",
+                                  "GROUPA=1-800 GROUPB=601-5000 SWITCH={EXP R_0=0.2 D_MAX=0.6}",
+                                  "GROUPA=1-5000 SWITCH={GAUSSIAN R_0=0.25 D_0=0.1 D_MAX=0.6}",
+                                  "GROUPA=1-5000 R_0=0.2"])
+def test_image_sweep_against_oracle_and_general_sweep(body, tri):
+    """The image-mode sweep (continuous coordinates, periodic image stored in the list entry, virial from positions;
+    sweep_img.cuh) against the oracle and against the general sweep (minimum image per pair) on the same steps:
+    rebuild steps, drifting atoms with far parts skipped and visited, atoms re-wrapped by the MD engine."""
+    n = 5000
+    pos0, box = water_box(n, 100.0, seed=61, triclinic=tri)
+    line = "c: COORDINATION %s NLIST NL_CUTOFF=0.8 NL_STRIDE=4" % body
+    runs = []
+    for env in ({}, {"B200COORD_NO_IMG_SWEEP": "1"}):
+        os.environ.update(env)
+        try:
+            c = P.Coordination.from_input(line)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        rng = np.random.default_rng(13)
+        pos, out, list_pos = pos0.copy(), [], None
+        for step in range(9):
+            pos = pos + (0.02 if step in (5, 6) else 0.004) * rng.standard_normal(pos.shape)
+            if step == 3:
+                pos[::6] += box[1]
+                pos[::10] -= box[0] + box[2]
+            if c.prepare(step):
+                list_pos = pos.copy()
+            c.calculate(pos, box)
+            if not env:
+                ref = oracle_from_line(line, pos, box, list_positions=list_pos, nthreads=8, fast_list=True)
+                assert_parity(c, ref, "step %d" % step)
+            st = c.stats()
+            out.append((c.value, c.derivatives.copy(), c.virial.copy(), st["pair_evals"], st["nl_size"]))
+        runs.append(out)
+        c.close()
+    for (v0, d0, w0, e0, s0), (v1, d1, w1, e1, s1) in zip(*runs):
+        assert abs(v0 - v1) <= 1e-12 * abs(v0)
+        assert rel_err(d0, d1) <= 1e-11 and rel_err(w0, w1) <= 1e-11
+        assert s0 == s1 and e0 == e1  # same list, same parts of it visited
+
+
+def test_update_list_then_calculate_uses_the_new_list_and_its_displacement_origin():
+    """calculate(P0) [rebuild], update_list(P1), calculate(P2 close to P0): the list, and the origin of the displacement
+    bound that lets the sweep skip far parts, are those of P1"""
+    n = 4000
+    pos0, box = water_box(n, 100.0, seed=71)
+    rng = np.random.default_rng(17)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.6} NLIST NL_CUTOFF=0.7 NL_STRIDE=50" % n
+    c = P.Coordination.from_input(line)
+    c.prepare(0)
+    c.calculate(pos0, box)
+    pos1 = pos0 + 0.05 * rng.standard_normal(pos0.shape)
+    c.update_list(pos1, box)
+    pos2 = pos0 + 0.001 * rng.standard_normal(pos0.shape)
+    assert not c.prepare(1)
+    c.calculate(pos2, box)
+    ref = oracle_from_line(line, pos2, box, list_positions=pos1, nthreads=8, fast_list=True)
+    assert_parity(c, ref, "after update_list")
+    np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
+    c.close()
