@@ -184,6 +184,8 @@ int b200coord_stream_elapsed_ms(b200coord_ctx* ctx, float* ms);   /* waits for t
 int b200coord_calculate_distributed(b200coord_ctx* ctx, const double* pos_slice, double* value, double* deriv_slice,
                                     double* virial);
 int b200coord_my_slice(const b200coord_ctx* ctx, unsigned* slot_begin, unsigned* slot_count);
+/* number of CUDA devices visible to this process (cudaGetDeviceCount) */
+int b200coord_device_count(int* n);
 /* FP64 FMA peak of the device measured with a register-resident DFMA kernel (roofline denominator) */
 int b200coord_measure_fp64_peak(int device, double* tflops);
 

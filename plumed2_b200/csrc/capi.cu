@@ -129,6 +129,7 @@ struct b200coord_ctx {
   bool f32_search = false;
   double band_rel = 0.0;
   unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
+  unsigned max_row = 0;        // longest row (near + far entries) of the current list
   DevBuf<double> d_q, d_sq;    // charges in slot order / sorted order (DHENERGY)
   bool have_charges = false, sq_valid = false;
   DevBuf<uint32_t> d_types, d_stype;  // interaction types in slot order / sorted order (GHBFIX)
@@ -373,8 +374,23 @@ unsigned next_row_cap(unsigned max_row, unsigned current) {
   return want;
 }
 
+// [DevPbc | DevSwitch] in global memory for the out-of-line exact paths (row patches, band decisions of the builders)
+int ensure_params(b200coord_ctx* c) {
+  if (!c->params_dirty) return B200COORD_OK;
+  CU(c, c->d_params.reserve(sizeof(DevPbc) + sizeof(DevSwitch)));
+  CU(c, cudaMemcpyAsync(c->d_params.p, &c->dpbc, sizeof(DevPbc), cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync(c->d_params.p + sizeof(DevPbc), &c->dsw, sizeof(DevSwitch), cudaMemcpyHostToDevice, c->st));
+  c->params_dirty = false;
+  return B200COORD_OK;
+}
+
 int rebuild(b200coord_ctx* c, const double* d_pos) {
   const int mode = c->cfg.nl_mode;
+  {
+    const int rcp = ensure_params(c);
+    if (rcp) return rcp;
+  }
+  const DevPbc* pbc_g = reinterpret_cast<const DevPbc*>(c->d_params.p);
   if (c->cfg.style == B200COORD_STYLE_PAIR) {
     if (mode == B200COORD_NL_CLASSIC) {
       CU(c, c->d_active.reserve(c->n_a));
@@ -460,10 +476,11 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       if (rc2) return rc2;
     }
     if (cappable) c->row_cap = next_row_cap(c->h_capinfo[0], c->row_cap);
+    c->max_row = c->h_capinfo[0];
     return B200COORD_OK;
   };
   auto filter_launch = [&](int m) {
-    launch_nl_filter(m, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, c->dpbc, c->dbox, cut2,
+    launch_nl_filter(m, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, pbc_g, c->dbox, cut2,
                      c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p,
                      m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2, c->d_rowfar.p,
                      c->d_rowfar.p + rows, c->st);
@@ -535,7 +552,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       CU(c, c->d_srowstart.reserve(rows + 1));
       CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
       auto super_pass = [&](int m) {
-        launch_nl_rows_f32(m, true, true, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+        launch_nl_rows_f32(m, true, true, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, pbc_g,
                            c->dbox, sc2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_srowcount.p,
                            c->d_srowstart.p, m ? c->d_snbr.p : nullptr, 0u, c->d_capinfo.p, INFINITY, nullptr, nullptr, c->st);
       };
@@ -554,7 +571,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       if (rcf) return rcf;
     } else if (c->f32_search) {
       int rcf = build_rows([&](int m) {
-        launch_nl_rows_f32(m, false, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, c->dpbc,
+        launch_nl_rows_f32(m, false, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, pbc_g,
                            c->dbox, cut2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p,
                            c->d_rowstart.p, m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2,
                            c->d_rowfar.p, c->d_rowfar.p + rows, c->st);
@@ -637,11 +654,9 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     if (rc) return rc;
     c->invalidate = false;
   }
-  if (c->params_dirty) {
-    CU(c, c->d_params.reserve(sizeof(DevPbc) + sizeof(DevSwitch)));
-    CU(c, cudaMemcpyAsync(c->d_params.p, &c->dpbc, sizeof(DevPbc), cudaMemcpyHostToDevice, c->st));
-    CU(c, cudaMemcpyAsync(c->d_params.p + sizeof(DevPbc), &c->dsw, sizeof(DevSwitch), cudaMemcpyHostToDevice, c->st));
-    c->params_dirty = false;
+  {
+    const int rcp = ensure_params(c);
+    if (rcp) return rcp;
   }
   const DevPbc* pbc_g = reinterpret_cast<const DevPbc*>(c->d_params.p);
   const DevSwitch* sw_g = reinterpret_cast<const DevSwitch*>(c->d_params.p + sizeof(DevPbc));
@@ -744,6 +759,12 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
         const double lim = 0.5 * (0.5 * hmin * (1.0 - 1e-3) - c->cfg.nl_cutoff);
         a.img_disp2_max = (lim > 0.0) ? lim * lim : 0.0;
       }
+      // one block shape for both kernels (they fill the same partial records)
+      const unsigned acc_end = c->two_groups ? std::min(c->row_end, c->n_a) : c->row_end;
+      const unsigned rows_a = acc_end > c->row_begin ? acc_end - c->row_begin : 0u;
+      const unsigned rows_b = c->row_end - std::max(c->row_begin, acc_end);
+      a.rows_per_block = sweep_img_rows_per_block(rows_a, rows_b, c->max_row);
+      if (a.rows_per_block == 0u) a.img_disp2_max = 0.0;  // rows too long for the image sweep's trip table
     }
     a.scell = c->d_scell.p;
     a.cstart = c->d_cstart.p;
@@ -1244,6 +1265,17 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
   *value = c->h_small[9];
   refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_device_count(int* n) {
+  if (!n) return B200COORD_ERR_INVALID;
+  *n = 0;
+  if (cudaGetDeviceCount(n) != cudaSuccess) {
+    cudaGetLastError();
+    *n = 0;
+    return fail(nullptr, B200COORD_ERR_CUDA, "cudaGetDeviceCount failed");
+  }
   return B200COORD_OK;
 }
 

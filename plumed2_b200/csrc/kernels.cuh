@@ -118,15 +118,15 @@ __host__ __device__ __forceinline__ uint32_t super_image(int wx, int wy, int wz)
 }
 void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool images /*entries keep their image bits*/,
                       const double* pos /*caller's positions (exact band test)*/, const uint32_t* perm, const float4* lpos,
-                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
-                      const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
+                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr,
+                      const DevPbc* pbc_g /*box parameters in global memory*/, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
                       unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
 void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super /*super-list rows*/,
                         bool images /*entries carry the periodic image in their top 6 bits*/, const double* pos,
                         const uint32_t* perm, const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
-                        const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
+                        const DevGrid& g, const DevPbc* pbc_g /*global memory*/, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
                         unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
                         unsigned* cap_info /*[0] max row, [1] overflow*/, float far2 /*near/far split, r^2*/,
@@ -157,6 +157,7 @@ struct SweepArgs {
   const uint4* row_meta;   // image mode: {row start / 4, near count, far offset, far count} per row (k_pack_meta)
   const double* pos;       // the caller's positions (slot order): exact boundary patch
   double img_disp2_max;    // image mode is valid while the squared displacement since the rebuild is below this
+  unsigned rows_per_block; // image mode: both kernels use this block shape (0: the kernel picks)
   // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)
   // when the list was built, [row_start + row_far_off, +row_far_cnt) the rest (filled from the end of the row's
   // allocation).  A trip of the far part whose 32 pairs are all beyond D_MAX contributes exactly zero and stops
@@ -194,6 +195,8 @@ int launch_sweep_list(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw
 // images refer to.  Runs only while the displacement bound holds (device-side gate), k_sweep_list otherwise:
 // launch both, exactly one of them does the step.
 int launch_sweep_img(const SweepArgs& a, const DevPbc& box, const DevSwitch& sw, int variant, cudaStream_t st);
+// block shape for both kernels of an image-mode step (0: rows too long for the image sweep)
+unsigned sweep_img_rows_per_block(unsigned rows_a, unsigned rows_b, unsigned max_row);
 int launch_sweep_cells(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, cudaStream_t st);
 // PAIR style: one thread per pair (k, k+n_a); writes derivatives straight into out (slot order)
 int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DHENERGY*/,

@@ -293,8 +293,11 @@ __global__ void __launch_bounds__(256)
 // evaluated as (index0,index1) = (A atom, B atom) resp. (lower, higher slot), distance = pos[index1]-pos[index0],
 // kept iff modulo2(distance) <= cutoff^2, every operation as the reference's non-FMA build does it.
 // k, j: sorted indices; perm: sorted -> slot.
-__device__ __noinline__ bool exact_within(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const DevPbc& pbc,
-                                          uint32_t k, uint32_t j, int two_groups, bool k_in_a, double cutoff2) {
+// pbc_g lives in GLOBAL memory: a reference to the 1.4 KB kernel parameter would make every thread of the caller
+// copy it to its stack.
+__device__ __noinline__ bool exact_within(const double* __restrict__ pos, const uint32_t* __restrict__ perm,
+                                          const DevPbc* __restrict__ pbc_g, uint32_t k, uint32_t j, int two_groups,
+                                          bool k_in_a, double cutoff2) {
   const uint32_t sk = perm[k], sj = perm[j];
   const double* pk = pos + 3 * (size_t)sk;
   const double* pj = pos + 3 * (size_t)sj;
@@ -309,7 +312,7 @@ __device__ __noinline__ bool exact_within(const double* __restrict__ pos, const 
     d[1] = xsub(pk[1], pj[1]);
     d[2] = xsub(pk[2], pj[2]);
   }
-  min_image_exact(pbc, d);
+  min_image_exact(*pbc_g, d);
   return norm2_exact(d[0], d[1], d[2]) <= cutoff2;
 }
 
@@ -462,8 +465,8 @@ template <bool FILL, bool CAPPED, bool SUPER, bool IMAGES>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
                   const uint32_t* __restrict__ scell,
-                  const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g, DevPbc pbc,
-                  SearchF32 f, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
+                  const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g,
+                  const DevPbc* __restrict__ pbc_g, SearchF32 f, double cutoff2, unsigned n_a, int two_groups, unsigned row_begin,
                   unsigned row_end, uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start,
                   uint32_t* __restrict__ nbr, unsigned row_cap, unsigned* __restrict__ cap_info /*[0] max count, [1] overflow*/,
                   float far2, uint32_t* __restrict__ row_far_off, uint32_t* __restrict__ row_far_cnt) {
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(256, 4)
   const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
 
   // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
-  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc, k, j, two_groups, my_grp == 0u, cutoff2); };
+  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc_g, k, j, two_groups, my_grp == 0u, cutoff2); };
   auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz, bool& far) -> bool {
     const float dx = lj.x - ox, dy = lj.y - oy, dz = lj.z - oz;
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -597,7 +600,8 @@ template <bool FILL, bool CAPPED, bool IMAGES>
 __global__ void __launch_bounds__(256, 3)
     k_nl_filter(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
                 const unsigned long long* __restrict__ srow_start,
-                const uint32_t* __restrict__ srow_count, const uint32_t* __restrict__ snbr, DevPbc pbc, SearchF32 f,
+                const uint32_t* __restrict__ srow_count, const uint32_t* __restrict__ snbr, const DevPbc* __restrict__ pbc_g,
+                SearchF32 f,
                 double cutoff2, unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end,
                 uint32_t* __restrict__ row_count, const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr,
                 unsigned row_cap, unsigned* __restrict__ cap_info, float far2, uint32_t* __restrict__ row_far_off,
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(256, 3)
   unsigned total = 0, total_far = 0;
   const unsigned long long base = CAPPED ? (unsigned long long)(k - row_begin) * row_cap : (FILL ? row_start[k - row_begin] : 0ull);
   const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
-  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc, k, j, two_groups, my_grp == 0u, cutoff2); };
+  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc_g, k, j, two_groups, my_grp == 0u, cutoff2); };
   // `shifted`: some entry of this trip is seen through a periodic image (warp-uniform; rare away from the box faces)
   auto test = [&](bool in, uint32_t entry, const float4 lj, bool shifted, bool& far) -> bool {
     far = false;
@@ -907,7 +911,7 @@ void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const 
 
 void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super, bool images, const double* pos,
                         const uint32_t* perm, const float4* lpos, const uint32_t* scell, const uint32_t* cstart, const uint32_t* ccount,
-                        const DevGrid& g, const DevPbc& pbc, const DevPbc& box, double cutoff2, double band_rel,
+                        const DevGrid& g, const DevPbc* pbc_g, const DevPbc& box, double cutoff2, double band_rel,
                         unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* row_count,
                         unsigned long long* row_start, uint32_t* nbr, unsigned row_cap, unsigned* cap_info, float far2,
                         uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st) {
@@ -918,7 +922,7 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
   for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
   f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
   f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
-#define B200_F32_ARGS pos, perm, lpos, scell, cstart, ccount, g, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+#define B200_F32_ARGS pos, perm, lpos, scell, cstart, ccount, g, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
   if (super) {  // super-list rows: two passes only, always with images
@@ -937,7 +941,7 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
 
 void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool images, const double* pos, const uint32_t* perm,
                       const float4* lpos,
-                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc& pbc,
+                      const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc* pbc_g,
                       const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
                       unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st) {
@@ -948,7 +952,7 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
   for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
   f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
   f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
-#define B200_FLT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+#define B200_FLT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
   if (mode == 0) k_nl_filter<false, false, false><<<blocks, 256, 0, st>>>(B200_FLT_ARGS);

@@ -1,5 +1,7 @@
 // FP64 instances of the image-mode list sweep (sweep_img.cuh), one translation unit of its own so that it
 // compiles in parallel with the general sweeps.
+#include <algorithm>
+
 #include "sweep_img.cuh"
 
 namespace b200 {
@@ -47,6 +49,13 @@ static NearBands make_bands(const DevSwitch& sw) {
   band(0, sw.dmax_2, sw.band_dmax);
   band(1, sw.d0_2, sw.band_d0);
   return nb;
+}
+
+unsigned sweep_img_rows_per_block(unsigned rows_a, unsigned rows_b, unsigned max_row) {
+  // one shape for the GROUPA and the GROUPB launch: the smaller of the two picks
+  unsigned rpb = img_rows_per_block(rows_a ? rows_a : rows_b, max_row);
+  if (rows_a && rows_b) rpb = std::min(rpb, img_rows_per_block(rows_b, max_row));
+  return rpb;
 }
 
 int launch_sweep_img(const SweepArgs& a, const DevPbc& box, const DevSwitch& sw, int variant, cudaStream_t st) {

@@ -151,10 +151,11 @@ CoordinationB200::CoordinationB200(const ActionOptions& ao) : Action(ao), Coordi
     parse("MM", mm);
     parse("D_MAX", dmax);
     if (dmax > 0.0) {
-      const std::string def = "RATIONAL R_0=" + std::to_string(r0) + " D_0=" + std::to_string(d0) + " NN=" + std::to_string(nn) +
-                              " MM=" + std::to_string(mm) + " D_MAX=" + std::to_string(dmax);
+      // 17 significant digits: the text round-trips to the same doubles (std::to_string keeps 6 decimals)
+      char def[512];
+      std::snprintf(def, sizeof(def), "RATIONAL R_0=%.17g D_0=%.17g NN=%d MM=%d D_MAX=%.17g", r0, d0, nn, mm, dmax);
       char err[1024];
-      if (b200coord_switch_parse(def.c_str(), &sw, err, sizeof(err)) != B200COORD_OK) {
+      if (b200coord_switch_parse(def, &sw, err, sizeof(err)) != B200COORD_OK) {
         error("problem building the switching function : " + std::string(err));
       }
     } else {
@@ -287,9 +288,29 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
     error("when using PAIR option, the two groups should have the same number of elements");
   }
 
+  // device: GPU_DEVICE keyword > B200COORD_DEVICE > (several MPI ranks: the launcher's local rank modulo the number
+  // of visible devices, so that ranks of one node do not pile up on device 0) > the calling thread's current device
   int device = -1;
+  bool deviceFromRank = false;
   if (const char* env = std::getenv("B200COORD_DEVICE")) {
     device = std::atoi(env);
+  } else if (comm.Get_size() > 1) {
+    const char* names[] = {"OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID", "LOCAL_RANK"};
+    int local = -1;
+    for (const char* nm : names) {
+      if (const char* env = std::getenv(nm)) {
+        local = std::atoi(env);
+        break;
+      }
+    }
+    if (local < 0) {
+      local = comm.Get_rank();
+    }
+    int ndev = 0;
+    if (b200coord_device_count(&ndev) == B200COORD_OK && ndev > 0) {
+      device = local % ndev;
+      deviceFromRank = true;
+    }
   }
   parse("GPU_DEVICE", device);
   bool fp32 = false;
@@ -343,6 +364,15 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   char desc[512];
   b200coord_switch_describe(&sw, desc, sizeof(desc));
   log.printf("  B200-native %s (libb200coord, sm_100a kernels)\n", what);
+  if (device >= 0) {
+    log.printf("  on CUDA device %d%s\n", device, deviceFromRank ? " (local MPI rank modulo visible devices)" : "");
+  } else {
+    log.printf("  on the current CUDA device\n");
+  }
+  if (combineWithMpi) {
+    log.printf("  %d MPI ranks: each computes its share of the i-atoms on its own device, partial results are summed with Comm::Sum on the host\n",
+               comm.Get_size());
+  }
   if (fp32) {
     log.printf("  FP32 pair arithmetic (opt-in): results within 1e-5 of the FP64 path\n");
   }

@@ -144,6 +144,8 @@ __device__ __noinline__ RowFixImg row_fixup_img(const DevPbc* __restrict__ pbc_g
 // and the per-thread sums of g (x) S (only trips with a shifted entry touch them) and of the patch values.
 // The position part of the virial needs one register pair: lane q < 9 accumulates component q of deriv (x) u.
 constexpr int kImgMaxRows = 128;  // rows per block (pick_rows_per_block never exceeds it)
+constexpr int kImgTripCap = 208;  // trips per warp the table holds: 16 rows x 13 trips (img_rows_per_block adapts)
+constexpr unsigned kImgMaxRow = 65535u;  // longest row the 16-bit count of a trip descriptor can describe
 
 template <int K, bool ACC, int MINB>
 __global__ void __launch_bounds__(kSweepThreads, MINB)
@@ -178,65 +180,45 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
   unsigned nin = 0u;   // pairs inside D_MAX (Unstretched kinds)
   unsigned executed = 0u, fixmask = 0u;
 
-  // ---- trip iterator (warp-uniform): local rows wid, wid+8, ...; per row the near part, then the far part if visited
-  constexpr unsigned kOk = 0x80000000u, kFar = 0x40000000u, kRem = 0x3fffffffu;
-  unsigned it_r = wid;                 // local row
-  unsigned it_rem = 0u;                // entries left in the current part | flags
-  unsigned it_off = 0u;                // first entry of the iterator's trip, relative to the block's first row
+  // ---- trip table.  A warp owns the local rows wid, wid+8, ... (at most 16); per row the near part and, when visited,
+  // the far part, each cut into trips of 64 entries.  The table is built once per block (lane l lists the trips of the
+  // warp's l-th row), so the hot loop's "iterator" is one 8-byte shared-memory load: no branches, no state.
+  //   .x = first entry of the trip relative to the block's first row, .y = entries left in the part | row slot << 16 | flags
+  constexpr unsigned kOk = 0x80000000u, kFar = 0x40000000u, kRem = 0xffffu;
+  __shared__ uint2 s_trip[kSweepWarps][kImgTripCap + 2];
   const uint32_t base4 = nrows ? s_meta[0].x : 0u;
   const uint32_t* __restrict__ blk = a.nbr + 4ull * base4 + lane;  // rows of a block are stored in order
-  auto open_row = [&]() {  // first non-empty part at or after local row it_r
-    for (;;) {
-      if (it_r >= nrows) {
-        it_rem = 0u;
-        return;
-      }
-      const uint4 m = s_meta[it_r];
-      if (m.y) {
-        it_rem = m.y | kOk;
-        it_off = 4u * (m.x - base4);
-        executed += m.y;
-        return;
-      }
-      if (far_on && m.w) {
-        it_rem = m.w | kOk | kFar;
-        it_off = 4u * (m.x - base4) + m.z;
-        executed += m.w;
-        return;
-      }
-      it_r += kSweepWarps;
+  {
+    const unsigned rl = wid + kSweepWarps * lane;  // this lane's row of the warp (lanes >= 16 never have one)
+    uint4 m = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 16u && rl < nrows) m = s_meta[rl];
+    const unsigned tn = (m.y + 63u) >> 6, tf = far_on ? ((m.w + 63u) >> 6) : 0u;
+    uint32_t total;
+    unsigned at = warp_exclusive_scan(tn + tf, lane, total);
+    const uint32_t off0 = 4u * (m.x - base4);
+    for (unsigned t = 0; t < tn; ++t) s_trip[wid][at++] = make_uint2(off0 + 64u * t, (m.y - 64u * t) | (lane << 16) | kOk);
+    for (unsigned t = 0; t < tf; ++t)
+      s_trip[wid][at++] = make_uint2(off0 + m.z + 64u * t, (m.w - 64u * t) | (lane << 16) | kOk | kFar);
+    if (lane == 0) {
+      s_trip[wid][total] = make_uint2(0u, 0u);
+      s_trip[wid][total + 1] = make_uint2(0u, 0u);
     }
-  };
-  auto advance_slow = [&]() {
-    if (!(it_rem & kOk)) return;  // past the last row
-    if (!(it_rem & kFar) && far_on) {
-      const uint4 m = s_meta[it_r];
-      if (m.w) {
-        it_rem = m.w | kOk | kFar;
-        it_off = 4u * (m.x - base4) + m.z;
-        executed += m.w;
-        return;
-      }
-    }
-    it_r += kSweepWarps;
-    open_row();
-  };
-  auto advance = [&]() {
-    if ((it_rem & kRem) > 64u) {
-      it_rem -= 64u;
-      it_off += 64u;
-    } else {
-      advance_slow();
-    }
-  };
-  // entries of the iterator's trip (0 = sorted atom 0 through the home image: a valid record, masked out later)
-  auto entry = [&](unsigned off) -> uint32_t { return (off + lane < (it_rem & kRem)) ? __ldg(blk + it_off + off) : 0u; };
+    unsigned mine = m.y + (far_on ? m.w : 0u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    executed = mine;
+    __syncwarp();
+  }
+  unsigned it = 0u;  // next trip of the table
+  uint2 it_d = s_trip[wid][0];
+  // entries of the table's next trip (0 = sorted atom 0 through the home image: a valid record, masked out later)
+  auto entry = [&](unsigned off) -> uint32_t { return (off + lane < (it_d.y & kRem)) ? __ldg(blk + it_d.x + off) : 0u; };
 
   // Two register sets, A and B, alternate: while the trip of one set is evaluated, the records of the other set's
   // trip are in flight and the first set's entry registers are refilled with the trip after that.  No copies.
   struct Set {
     uint32_t ea, eb;   // entries (lane, lane + 32) of the set's trip
-    unsigned r, m;     // its local row; entries left in its part | flags
+    unsigned m;        // entries left in its part | row slot << 16 | flags
     RecBuf pa, pb;     // partner records
     double qa, qb;     // DHENERGY: their charges
     uint32_t ta, tb;   // GHBFIX: their types
@@ -253,17 +235,15 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       s.tb = __ldg(a.stype + (s.eb & kSuperIndexMask));
     }
   };
-  auto refill = [&](Set& s) {  // descriptor and entries of the iterator's trip; the iterator moves on
-    s.r = it_r;
-    s.m = it_rem;
+  auto refill = [&](Set& s) {  // descriptor and entries of the table's next trip
+    s.m = it_d.y;
     s.ea = entry(0u);
     s.eb = entry(32u);
-    advance();
+    it_d = s_trip[wid][++it];
   };
   Set A, B;
   A.qa = A.qb = B.qa = B.qb = 1.0;
   A.ta = A.tb = B.ta = B.tb = 0u;
-  open_row();
   refill(A);
   refill(B);
   request(A);
@@ -302,9 +282,8 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
   // one trip: `cur` holds its entries, descriptor and (arrived) records, `nxt` the entries of the next trip
   auto step = [&](Set& cur, Set& nxt) {
     const uint32_t ia = cur.ea, ib = cur.eb;
-    const unsigned r = cur.r, m = cur.m;
-    refill(cur);   // entries of the trip after next (HBM stream, two trips ahead)
-    request(nxt);  // records of the next trip (L1/L2 gather, one trip ahead)
+    const unsigned m = cur.m;
+    const unsigned r = wid + kSweepWarps * ((m >> 16) & 15u);
     if (r != cur_r) {  // a new row starts with this trip
       if (cur_r != 0xffffffffu) row_done();
       cur_r = r;
@@ -319,8 +298,17 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       if (K == K_DH) qi = __ldg(a.sq + first + r);
       if (K == K_GHB) ti = __ldg(a.stype + first + r);
     }
+    // Order matters: a warp has six scoreboards for its loads in flight, so a wait for an old load also waits for
+    // any younger load that shares its scoreboard.  Everything this trip has to WAIT for -- its records, then the
+    // entries of the next trip -- is therefore consumed before this trip ISSUES anything new.
     double ax = cur.pa.x - xi, ay = cur.pa.y - yi, az = cur.pa.z - zi;
     double bx = cur.pb.x - xi, by = cur.pb.y - yi, bz = cur.pb.z - zi;
+    const unsigned long long wa = (unsigned long long)__double_as_longlong(cur.pa.w);
+    const unsigned long long wb = (unsigned long long)__double_as_longlong(cur.pb.w);
+    const double qa = cur.qa, qb = cur.qb;
+    const uint32_t ta = cur.ta, tb = cur.tb;
+    request(nxt);  // records of the next trip (L1/L2 gather, one trip ahead)
+    refill(cur);   // entries of the trip after next (HBM stream, two trips ahead)
     const unsigned rem = m & kRem;
     const bool va = lane < rem, vb = lane + 32u < rem;
     // everything after the vector: same for both flavours of the trip
@@ -335,15 +323,15 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       img_eval<K>(sw, ra, va, sa, dfa, nin);
       img_eval<K>(sw, rb, vb, sb, dfb, nin);
       if (K == K_DH) {
-        const double qqa = qi * cur.qa, qqb = qi * cur.qb;
+        const double qqa = qi * qa, qqb = qi * qb;
         sa *= qqa; dfa *= qqa;
         sb *= qqb; dfb *= qqb;
       }
       if (K == K_GHB) {  // eta[type of the pair's first atom][type of its second atom], GHBFIX.cpp:189-197
-        const bool fa = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(cur.pa.w));
-        const bool fb = a.two_groups ? row_is_b : (wi > (unsigned long long)__double_as_longlong(cur.pb.w));
-        const double qqa = __ldg(a.etas + (fa ? cur.ta * a.ntypes + ti : ti * a.ntypes + cur.ta));
-        const double qqb = __ldg(a.etas + (fb ? cur.tb * a.ntypes + ti : ti * a.ntypes + cur.tb));
+        const bool fa = a.two_groups ? row_is_b : (wi > wa);
+        const bool fb = a.two_groups ? row_is_b : (wi > wb);
+        const double qqa = __ldg(a.etas + (fa ? ta * a.ntypes + ti : ti * a.ntypes + ta));
+        const double qqb = __ldg(a.etas + (fb ? tb * a.ntypes + ti : ti * a.ntypes + tb));
         sa *= qqa; dfa *= qqa;
         sb *= qqb; dfb *= qqb;
       }
@@ -457,20 +445,33 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
 // ------------------------------------------------------------------------------------------------
 // dispatch.  Same grid shape as run_sweep (sweep_kernels.cuh): whichever of the two kernels takes the step fills
 // the same partial records.
+// rows per block for the image sweep: pick_rows_per_block, reduced until the trips of a warp's rows fit its table
+// (a row of r entries in two parts is at most ceil(r / 64) + 1 trips).  0: rows too long for this kernel.
+static inline unsigned img_rows_per_block(unsigned rows, unsigned max_row) {
+  if (max_row > kImgMaxRow) return 0u;
+  const unsigned trips_per_row = (max_row + 63u) / 64u + 1u;
+  unsigned per_warp = (unsigned)kImgTripCap / trips_per_row;
+  if (per_warp == 0u) return 0u;
+  if (per_warp > 16u) per_warp = 16u;
+  unsigned rpb = pick_rows_per_block(rows);
+  if (rpb > per_warp * kSweepWarps) rpb = per_warp * kSweepWarps;
+  return rpb;
+}
+
 template <int K, int MINB>
 static int run_sweep_img(const SweepArgs& a, const DevSwitch& sw, const ImgShifts& sh, const NearBands& nb, cudaStream_t st) {
   const unsigned acc_end = a.two_groups ? min(a.row_end, a.n_a) : a.row_end;
   int nblocks = 0;
   if (a.row_begin < acc_end) {
     const unsigned rows = acc_end - a.row_begin;
-    const unsigned rpb = pick_rows_per_block(rows);
+    const unsigned rpb = a.rows_per_block;
     nblocks = (int)((rows + rpb - 1) / rpb);
     k_sweep_img<K, true, MINB><<<nblocks, kSweepThreads, 0, st>>>(a, sw, sh, nb, rpb, a.row_begin, acc_end);
   }
   const unsigned b_begin = max(a.row_begin, acc_end);
   if (b_begin < a.row_end) {
     const unsigned rows = a.row_end - b_begin;
-    const unsigned rpb = pick_rows_per_block(rows);
+    const unsigned rpb = a.rows_per_block;
     const int nb2 = (int)((rows + rpb - 1) / rpb);
     SweepArgs b = a;
     b.partials = a.partials + (size_t)nblocks * kPartialStride;  // B rows: position part of the virial only

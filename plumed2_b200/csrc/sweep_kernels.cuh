@@ -256,7 +256,7 @@ static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>&
   int nblocks = 0;
   if (a.row_begin < acc_end) {
     const unsigned rows = acc_end - a.row_begin;
-    const unsigned rpb = pick_rows_per_block(rows);
+    const unsigned rpb = a.rows_per_block ? a.rows_per_block : pick_rows_per_block(rows);
     nblocks = (int)((rows + rpb - 1) / rpb);
     if (LIST)
       k_sweep_list<K, PBC, true, T><<<nblocks, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, a.row_begin, acc_end);
@@ -266,7 +266,7 @@ static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>&
   const unsigned b_begin = max(a.row_begin, acc_end);
   if (b_begin < a.row_end) {
     const unsigned rows = a.row_end - b_begin;
-    const unsigned rpb = pick_rows_per_block(rows);
+    const unsigned rpb = a.rows_per_block ? a.rows_per_block : pick_rows_per_block(rows);
     const int nb = (int)((rows + rpb - 1) / rpb);
     if (LIST)
       k_sweep_list<K, PBC, false, T><<<nb, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, b_begin, a.row_end);
