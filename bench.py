@@ -7,24 +7,37 @@
 Workload (BASELINE.json configs[1] at the north-star headline size): one group of `--natoms-per-gpu` x N atoms
 (default 1,000,000 per GPU), uniform water-like box at 100 atoms/nm^3, orthorhombic PBC,
 `COORDINATION GROUPA=1-n SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=10`.
-A step = prepare() + calculate() on one frame (frames: base configuration + a small wiggle, so the frozen list
-stays valid between the rebuilds that happen every 10th step).  The i-atoms are sharded over the ranks and the
-per-GPU share is fixed -> "scaling": "weak".
+A step = prepare() + calculate() on one frame.  The i-atoms are sharded over the ranks and the per-GPU share is
+fixed -> "scaling": "weak".
 
-Numerator of the metric for BOTH arms: the number of pairs within NL_CUTOFF at the last rebuild (= the size of
-the reference's NLIST list); evaluating a pair from both ends on the GPU does not count twice.
+Frames: a CUMULATIVE random walk (0.0013 nm rms per coordinate and step, about water at 300 K with a 2 fs step), one
+new frame per step, so everything the engine conditions on displacements sees what an MD run shows it: partners that
+come back inside D_MAX + skin (far parts of the rows get visited), a super-list that expires.  `regimes` also times
+the two ends: "best" = frames that only jitter around one configuration (round-1 bench: both shortcuts always
+apply), "worst" = the same drifting frames with both shortcuts switched off (every far part visited, every rebuild a
+full cell scan).  The headline `value` is "typical".
 
-  value : inputs resident in HBM (positions of all frames uploaded before the timed region, result left on the
-          device), all K steps enqueued on the library's stream and timed with CUDA events on that stream.
-  e2e   : the same K steps through the reference-facing C-ABI call with pinned HOST buffers: each rank uploads
-          its slice of the positions, downloads its slice of the derivatives + value + virial every step.
+Numerator of the metric for BOTH arms: the number of pairs within NL_CUTOFF at the last rebuild (= the size of the
+reference's NLIST list); evaluating a pair from both ends on the GPU does not count twice.
+
+  value : inputs resident in HBM (all frames uploaded before the timed region, result left on the device), the K
+          steps enqueued on the library's stream and timed with CUDA events on that stream.
+  sustained : the same K-step block repeated (frames walked back and forth) until >= 1 s has been timed.
+  e2e   : the same K steps through the reference-facing C-ABI call with pinned HOST buffers: each rank uploads its
+          slice of the positions, downloads its slice of the derivatives + value + virial every step.
+  e2e_plumed : (1 GPU) the same steps through the UNMODIFIED PlumedMain of oracle/_ref, driven with plumed_cmd like
+          an MD engine, with `LOAD FILE=libb200coord_plumed.so` -- the whole drop-in path including PLUMED's own
+          per-step host work (atom gather, Value stores, apply()).  The reference build only hosts the plugin here.
+  parity_check : (N > 1) one untimed step of the distributed engine against a single-GPU context on the same frame.
   roofline : the pair-sweep kernel; achieved = 68 algorithmic FLOP per listed pair / CUDA-event
           duration of the kernel, peak = FP64 FMA rate measured in this run with a DFMA microbenchmark.
+  other_configs : BASELINE.json configs[0], [2] (both list flavours), [3] (through plumed_cmd) and [4] (strong
+          scaling over the N GPUs of this run), a few steps each.
   cpu_baseline : the REAL reference (oracle/_ref) timed on this box's host cores on a bounded sample.
 
---impl reference times the reference's own CPU COORDINATION (oracle/_ref through plumed_cmd, all host threads)
-on a bounded sample of the same workload (same density and keywords, fewer atoms; the reference's cost is linear
-in the atom count with NLISTCELLS, the only list flavour it can run above 32768 atoms).
+--impl reference times the reference's own CPU COORDINATION (oracle/_ref through plumed_cmd, all host threads) at
+the literal size of BASELINE configs[1] (100,000 atoms; NLISTCELLS + PLUMED_IGNORE_NL_MEMORY_ERROR, the only list
+flavour the reference can run above 32768 atoms) and says so in ITS config.workload.
 """
 import argparse
 import ctypes as C
@@ -45,20 +58,48 @@ DENSITY = 100.0
 FLOP_PER_PAIR = 68.0  # ortho PBC + rational 6/12, SURVEY.md 8(d)
 SWITCH = "RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8"
 NL_CUTOFF, NL_STRIDE = 1.0, 10
+DRIFT = 0.0013  # nm rms per coordinate and step
 METRIC = "COORDINATION pair evals/s (value+3N derivs+virial)"
 UNIT = "pair_evals/s"
 
 
-def make_frames(n, nframes, seed=SEED):
-    """base configuration + small cumulative wiggle (<=0.01 nm from the base), box edge L"""
+def box_edge(n, density=DENSITY):
+    return (n / density) ** (1.0 / 3.0)
+
+
+def make_frames(n, nframes, seed=SEED, drift=None, density=DENSITY):
+    """numpy frames: base configuration + i.i.d. jitter (drift None) or a cumulative random walk"""
     rng = np.random.default_rng(seed)
-    L = (n / DENSITY) ** (1.0 / 3.0)
-    base = rng.random((n, 3)) * L
+    L = box_edge(n, density)
+    pos = rng.random((n, 3)) * L
     frames = []
-    for f in range(nframes):
-        d = rng.standard_normal((n, 3))
-        frames.append(base + 0.002 * d)
+    for _ in range(nframes):
+        if drift is None:
+            frames.append(pos + 0.002 * rng.standard_normal((n, 3)))
+        else:
+            pos = pos + drift * rng.standard_normal((n, 3))
+            frames.append(pos.copy())
     return frames, np.diag([L, L, L])
+
+
+def make_frames_device(n, nframes, drift, seed=SEED, density=DENSITY, box=None):
+    """the same kind of frames generated on the GPU (identical on every rank: same seed, same generator)"""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    L = box_edge(n, density)
+    boxm = np.diag([L, L, L]) if box is None else box
+    frac = torch.rand((n, 3), generator=g, device="cuda", dtype=torch.float64)
+    pos = frac @ torch.tensor(boxm, device="cuda", dtype=torch.float64)
+    frames = []
+    for _ in range(nframes):
+        step = torch.randn((n, 3), generator=g, device="cuda", dtype=torch.float64)
+        if drift is None:
+            frames.append(pos + 0.002 * step)
+        else:
+            pos = pos + drift * step
+            frames.append(pos.clone())
+    return frames, boxm
 
 
 class ClockSampler(threading.Thread):
@@ -101,11 +142,12 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         inside = [r for r in self.rows if any(w[0] <= r[-1] <= (w[1] or r[-1]) for w in self.windows)]
-        which = "timed regions (value + e2e)"
+        which = "timed regions (value + sustained + e2e)"
         if not inside:  # regions shorter than the sampling period: fall back to everything sampled under load
             inside, which = self.rows, "whole run (timed regions shorter than the 20 ms sampling period)"
         sm = [float(r[0]) for r in inside if len(r) >= 8 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in inside if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in inside if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
         for r in inside:
             if len(r) >= 8:
@@ -113,13 +155,13 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": which}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
 def pin_to_gpu_numa_node(local):
     """Multi-GPU runs: keep this rank's threads (and therefore its page-locked staging buffers, which are placed by
     first touch) on the NUMA node its GPU hangs off, so that eight ranks do not push their PCIe traffic through one
-    socket.  Best effort: returns the node or None."""
+    socket.  Best effort: returns the node or None (single-node boxes report -1)."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local)
@@ -151,12 +193,12 @@ def pinned_array(L, shape):
 
 
 # ------------------------------------------------------------------------------------------------
-def reference_cpu(sample_atoms, steps, warmup, threads):
-    """the reference's CPU COORDINATION on a bounded sample; returns dict(value, ms_per_step, ...).
+# the reference on the host
+def reference_cpu(natoms, steps, warmup, threads, flavours=("NLIST", "NLISTCELLS"), drift=DRIFT):
+    """the reference's CPU COORDINATION through plumed_cmd; returns the faster flavour's dict plus all flavours.
 
-    Both list flavours are timed and the FASTER one is reported: NLIST (the keyword our arm uses; the reference
-    can only run it below 32768 atoms and its rebuild is O(N^2), so a 20000-atom sample flatters it) and NLISTCELLS
-    (the only flavour it can run at the headline size; cost linear in N, but it sweeps the 27-cell superset)."""
+    NLIST is the keyword our arm uses; the reference can only run it below 32768 atoms and its rebuild is O(N^2).
+    NLISTCELLS is the only flavour it can run above that (cost linear in N, but it sweeps the 27-cell superset)."""
     os.environ["PLUMED_NUM_THREADS"] = str(threads)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
@@ -164,31 +206,32 @@ def reference_cpu(sample_atoms, steps, warmup, threads):
     from oracle import oracle as O
     if not R.available():
         return None
-    n = sample_atoms
-    frames, box = make_frames(n, 4)
+    n = natoms
+    frames, box = make_frames(n, min(warmup + steps, 2 * NL_STRIDE), drift=drift)
     # numerator: pairs within NL_CUTOFF at the rebuild frame (what NLIST lists)
     nl = O.NeighborList(O.NL_SINGLELIST, n, 0, cutoff=NL_CUTOFF, stride=NL_STRIDE)
     nl.update(O.make_pbc(box), frames[0], fast=True)
     pairs = int(nl.size())
-    best = None
-    flavours = {}
-    for flavour in (["NLIST", "NLISTCELLS"] if n <= 32768 else ["NLISTCELLS"]):
+    best, out = None, {}
+    for flavour in flavours:
+        if flavour == "NLIST" and n > 32768:
+            continue
         line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} %s NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, flavour, NL_CUTOFF, NL_STRIDE)
         p = R.Plumed(n, [line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"])
         for s in range(warmup):
             p.calc(s, frames[s % len(frames)], box)
-        nsteps = steps * (3 if flavour == "NLIST" else 1)  # NLIST steps are ~8x cheaper: time three times as many
         t0 = time.perf_counter()
-        for s in range(warmup, warmup + nsteps):
+        for s in range(warmup, warmup + steps):
             p.calc(s, frames[s % len(frames)], box)
         dt = time.perf_counter() - t0
         p.close()
-        r = {"value": pairs * nsteps / dt, "ms_per_step": 1e3 * dt / nsteps, "pairs_per_step": pairs, "atoms": n,
-             "keywords": line, "seconds": dt, "flavour": flavour, "steps": nsteps}
-        flavours[flavour] = r["value"]
+        r = {"value": pairs * steps / dt, "ms_per_step": 1e3 * dt / steps, "pairs_per_step": pairs, "atoms": n,
+             "keywords": line, "seconds": dt, "flavour": flavour, "steps": steps}
+        out[flavour] = r
         if best is None or r["value"] > best["value"]:
             best = r
-    best["flavours"] = flavours
+    best = dict(best)
+    best["flavours"] = {k: v["value"] for k, v in out.items()}
     return best
 
 
@@ -197,19 +240,24 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    r = reference_cpu(args.ref_sample_atoms, args.steps, args.warmup, threads)
+    n = args.ref_atoms
+    r = reference_cpu(n, args.steps, args.warmup, threads, flavours=("NLISTCELLS",) if n > 32768 else ("NLIST", "NLISTCELLS"))
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
         return
-    sample = ("%d-atom box of the same density/keywords, faster of the reference's two list flavours (%s; pair evals/s: %s); "
-              "%d warm-up + %d timed steps incl. rebuilds every %d.  The reference cannot run NLIST above 32768 atoms, "
-              "NLISTCELLS costs the same per atom at any size" %
+    sample = ("the whole %d-atom box of BASELINE configs[1] (%s; pair evals/s: %s), %d warm-up + %d timed steps incl. a list "
+              "rebuild every %d.  The reference cannot run NLIST above 32768 atoms (SURVEY 9.5); NLISTCELLS costs the same "
+              "per atom at any size, so this is also its rate at the 1 M atoms of the GPU arm" %
               (r["atoms"], r["flavour"], ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), args.warmup, args.steps,
                NL_STRIDE))
+    cfg = {"workload": "BASELINE configs[1] at its literal size: COORDINATION single group, %d atoms, orthorhombic PBC, "
+                       "SWITCH={%s} %s NL_CUTOFF=%g NL_STRIDE=%d, 100 atoms/nm^3, drifting frames; reference CPU code on "
+                       "%d host threads" % (r["atoms"], SWITCH, r["flavour"], NL_CUTOFF, NL_STRIDE, threads),
+           "natoms": r["atoms"], "gpu_arm_natoms_per_gpu": args.natoms_per_gpu,
+           "pair_count": "pairs within NL_CUTOFF at the last rebuild (NLIST size); both arms"}
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "reference_keywords": r["keywords"], "pairs_per_step_sample": r["pairs_per_step"]}
@@ -221,134 +269,170 @@ def workload_config(args, world):
     return {"workload": "BASELINE configs[1] at headline size: COORDINATION single group, %d atoms (%d per GPU), "
                         "orthorhombic PBC, SWITCH={%s} NLIST NL_CUTOFF=%g NL_STRIDE=%d, 100 atoms/nm^3"
                         % (n, args.natoms_per_gpu, SWITCH, NL_CUTOFF, NL_STRIDE),
-            "natoms": n, "natoms_per_gpu": args.natoms_per_gpu, "parallelism": "i-atom shards x%d%s" % (world, "" if world == 1 else (", NCCL all-gather" if args.no_peer else ", in-kernel NVLink peer stores")),
+            "natoms": n, "natoms_per_gpu": args.natoms_per_gpu,
+            "parallelism": "i-atom shards x%d%s" % (world, "" if world == 1 else (", NCCL all-gather" if args.no_peer else ", NVLink peer memory")),
+            "frames": "cumulative random walk, %.4f nm rms per coordinate and step, one new frame per step" % DRIFT,
             "pair_count": "pairs within NL_CUTOFF at the last rebuild (NLIST size); both arms",
             "cache": "per-step inputs (neighbour list %.1f GB + positions) exceed the 126 MB L2" %
                      (n / world * 419 * 4 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+class Engine:
+    """one context per rank + the plumbing the legs share"""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    numa_node = pin_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, self.world))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.numa_node = pin_to_gpu_numa_node(self.local) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import plumed2_b200 as P
+        from plumed2_b200 import capi
+        self.P, self.capi, self.L = P, capi, capi.lib()
+        self.args = args
 
-    import plumed2_b200 as P
-    from plumed2_b200 import capi
-    L = capi.lib()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+        self.capi.check(self.L.b200coord_device_synchronize())
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        capi.check(L.b200coord_device_synchronize())
-
-    def allmax(x):
-        if world == 1:
+    def allmax(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def allsum(x):
-        if world == 1:
+    def allsum(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
-    n = args.natoms_per_gpu * world
-    K, W, F = args.steps, args.warmup, args.frames
-    frames, box = make_frames(n, F)
-    line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
-    c = P.Coordination.from_input(line, device=local, rank=rank, nranks=world,
-                                  precision=capi.FP32 if args.fp32 else capi.FP64)
-    if world > 1:
-        ids = [P.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        c.comm_init(ids[0])
-        if not args.no_peer:  # fused sweep + exchange: derivative rows go to the peers from inside the sweep kernel
-            handles = [None] * world
-            dist.all_gather_object(handles, c.peer_export())
-            c.peer_attach(handles)
+    def context(self, line, env=None, sharded=True, **kw):
+        """a Coordination context of this rank; env = A/B switches read at creation"""
+        env = env or {}
+        os.environ.update(env)
+        try:
+            c = self.P.Coordination.from_input(line, device=self.local, rank=self.rank if sharded else 0,
+                                               nranks=self.world if sharded else 1, **kw)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        if sharded and self.world > 1:
+            ids = [self.P.comm_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(ids, src=0)
+            c.comm_init(ids[0])
+            if not self.args.no_peer:
+                handles = [None] * self.world
+                self.dist.all_gather_object(handles, c.peer_export())
+                c.peer_attach(handles)
+        return c
+
+    def device_steps(self, c, frames, d_out, step, count, order=None):
+        """enqueue `count` steps on the context's stream; frames[i] are device tensors; returns the next step number"""
+        L, capi, ctx = self.L, self.capi, c._ctx
+        F = len(frames)
+        for i in range(count):
+            c.prepare(step)
+            f = frames[order[i] if order is not None else step % F]
+            capi.check(L.b200coord_enqueue_device(ctx, C.c_void_p(f.data_ptr()), C.c_void_p(d_out.data_ptr())), ctx)
+            step += 1
+        return step
+
+    def timed_device_block(self, c, frames, d_out, step, count, order=None):
+        L, capi, ctx = self.L, self.capi, c._ctx
+        capi.check(L.b200coord_stream_mark(ctx, 0), ctx)
+        step = self.device_steps(c, frames, d_out, step, count, order)
+        capi.check(L.b200coord_stream_mark(ctx, 1), ctx)
+        ms = C.c_float(0)
+        capi.check(L.b200coord_stream_elapsed_ms(ctx, C.byref(ms)), ctx)
+        return step, float(ms.value)
+
+
+def regime_run(E, line, box, frames, W, K, env=None, sampler=None, sustained=False):
+    """W warm-up + K timed device-resident steps of a fresh context; dict with times and what the engine did"""
+    torch = E.torch
+    n = frames[0].shape[0]
+    c = E.context(line, env=env)
     c._set_box(box)
-    ctx = c._ctx
+    d_out = torch.empty(3 * n + 10, dtype=torch.float64, device="cuda")
+    step = E.device_steps(c, frames, d_out, 0, W)
+    E.barrier()
+    st0 = c.stats()
+    if sampler:
+        sampler.open_window()
+    step, ms = E.timed_device_block(c, frames, d_out, step, K)
+    if sampler:
+        sampler.close_window()
+    E.barrier()
+    st1 = c.stats()
+    ms = E.allmax(ms)
+    pairs = E.allsum(float(st1["nl_size"]))
+    out = {"ms_per_step": ms / K, "value": pairs * K / (ms * 1e-3), "pairs_per_step": pairs,
+           "sweep_ms": st1["sweep_ms_sum"] / max(1, st1["sweep_count"]),
+           "rebuild_ms": st1["build_ms_sum"] / max(1, st1["build_count"]), "rebuilds": int(st1["build_count"]),
+           "super_list_builds_total": int(st1["super_builds"]), "filter_rebuilds_total": int(st1["filter_rebuilds"]),
+           "rebuilds_total": int(st1["rebuilds"]),
+           "entries_evaluated_last_step": int(st1["pair_evals"]), "entries_listed": 2 * int(st1["nl_size"]),
+           "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]), "my_pairs": float(st1["nl_size"])}
+    if sustained:
+        # the K-step block again and again (frames walked back and forth, so that consecutive frames stay one step
+        # apart) until at least a second has been timed
+        F = len(frames)
+        fwd = [(W + i) % F for i in range(K)]
+        total_ms, total_steps, flip = 0.0, 0, False
+        if sampler:
+            sampler.open_window()
+        while total_ms < 1000.0 and total_steps < 200 * K:
+            order = fwd[::-1] if not flip else fwd
+            flip = not flip
+            step, ms = E.timed_device_block(c, frames, d_out, step, K, order)
+            total_ms += E.allmax(ms)
+            total_steps += K
+        if sampler:
+            sampler.close_window()
+        st2 = c.stats()
+        out["sustained"] = {"ms_per_step": total_ms / total_steps, "value": pairs * total_steps / (total_ms * 1e-3),
+                            "steps": total_steps, "seconds": total_ms * 1e-3,
+                            "sweep_ms": st2["sweep_ms_sum"] / max(1, st2["sweep_count"])}
+    tail = d_out[3 * n:].cpu().numpy()
+    out["cv_value"] = float(tail[9])
+    return c, d_out, step, out
+
+
+def e2e_run(E, c, frames, step, W, K, sampler):
+    """the same steps through b200coord_calculate[_distributed] with pinned host buffers"""
+    L, capi, ctx = E.L, E.capi, c._ctx
     sb, sc = C.c_uint(), C.c_uint()
     capi.check(L.b200coord_my_slice(ctx, C.byref(sb), C.byref(sc)))
     lo, cnt = sb.value, sc.value
-
-    peak = C.c_double(0)
-    capi.check(L.b200coord_measure_fp64_peak(local, C.byref(peak)))
-
-    # ---------------- value: inputs resident in HBM
-    d_frames = []
-    for f in frames:
-        p = C.c_void_p()
-        capi.check(L.b200coord_device_alloc(f.nbytes, C.byref(p)))
-        capi.check(L.b200coord_memcpy_h2d(p, np.ascontiguousarray(f).ctypes.data_as(C.c_void_p), f.nbytes))
-        d_frames.append(p)
-    d_out = C.c_void_p()
-    capi.check(L.b200coord_device_alloc((3 * n + 10) * 8, C.byref(d_out)))
-    step = 0
-    for _ in range(W):
-        c.prepare(step)
-        capi.check(L.b200coord_enqueue_device(ctx, d_frames[step % F], d_out), ctx)
-        step += 1
-    barrier()
-    st0 = c.stats()
-    sampler = ClockSampler(local)
-    sampler.start()
-    sampler.wait_first()
-    barrier()
-    sampler.open_window()
-    capi.check(L.b200coord_stream_mark(ctx, 0), ctx)
-    for _ in range(K):
-        c.prepare(step)
-        capi.check(L.b200coord_enqueue_device(ctx, d_frames[step % F], d_out), ctx)
-        step += 1
-    capi.check(L.b200coord_stream_mark(ctx, 1), ctx)
-    ms = C.c_float(0)
-    capi.check(L.b200coord_stream_elapsed_ms(ctx, C.byref(ms)), ctx)
-    sampler.close_window()
-    barrier()
-    st1 = c.stats()
-    value_ms = allmax(float(ms.value))
-    pairs_per_step = allsum(float(st1["nl_size"]))
-    launches = int(st1["kernel_launches"] - st0["kernel_launches"])
-    sweep_ms = st1["sweep_ms_sum"] / max(1, st1["sweep_count"])
-    build_ms = st1["build_ms_sum"] / max(1, st1["build_count"])
-    tail = np.zeros(10)
-    capi.check(L.b200coord_memcpy_d2h(tail.ctypes.data_as(C.c_void_p), C.c_void_p(d_out.value + 3 * n * 8), 80))
-    value_cv = float(tail[9])
-    for p in d_frames:
-        L.b200coord_device_free(p)
-    L.b200coord_device_free(d_out)
-
-    # ---------------- e2e: pinned host buffers through the C-ABI call, H2D + D2H inside the timed region
     h_frames = []
     for f in frames:
         a, _ptr = pinned_array(L, (max(cnt, 1), 3))
-        a[:cnt] = f[lo:lo + cnt]
+        a[:cnt] = f[lo:lo + cnt].cpu().numpy()
         h_frames.append(a)
     h_deriv, _p2 = pinned_array(L, (max(cnt, 1), 3))
     vir = np.zeros(9)
     val = C.c_double(0)
+    F = len(frames)
 
-    def e2e_step(s):
+    def one(s):
         c.prepare(s)
         src = h_frames[s % F]
-        if world > 1:
+        if E.world > 1:
             capi.check(L.b200coord_calculate_distributed(ctx, src.ctypes.data_as(C.c_void_p), C.byref(val),
                                                          h_deriv.ctypes.data_as(C.c_void_p),
                                                          vir.ctypes.data_as(C.POINTER(C.c_double))), ctx)
@@ -358,35 +442,265 @@ def run_b200(args):
                                              vir.ctypes.data_as(C.POINTER(C.c_double))), ctx)
 
     for _ in range(W):
-        e2e_step(step)
+        one(step)
         step += 1
-    barrier()
+    E.barrier()
     sampler.open_window()
+    ms = C.c_float(0)
     capi.check(L.b200coord_stream_mark(ctx, 0), ctx)
     t0 = time.perf_counter()
     for _ in range(K):
-        e2e_step(step)
+        one(step)
         step += 1
     capi.check(L.b200coord_stream_mark(ctx, 1), ctx)
     capi.check(L.b200coord_stream_elapsed_ms(ctx, C.byref(ms)), ctx)
     wall_ms = 1e3 * (time.perf_counter() - t0)
     sampler.close_window()
+    E.barrier()
+    e2e_ms = E.allmax(max(float(ms.value), wall_ms))
+    pairs = E.allsum(float(c.stats()["nl_size"]))
+    res = {"value": pairs * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
+           "h2d_bytes_per_step": int(cnt * 24), "d2h_bytes_per_step": int(cnt * 24 + 80),
+           "api": "b200coord_calculate_distributed" if E.world > 1 else "b200coord_calculate",
+           "numa_node_of_rank0": E.numa_node}
+    return step, res, (lo, cnt, h_frames, h_deriv, float(val.value), vir.copy())
+
+
+def parity_check(E, c, line, box, frame, step, e2e_state):
+    """N > 1: one more (untimed) distributed step against a single-GPU context on the same frame.  The frozen list of
+    the distributed engine and the fresh list of the checker both hold every pair that can be inside D_MAX (the walk
+    moves atoms by ~0.01 nm per list interval, the list reaches 0.2 nm beyond D_MAX), so the numbers must agree to
+    rounding."""
+    torch, dist, L, capi = E.torch, E.dist, E.L, E.capi
+    lo, cnt, _h, h_deriv, _v, _w = e2e_state
+    n = frame.shape[0]
+    src, _p = pinned_array(L, (max(cnt, 1), 3))
+    src[:cnt] = frame[lo:lo + cnt].cpu().numpy()
+    vir = np.zeros(9)
+    val = C.c_double(0)
+    c.prepare(step * NL_STRIDE + 1)  # never a rebuild step
+    capi.check(L.b200coord_calculate_distributed(c._ctx, src.ctypes.data_as(C.c_void_p), C.byref(val),
+                                                 h_deriv.ctypes.data_as(C.c_void_p),
+                                                 vir.ctypes.data_as(C.POINTER(C.c_double))), c._ctx)
+    full = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    ref_tail = torch.zeros(10, dtype=torch.float64, device="cuda")
+    if E.rank == 0:
+        c1 = E.context(line, sharded=False)
+        c1.prepare(0)
+        c1.calculate(frame.cpu().numpy(), box)
+        full.copy_(torch.from_numpy(np.ascontiguousarray(c1.derivatives)))
+        ref_tail[:9] = torch.from_numpy(np.asarray(c1.virial).reshape(9))
+        ref_tail[9] = c1.value
+        c1.close()
+    dist.broadcast(full, src=0)
+    dist.broadcast(ref_tail, src=0)
+    mine = torch.from_numpy(h_deriv[:cnt].copy()).cuda()
+    scale = float(full.abs().max().item())
+    err = float((mine - full[lo:lo + cnt]).abs().max().item()) / max(scale, 1e-300) if cnt else 0.0
+    err = E.allmax(err)
+    rt = ref_tail.cpu().numpy()
+    return {"max_rel_derivatives": err, "rel_value": abs(val.value - rt[9]) / abs(rt[9]),
+            "max_rel_virial": float(np.abs(vir - rt[:9]).max() / np.abs(rt[:9]).max()),
+            "against": "single-GPU context of the same library on the same frame (rank 0), every rank compares its own slice",
+            "tolerance": 1e-10}
+
+
+def plumed_e2e(E, line, box, frames, W, K):
+    """the same steps through the unmodified PlumedMain + LOAD plugin (1 GPU); wall clock around plumed_cmd("calc")"""
+    from oracle import refplumed as R
+    plugin = os.path.join(os.path.dirname(E.capi.LIB_PATH), "libb200coord_plumed.so")
+    if not (R.available() and os.path.exists(plugin)):
+        return {"unavailable": "oracle/_ref or the plugin .so is not present on this box"}
+    os.environ["PLUMED_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
+    os.environ["B200COORD_DEVICE"] = str(E.local)
+    os.environ["B200COORD_PIN_HOST"] = "1"
+    n = frames[0].shape[0]
+    host = [f.cpu().numpy() for f in frames]
+    p = R.Plumed(n, ["LOAD FILE=" + plugin, line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"], log="/tmp/bench_plumed_e2e.log")
+    F = len(host)
+    for s in range(W):
+        p.calc(s, host[s % F], box)
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        p.calc(s, host[s % F], box)
+    dt = time.perf_counter() - t0
+    p.close()
+    return {"ms_per_step": 1e3 * dt / K, "threads": os.cpu_count() or 1,
+            "path": "plumed_cmd(setPositions..calc) -> PlumedMain -> CoordinationB200 (LOAD) -> libb200coord; forces and "
+                    "virial returned to the caller every step; pageable caller arrays registered once (B200COORD_PIN_HOST)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def other_configs(E, peak_tflops, args):
+    """BASELINE.json configs[0], [2], [3], [4]: a few device-resident steps each (jittering frames: these lines are
+    here for coverage of the kernels they run, not for the displacement-conditioned shortcuts)"""
+    torch = E.torch
+    out = {}
+
+    def run(name, line, n, box, flop, steps=10, warm=3, drift=None, note=None, sharded=False):
+        frames, _ = make_frames_device(n, 4 if drift is None else steps + warm, drift, seed=SEED + 7, box=box)
+        c = E.context(line, sharded=sharded)
+        c._set_box(box)
+        d_out = torch.empty(3 * n + 10, dtype=torch.float64, device="cuda")
+        step = E.device_steps(c, frames, d_out, 0, warm)
+        E.barrier()
+        step, ms = E.timed_device_block(c, frames, d_out, step, steps)
+        E.barrier()
+        st = c.stats()
+        ms = E.allmax(ms)
+        pairs = E.allsum(float(st["nl_size"]))
+        sweep = st["sweep_ms_sum"] / max(1, st["sweep_count"])
+        r = {"keywords": line if len(line) < 200 else line[:200] + "...", "natoms": n, "ms_per_step": ms / steps,
+             "pairs_per_step": pairs, "value": pairs * steps / (ms * 1e-3), "sweep_ms": sweep,
+             "rebuild_ms": st["build_ms_sum"] / max(1, st["build_count"]), "rebuilds": int(st["build_count"]),
+             "flop_per_pair": flop,
+             "roofline_frac": (flop * float(st["nl_size"]) / (sweep * 1e-3) / 1e12 / peak_tflops) if sweep > 0 else None,
+             "cv_value": float(d_out[3 * n + 9].item())}
+        if note:
+            r["note"] = note
+        c.close()
+        del frames, d_out
+        torch.cuda.empty_cache()
+        out[name] = r
+
+    if E.world == 1:
+        # configs[0]: plumed driver, 1k atoms, no NL
+        n = 1000
+        L0 = box_edge(n)
+        run("configs[0]", "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 NN=6 MM=12}" % n, n, np.diag([L0] * 3), 68.0,
+            steps=20)
+        # configs[2]: 10k solute vs 1M solvent, triclinic, EXP, rebuild every step; both list flavours
+        na, nb = 10000, 1000000
+        n = na + nb
+        L2 = box_edge(n)
+        tri = L2 * np.array([[1.0, 0.0, 0.0], [0.2, 1.0, 0.0], [0.1, 0.3, 1.0]])
+        for flavour in ("NLIST", "NLISTCELLS"):
+            run("configs[2] " + flavour,
+                "c: COORDINATION GROUPA=1-%d GROUPB=%d-%d SWITCH={EXP R_0=0.2 D_MAX=0.9} %s NL_CUTOFF=1.0 NL_STRIDE=1"
+                % (na, na + 1, n, flavour), n, tri, 102.0,
+                note="pairs = list size: NLIST pairs within NL_CUTOFF, NLISTCELLS the 27-cell superset the reference iterates")
+        out["configs[3]"] = config3_metad(E)
+    # configs[4]: 4M atoms, strong scaling over the ranks of this run
+    n = 4000000
+    L4 = box_edge(n, 33.4)
+    frames_note = "4M atoms at 33.4 atoms/nm^3 (O-only water, SURVEY 8(d)); total work fixed, sharded over %d GPU(s)" % E.world
+    run("configs[4]", "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE),
+        n, np.diag([L4] * 3), 68.0, steps=20, warm=5, note=frames_note, sharded=True)
+    # the frames of configs[4] use density 100 positions scaled into the 33.4 box by make_frames_device(box=...)
+    return out
+
+
+def config3_metad(E):
+    """configs[3]: COORDINATION (250k atoms) driving METAD with a GRID through plumed_cmd, forces + virial returned"""
+    from oracle import refplumed as R
+    plugin = os.path.join(os.path.dirname(E.capi.LIB_PATH), "libb200coord_plumed.so")
+    if not (R.available() and os.path.exists(plugin)):
+        return {"unavailable": "oracle/_ref or the plugin .so is not present on this box"}
+    os.environ["PLUMED_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
+    os.environ["B200COORD_DEVICE"] = str(E.local)
+    os.environ["B200COORD_PIN_HOST"] = "1"
+    n = 250000
+    frames, box = make_frames(n, 25, seed=SEED + 3, drift=DRIFT)
+    body = "GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
+    c = E.context("c: COORDINATION " + body, sharded=False)
+    c.prepare(0)
+    v0 = c.calculate(frames[0], box)
+    c.close()
+    lines = ["LOAD FILE=" + plugin, "c: COORDINATION " + body,
+             "METAD ARG=c SIGMA=%g HEIGHT=1.2 PACE=5 GRID_MIN=%g GRID_MAX=%g GRID_BIN=2000 FILE=/tmp/bench_HILLS" %
+             (2e-4 * v0, 0.9 * v0, 1.1 * v0)]
+    p = R.Plumed(n, lines, log="/tmp/bench_config3.log")
+    W, K = 5, 20
+    for s in range(W):
+        p.calc(s, frames[s], box)
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        r = p.calc(s, frames[s], box)
+    dt = time.perf_counter() - t0
+    p.close()
+    return {"keywords": lines[1][:120] + " + " + lines[2][:60] + "...", "natoms": n, "ms_per_step": 1e3 * dt / K,
+            "path": "plumed_cmd -> PlumedMain -> CoordinationB200 (LOAD) + the reference's own METAD; wall clock",
+            "bias_last_step": r["bias"], "max_abs_force_last_step": float(np.abs(r["forces"]).max()), "cv_first_frame": v0}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    E = Engine(args)
+    torch, capi, L = E.torch, E.capi, E.L
+    world, rank, local = E.world, E.rank, E.local
+    n = args.natoms_per_gpu * world
+    K, W = args.steps, args.warmup
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
+
+    peak = C.c_double(0)
+    capi.check(L.b200coord_measure_fp64_peak(local, C.byref(peak)))
+
+    frames, box = make_frames_device(n, W + K, DRIFT)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first()
+    E.barrier()
+
+    # ---------------- value (typical regime) + sustained
+    c, d_out, step, typ = regime_run(E, line, box, frames, W, K, sampler=sampler, sustained=True)
+    # ---------------- e2e through the C-ABI call with host buffers, same context, same frames
+    step = ((step + NL_STRIDE - 1) // NL_STRIDE) * NL_STRIDE  # the e2e leg starts on a rebuild step like the value leg
+    step, e2e, e2e_state = e2e_run(E, c, frames, step, W, K, sampler)
     clocks = sampler.stop()
-    barrier()
-    e2e_ms = allmax(max(float(ms.value), wall_ms))
-    st2 = c.stats()
-    e2e_pairs = allsum(float(st2["nl_size"]))
+    parity = None
+    if world > 1:
+        parity = parity_check(E, c, line, box, frames[-1], step, e2e_state)
+    c.close()
+    del d_out
+    torch.cuda.empty_cache()
+
+    regimes = {"typical": {k: typ[k] for k in ("ms_per_step", "value", "sweep_ms", "rebuild_ms", "rebuilds",
+                                                "super_list_builds_total", "filter_rebuilds_total", "rebuilds_total",
+                                                "entries_evaluated_last_step", "entries_listed")}}
+    regimes["typical"]["what"] = "drifting frames, engine defaults (the headline)"
+    if world == 1 and not args.no_regimes:
+        jit, _ = make_frames_device(n, 4, None)
+        cb, _d, _s, best = regime_run(E, line, box, jit, W, K)
+        cb.close()
+        del jit, _d
+        torch.cuda.empty_cache()
+        cw, _d, _s, worst = regime_run(E, line, box, frames, W, K,
+                                       env={"B200COORD_NO_FAR_SPLIT": "1", "B200COORD_NO_SUPERLIST": "1"})
+        cw.close()
+        del _d
+        torch.cuda.empty_cache()
+        keys = ("ms_per_step", "value", "sweep_ms", "rebuild_ms", "rebuilds", "super_list_builds_total",
+                "filter_rebuilds_total", "entries_evaluated_last_step", "entries_listed")
+        regimes["best"] = {k: best[k] for k in keys}
+        regimes["best"]["what"] = "frames that jitter around one configuration: far parts never visited, every rebuild filters the super-list"
+        regimes["worst"] = {k: worst[k] for k in keys}
+        regimes["worst"]["what"] = "drifting frames, B200COORD_NO_FAR_SPLIT=1 B200COORD_NO_SUPERLIST=1: every listed pair evaluated every step, every rebuild a full cell scan"
+
+    e2e_pl = None
+    others = None
+    if world == 1 and not args.no_plumed_e2e:
+        e2e_pl = plumed_e2e(E, line, box, frames, W, K)
+        if "ms_per_step" in e2e_pl:
+            e2e_pl["value"] = typ["pairs_per_step"] / (e2e_pl["ms_per_step"] * 1e-3)
+            e2e_pl["unit"] = UNIT
+    del frames
+    torch.cuda.empty_cache()
+    if not args.no_other_configs:
+        others = other_configs(E, peak.value, args)
 
     if rank == 0:
-        value = pairs_per_step * K / (value_ms * 1e-3)
-        e2e_value = e2e_pairs * K / (e2e_ms * 1e-3)
-        my_pairs = float(st1["nl_size"])
+        sweep_ms = typ["sweep_ms"]
+        my_pairs = typ["my_pairs"]
         achieved = FLOP_PER_PAIR * my_pairs / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else None
-        traffic = None
+        traffic, traffic_src = None, None
         tf = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                tj = json.load(open(tf))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "recorded, not measured in this run: " + tj.get("source", "profiles/sweep_traffic.json")
             except Exception:
                 traffic = None
         peaks = {}
@@ -398,35 +712,40 @@ def run_b200(args):
         rows_mine = n / world
         # algorithmic HBM bytes of one sweep: 4 B per list entry (2 per pair), the 32 B records once, 24 B of derivatives
         list_bytes = 2.0 * my_pairs * 4 + 32.0 * n + 24.0 * rows_mine
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32 pair arithmetic, f64 minimum image and accumulation (opt-in, 1e-5)" if args.fp32 else "f64",
-               "data": "synthetic", "config": workload_config(args, world),
-               "pairs_per_step": pairs_per_step, "cv_value": value_cv,
-               "roofline": {"kernel": "k_sweep_list<rationalfix6, orthorhombic, %s>" % ("float" if args.fp32 else "double"),
-                            "bound": "fp64",
+        out = {"metric": METRIC, "value": typ["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": typ["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+               "pairs_per_step": typ["pairs_per_step"], "cv_value": typ["cv_value"],
+               "regimes": regimes, "sustained": typ.get("sustained"),
+               "roofline": {"kernel": "k_sweep_img<rationalfix6, double> (image-mode list sweep)", "bound": "fp64",
                             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                            "frac": (achieved / peak.value) if achieved else None, "traffic": traffic,
+                            "frac": (achieved / peak.value) if achieved else None,
+                            "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                             "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": my_pairs,
-                            "kernel_ms": sweep_ms, "executed_pair_evals_per_launch": 2.0 * my_pairs,
+                            "kernel_ms": sweep_ms,
+                            "entries_evaluated_per_launch": typ["entries_evaluated_last_step"],
+                            "entries_listed": typ["entries_listed"],
                             "hbm": {"achieved_gbs": list_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None,
                                     "peak_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-               "rebuild_ms": build_ms, "rebuilds_in_timed_region": int(st1["build_count"]),
-               "rebuild_kinds": {"super_list_builds_total": int(st1["super_builds"]),
-                                 "filter_rebuilds_total": int(st1["filter_rebuilds"]), "rebuilds_total": int(st1["rebuilds"])},
-               "clocks": clocks, "gpu_launches": launches,
-               "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
-                       "h2d_bytes_per_step": int(cnt * 24), "d2h_bytes_per_step": int(cnt * 24 + 80),
-                       "api": "b200coord_calculate_distributed" if world > 1 else "b200coord_calculate",
-                       "numa_node_of_rank0": numa_node}}
+               "rebuild_ms": typ["rebuild_ms"], "rebuilds_in_timed_region": typ["rebuilds"],
+               "rebuild_kinds": {"super_list_builds_total": typ["super_list_builds_total"],
+                                 "filter_rebuilds_total": typ["filter_rebuilds_total"], "rebuilds_total": typ["rebuilds_total"]},
+               "clocks": clocks, "gpu_launches": typ["gpu_launches"], "e2e": e2e}
+        if e2e_pl is not None:
+            out["e2e_plumed"] = e2e_pl
+        if parity is not None:
+            out["parity_check"] = parity
+        if others is not None:
+            out["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            r = reference_cpu(args.ref_sample_atoms, NL_STRIDE, 0, threads)
+            r = reference_cpu(args.ref_sample_atoms, NL_STRIDE, 1, threads)
             if r is not None:
                 out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
-                                       "sample": "%d-atom box, same density/keywords, faster of NLIST / NLISTCELLS (%s; %s), "
-                                                 "%d steps with a rebuild every %d, %.1f s" %
+                                       "sample": "%d-atom box, same density/keywords/frames, faster of NLIST / NLISTCELLS (%s; %s), "
+                                                 "%d steps with a rebuild every %d, %.1f s.  `--impl reference` runs the "
+                                                 "literal configs[1] size (100k atoms, NLISTCELLS)" %
                                                  (r["atoms"], r["flavour"],
                                                   ", ".join("%s %.3g" % kv for kv in r["flavours"].items()), r["steps"],
                                                   NL_STRIDE, r["seconds"])}
@@ -434,10 +753,9 @@ def run_b200(args):
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
                                        "sample": "oracle/_ref not present on this box"}
         print(json.dumps(out))
-    c.close()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        E.dist.barrier()
+        E.dist.destroy_process_group()
 
 
 def main():
@@ -447,15 +765,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--natoms-per-gpu", type=int, default=1000000)
-    ap.add_argument("--frames", type=int, default=4)
-    ap.add_argument("--ref-sample-atoms", type=int, default=20000)
+    ap.add_argument("--ref-atoms", type=int, default=100000, help="atoms of the --impl reference run (configs[1]: 100000)")
+    ap.add_argument("--ref-sample-atoms", type=int, default=20000, help="atoms of the in-run cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fp32", action="store_true",
-                    help="opt-in FP32 sweep (B200COORD_FP32); the default and the headline number are FP64")
-    ap.add_argument("--no-peer", action="store_true", help="combine with NCCL all-gather instead of in-kernel peer stores")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the best / worst regime runs")
+    ap.add_argument("--no-plumed-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="only value + e2e (profiling runs)")
+    ap.add_argument("--no-peer", action="store_true", help="combine with NCCL all-gather instead of NVLink peer memory")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.quick:
+        args.no_cpu_baseline = args.no_regimes = args.no_plumed_e2e = args.no_other_configs = True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -17,7 +17,7 @@ def test_reference_arm_json_line():
     if not R.available():
         pytest.skip("oracle/_ref not built")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
-                          "--warmup", "3", "--ref-sample-atoms", "3000"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "3", "--ref-atoms", "3000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -28,6 +28,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["steps"] == 3 and "workload" in d["config"]
+    assert d["config"]["natoms"] == 3000 and "3000 atoms" in d["config"]["workload"]  # the arm states ITS size
 
 
 def test_non_root_ranks_of_reference_arm_exit_quietly():
