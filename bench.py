@@ -194,7 +194,7 @@ def pinned_array(L, shape):
 
 # ------------------------------------------------------------------------------------------------
 # the reference on the host
-def reference_cpu(natoms, steps, warmup, threads, flavours=("NLIST", "NLISTCELLS"), drift=DRIFT):
+def reference_cpu(natoms, steps, warmup, threads, flavours=("NLIST", "NLISTCELLS"), drift=DRIFT, steps_cells=None):
     """the reference's CPU COORDINATION through plumed_cmd; returns the faster flavour's dict plus all flavours.
 
     NLIST is the keyword our arm uses; the reference can only run it below 32768 atoms and its rebuild is O(N^2).
@@ -218,15 +218,16 @@ def reference_cpu(natoms, steps, warmup, threads, flavours=("NLIST", "NLISTCELLS
             continue
         line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} %s NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, flavour, NL_CUTOFF, NL_STRIDE)
         p = R.Plumed(n, [line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"])
+        nst = steps_cells if (flavour == "NLISTCELLS" and steps_cells) else steps  # the superset flavour is ~8x slower
         for s in range(warmup):
             p.calc(s, frames[s % len(frames)], box)
         t0 = time.perf_counter()
-        for s in range(warmup, warmup + steps):
+        for s in range(warmup, warmup + nst):
             p.calc(s, frames[s % len(frames)], box)
         dt = time.perf_counter() - t0
         p.close()
-        r = {"value": pairs * steps / dt, "ms_per_step": 1e3 * dt / steps, "pairs_per_step": pairs, "atoms": n,
-             "keywords": line, "seconds": dt, "flavour": flavour, "steps": steps}
+        r = {"value": pairs * nst / dt, "ms_per_step": 1e3 * dt / nst, "pairs_per_step": pairs, "atoms": n,
+             "keywords": line, "seconds": dt, "flavour": flavour, "steps": nst}
         out[flavour] = r
         if best is None or r["value"] > best["value"]:
             best = r
@@ -331,6 +332,7 @@ class Engine:
         finally:
             for k in env:
                 os.environ.pop(k)
+        c.sharded = bool(sharded and self.world > 1)
         if sharded and self.world > 1:
             ids = [self.P.comm_unique_id() if self.rank == 0 else None]
             self.dist.broadcast_object_list(ids, src=0)
@@ -345,12 +347,22 @@ class Engine:
         """enqueue `count` steps on the context's stream; frames[i] are device tensors; returns the next step number"""
         L, capi, ctx = self.L, self.capi, c._ctx
         F = len(frames)
+        # several ranks: every rank keeps the derivatives of its own slice of the atoms (like the e2e call)
+        call = L.b200coord_enqueue_device_distributed if (self.world > 1 and c.sharded) else L.b200coord_enqueue_device
         for i in range(count):
             c.prepare(step)
             f = frames[order[i] if order is not None else step % F]
-            capi.check(L.b200coord_enqueue_device(ctx, C.c_void_p(f.data_ptr()), C.c_void_p(d_out.data_ptr())), ctx)
+            capi.check(call(ctx, C.c_void_p(f.data_ptr()), C.c_void_p(d_out.data_ptr())), ctx)
             step += 1
         return step
+
+    def out_buffer(self, c, n):
+        """device buffer for the result of a device-resident step: [derivatives | virial 9 | value]"""
+        if self.world > 1 and c.sharded:
+            sb, sc = C.c_uint(), C.c_uint()
+            self.capi.check(self.L.b200coord_my_slice(c._ctx, C.byref(sb), C.byref(sc)))
+            return self.torch.empty(3 * sc.value + 10, dtype=self.torch.float64, device="cuda")
+        return self.torch.empty(3 * n + 10, dtype=self.torch.float64, device="cuda")
 
     def timed_device_block(self, c, frames, d_out, step, count, order=None):
         L, capi, ctx = self.L, self.capi, c._ctx
@@ -368,7 +380,7 @@ def regime_run(E, line, box, frames, W, K, env=None, sampler=None, sustained=Fal
     n = frames[0].shape[0]
     c = E.context(line, env=env)
     c._set_box(box)
-    d_out = torch.empty(3 * n + 10, dtype=torch.float64, device="cuda")
+    d_out = E.out_buffer(c, n)
     step = E.device_steps(c, frames, d_out, 0, W)
     E.barrier()
     st0 = c.stats()
@@ -408,8 +420,7 @@ def regime_run(E, line, box, frames, W, K, env=None, sampler=None, sustained=Fal
         out["sustained"] = {"ms_per_step": total_ms / total_steps, "value": pairs * total_steps / (total_ms * 1e-3),
                             "steps": total_steps, "seconds": total_ms * 1e-3,
                             "sweep_ms": st2["sweep_ms_sum"] / max(1, st2["sweep_count"])}
-    tail = d_out[3 * n:].cpu().numpy()
-    out["cv_value"] = float(tail[9])
+    out["cv_value"] = float(d_out[-1].item())
     return c, d_out, step, out
 
 
@@ -517,16 +528,40 @@ def plumed_e2e(E, line, box, frames, W, K):
     os.environ["B200COORD_PIN_HOST"] = "1"
     n = frames[0].shape[0]
     host = [f.cpu().numpy() for f in frames]
-    p = R.Plumed(n, ["LOAD FILE=" + plugin, line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"], log="/tmp/bench_plumed_e2e.log")
+    p = R.Plumed(n, ["LOAD FILE=" + plugin, "DEBUG DETAILED_TIMERS", line, "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"],
+                 log="/tmp/bench_plumed_e2e.log")
     F = len(host)
+    # what an MD engine does every step: hand over its arrays (forces are ADDED to, so nothing is cleared) and call calc
+    forces = np.zeros((n, 3))
+    virial = np.zeros((3, 3))
+    boxm = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(3, 3))
+
+    def one(s):
+        p.cmd("setStep", C.c_int(int(s)))
+        p.cmd("setPositions", host[s % F])
+        p.cmd("setMasses", p.masses)
+        p.cmd("setCharges", p.charges)
+        p.cmd("setBox", boxm)
+        p.cmd("setForces", forces)
+        p.cmd("setVirial", virial)
+        p.cmd("calc", None)
+        p._keep = p._keep[-64:]
+
     for s in range(W):
-        p.calc(s, host[s % F], box)
+        one(s)
     t0 = time.perf_counter()
     for s in range(W, W + K):
-        p.calc(s, host[s % F], box)
+        one(s)
     dt = time.perf_counter() - t0
     p.close()
-    return {"ms_per_step": 1e3 * dt / K, "threads": os.cpu_count() or 1,
+    timers = []
+    try:
+        for ln in open("/tmp/bench_plumed_e2e.log"):
+            if "PLUMED:" in ln and any(k in ln for k in ("Prepare", "Sharing", "Waiting", "Calculating", "Applying", "4A ", "5A ", "Update")):
+                timers.append(" ".join(ln.split()[1:]))
+    except Exception:
+        pass
+    return {"ms_per_step": 1e3 * dt / K, "threads": os.cpu_count() or 1, "plumed_timers": timers[:16],
             "path": "plumed_cmd(setPositions..calc) -> PlumedMain -> CoordinationB200 (LOAD) -> libb200coord; forces and "
                     "virial returned to the caller every step; pageable caller arrays registered once (B200COORD_PIN_HOST)"}
 
@@ -542,7 +577,7 @@ def other_configs(E, peak_tflops, args):
         frames, _ = make_frames_device(n, 4 if drift is None else steps + warm, drift, seed=SEED + 7, box=box)
         c = E.context(line, sharded=sharded)
         c._set_box(box)
-        d_out = torch.empty(3 * n + 10, dtype=torch.float64, device="cuda")
+        d_out = E.out_buffer(c, n)
         step = E.device_steps(c, frames, d_out, 0, warm)
         E.barrier()
         step, ms = E.timed_device_block(c, frames, d_out, step, steps)
@@ -556,7 +591,7 @@ def other_configs(E, peak_tflops, args):
              "rebuild_ms": st["build_ms_sum"] / max(1, st["build_count"]), "rebuilds": int(st["build_count"]),
              "flop_per_pair": flop,
              "roofline_frac": (flop * float(st["nl_size"]) / (sweep * 1e-3) / 1e12 / peak_tflops) if sweep > 0 else None,
-             "cv_value": float(d_out[3 * n + 9].item())}
+             "cv_value": float(d_out[-1].item())}
         if note:
             r["note"] = note
         c.close()
@@ -740,7 +775,7 @@ def run_b200(args):
             out["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            r = reference_cpu(args.ref_sample_atoms, NL_STRIDE, 1, threads)
+            r = reference_cpu(args.ref_sample_atoms, 12 * NL_STRIDE, 1, threads, steps_cells=NL_STRIDE)
             if r is not None:
                 out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
                                        "sample": "%d-atom box, same density/keywords/frames, faster of NLIST / NLISTCELLS (%s; %s), "

@@ -184,6 +184,10 @@ int b200coord_stream_elapsed_ms(b200coord_ctx* ctx, float* ms);   /* waits for t
 int b200coord_calculate_distributed(b200coord_ctx* ctx, const double* pos_slice, double* value, double* deriv_slice,
                                     double* virial);
 int b200coord_my_slice(const b200coord_ctx* ctx, unsigned* slot_begin, unsigned* slot_count);
+/* enqueue-only distributed step for callers whose positions already live on the GPU: d_pos = the WHOLE position array
+ * on this rank's device, d_out_slice = 3*slot_count+10 doubles on this device = [derivatives of this rank's slots |
+ * virial(9) | value].  No host synchronisation unless the list is rebuilt. */
+int b200coord_enqueue_device_distributed(b200coord_ctx* ctx, const double* d_pos, double* d_out_slice);
 /* number of CUDA devices visible to this process (cudaGetDeviceCount) */
 int b200coord_device_count(int* n);
 /* FP64 FMA peak of the device measured with a register-resident DFMA kernel (roofline denominator) */
@@ -200,12 +204,14 @@ int b200coord_nl_pairs(b200coord_ctx* ctx, unsigned* pairs, unsigned long long c
 int b200coord_comm_unique_id(char id[B200COORD_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */
 int b200coord_comm_init(b200coord_ctx* ctx, const char id[B200COORD_UNIQUE_ID_BYTES]); /* every rank */
 
-/* Fused sweep + exchange over NVLink peer memory (optional, after b200coord_comm_init): every rank exports IPC
- * handles of its derivative-row buffers, the host gathers the handles of all ranks (rank order) and hands them
- * back; from then on the sweep kernel stores each finished derivative row straight into every peer's buffer
- * (posted NVLink writes that overlap the arithmetic) and the NCCL all-gather of the rows disappears -- only the
- * 10-double all-reduce of virial/value remains, which also orders the ranks. */
-#define B200COORD_PEER_HANDLE_BYTES 128
+/* Exchange over NVLink peer memory (optional, after b200coord_comm_init): every rank exports IPC handles of its
+ * derivative-row buffers and of its position-slice buffers, the host gathers the handles of all ranks (rank order)
+ * and hands them back.  From then on nothing is broadcast: a rank's derivative rows stay in its own buffer and every
+ * rank PULLS the rows of the atoms it returns (24 bytes each); on steps that keep the neighbour list a rank uploads
+ * only its slice of the positions and the gather of every rank pulls the positions around its own rows from the
+ * owners.  What remains of NCCL per step is the 10-double all-reduce of virial/value (which also orders the ranks)
+ * and a one-element all-reduce as a barrier after the uploads; rebuild steps still all-gather the positions. */
+#define B200COORD_PEER_HANDLE_BYTES 256
 int b200coord_peer_export(b200coord_ctx* ctx, char handle[B200COORD_PEER_HANDLE_BYTES]);
 int b200coord_peer_attach(b200coord_ctx* ctx, const char* all_handles /* nranks * B200COORD_PEER_HANDLE_BYTES */);
 

@@ -15,7 +15,7 @@ STYLE_PAIR, STYLE_TWOLIST, STYLE_SINGLELIST = 0, 1, 2
 NL_NONE, NL_CLASSIC, NL_CELLS = 0, 1, 2
 FP64, FP32 = 0, 1
 UNIQUE_ID_BYTES = 128
-PEER_HANDLE_BYTES = 128
+PEER_HANDLE_BYTES = 256
 
 SW_NAMES = ["rationalfix12", "rationalfix10", "rationalfix8", "rationalfix6", "rationalfix4", "rationalfix2",
             "rational", "rationalFast", "rationalSimple", "rationalSimpleFast", "exponential", "gaussian",
@@ -32,7 +32,7 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
             "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach",
             "b200coord_pairing_dhenergy", "b200coord_set_charges", "b200coord_pairing_ghbfix",
-            "b200coord_set_types", "b200coord_device_count"]
+            "b200coord_set_types", "b200coord_device_count", "b200coord_enqueue_device_distributed"]
 
 
 class B200CoordError(RuntimeError):
@@ -115,6 +115,7 @@ def lib():
     L.b200coord_my_slice.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
     L.b200coord_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.b200coord_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.b200coord_enqueue_device_distributed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200coord_peer_export.argtypes = [C.c_void_p, C.c_char_p]
     L.b200coord_peer_attach.argtypes = [C.c_void_p, C.c_char_p]
     if L.b200coord_abi_version() != ABI_VERSION:

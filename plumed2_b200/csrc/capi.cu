@@ -181,6 +181,14 @@ struct b200coord_ctx {
   DevBuf<double> d_sderiv_b;          // second parity buffer (d_sderiv is the first)
   double* peer_rows[2][8] = {{nullptr}};  // [parity][rank], own entries point at the local buffers
   unsigned parity = 0;
+  // positions over peer memory: every rank uploads only its slot slice into one of two slice buffers, and the gather
+  // of a step that keeps its list pulls the positions it needs from the owners (kernels.cuh: PosSrc)
+  DevBuf<double> d_pslice[2];
+  double* peer_pos[2][8] = {{nullptr}};
+  unsigned pos_parity = 0;
+  DevBuf<uint32_t> d_inv;             // slot -> sorted index (inverse of d_perm)
+  IdxRanges needed;                   // sorted indices this rank's rows can touch (its rows + every possible partner)
+  unsigned* h_idx = nullptr;          // pinned scratch for compute_needed
   b200coord_stats stats;
   std::string err;
 };
@@ -343,6 +351,8 @@ int ensure_cell_arrays(b200coord_ctx* c) {
   return B200COORD_OK;
 }
 
+void needed_all(b200coord_ctx* c);
+
 // no neighbour list: one "cell" per group holding every atom in slot order (NeighborList.cpp:133-140 order)
 int setup_all_pairs(b200coord_ctx* c) {
   DevGrid& g = c->grid;
@@ -357,11 +367,102 @@ int setup_all_pairs(b200coord_ctx* c) {
   CU(c, cudaMemcpyAsync(c->d_cstart.p, starts, m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
   CU(c, cudaMemcpyAsync(c->d_ccount.p, counts, m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
   launch_identity(c->n, c->d_perm.p, c->d_scell.p, c->st);
-  c->stats.kernel_launches += 1;
+  launch_identity(c->n, c->d_inv.p, c->d_scell.p, c->st);
+  needed_all(c);
+  c->stats.kernel_launches += 2;
   CU(c, cudaStreamSynchronize(c->st));  // starts/counts live on this stack frame
   CU_LAST(c, "identity perm");
   c->sorted_valid = true;
   for (int k = 0; k < 3; ++k) c->stats.ncells[k] = 1;
+  return B200COORD_OK;
+}
+
+void needed_all(b200coord_ctx* c) {
+  std::memset(&c->needed, 0, sizeof(c->needed));
+  c->needed.n = 1;
+  c->needed.lo[0] = 0;
+  c->needed.len[0] = c->n;
+  c->needed.total = c->n;
+}
+
+// After a re-sort on a sharded context: the sorted atoms this rank can touch until the next re-sort, as intervals of
+// sorted indices.  Atoms are sorted by (group, cell) with cell = x + y n0 + z n0 n1, so the rank's rows cover a range
+// of z layers; every partner candidate lies within `radius` layers of its row's layer (the stencil), in either group.
+// Conservative (whole layers) and cheap: a handful of 4-byte reads per re-sort.
+int compute_needed(b200coord_ctx* c) {
+  needed_all(c);
+  if (c->cfg.nranks <= 1 || c->row_end <= c->row_begin) return B200COORD_OK;
+  const DevGrid& g = c->grid;
+  const unsigned layer = (unsigned)g.n[0] * (unsigned)g.n[1];
+  const int n2 = g.n[2];
+  if (n2 < 4 || layer == 0) return B200COORD_OK;
+  // cells of the first and last row of each part (GROUPA rows / GROUPB rows) of my range
+  unsigned parts[2][2];
+  int nparts = 0;
+  const unsigned split = c->two_groups ? c->n_a : c->n;
+  if (c->row_begin < std::min(c->row_end, split)) {
+    parts[nparts][0] = c->row_begin;
+    parts[nparts++][1] = std::min(c->row_end, split) - 1;
+  }
+  if (std::max(c->row_begin, split) < c->row_end) {
+    parts[nparts][0] = std::max(c->row_begin, split);
+    parts[nparts++][1] = c->row_end - 1;
+  }
+  for (int q = 0; q < nparts; ++q)
+    for (int e = 0; e < 2; ++e)
+      CU(c, cudaMemcpyAsync(c->h_idx + 2 * q + e, c->d_scell.p + parts[q][e], sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  std::vector<char> need((size_t)n2, 0);
+  const int R = g.radius;
+  for (int q = 0; q < nparts; ++q) {
+    const int zlo = (int)(c->h_idx[2 * q] / layer), zhi = (int)(c->h_idx[2 * q + 1] / layer);
+    for (int z = zlo - R; z <= zhi + R; ++z) {
+      if (g.stencil_pbc) need[(size_t)(((z % n2) + n2) % n2)] = 1;
+      else if (z >= 0 && z < n2) need[(size_t)z] = 1;
+    }
+  }
+  // runs of needed layers -> cell ranges -> sorted-index intervals in every group
+  struct Run { int za, zb; };
+  std::vector<Run> runs;
+  for (int z = 0; z < n2;) {
+    if (!need[(size_t)z]) { ++z; continue; }
+    int zb = z;
+    while (zb + 1 < n2 && need[(size_t)zb + 1]) ++zb;
+    runs.push_back({z, zb});
+    z = zb + 1;
+  }
+  if (runs.size() == 1 && runs[0].za == 0 && runs[0].zb == n2 - 1) return B200COORD_OK;
+  const int ngroups = c->two_groups ? 2 : 1;
+  if (runs.size() * ngroups > 6) return B200COORD_OK;
+  int m = 0;
+  for (int grp = 0; grp < ngroups; ++grp)
+    for (const Run& r : runs) {
+      const size_t first = (size_t)grp * g.ncell + (size_t)r.za * layer;
+      CU(c, cudaMemcpyAsync(c->h_idx + 8 + 2 * m, c->d_cstart.p + first, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+      if (r.zb + 1 < n2) {
+        const size_t past = (size_t)grp * g.ncell + (size_t)(r.zb + 1) * layer;
+        CU(c, cudaMemcpyAsync(c->h_idx + 8 + 2 * m + 1, c->d_cstart.p + past, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+      }
+      ++m;
+    }
+  CU(c, cudaStreamSynchronize(c->st));
+  IdxRanges out;
+  std::memset(&out, 0, sizeof(out));
+  m = 0;
+  for (int grp = 0; grp < ngroups; ++grp)
+    for (const Run& r : runs) {
+      const unsigned group_end = (grp == 0 && c->two_groups) ? c->n_a : c->n;
+      const unsigned lo = c->h_idx[8 + 2 * m];
+      const unsigned hi = (r.zb + 1 < n2) ? c->h_idx[8 + 2 * m + 1] : group_end;
+      ++m;
+      if (hi <= lo) continue;
+      out.lo[out.n] = lo;
+      out.len[out.n] = hi - lo;
+      out.total += hi - lo;
+      out.n++;
+    }
+  if (out.n == 0) return B200COORD_OK;
+  c->needed = out;
   return B200COORD_OK;
 }
 
@@ -492,8 +593,15 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     if (ok) {
       // frozen permutation: continuous coordinates, their float copy, and the largest displacement since the sort
       CU(c, cudaMemsetAsync(c->d_u64.p + 11, 0, sizeof(unsigned long long), c->st));
-      launch_gather_u(true, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_spos.p,
-                      c->d_bpos.p, c->d_lpos.p, c->d_u64.p + 11, c->st);
+      launch_gather_u(true, pos_src_local(d_pos), c->d_perm.p, c->d_abs.p, c->needed, c->d_wpos.p, c->d_braw.p, c->dpbc,
+                      c->d_spos.p, c->d_bpos.p, c->d_lpos.p, c->d_u64.p + 11, c->st);
+      if (c->comm) {
+        // every rank looked at the atoms it needs; all must take the same decision (the permutation is shared):
+        // the largest displacement anywhere (non-negative doubles order like their bit patterns)
+        NcclApi& api = nccl_api();
+        ncclResult_t r = api.AllReduce(c->d_u64.p + 11, c->d_u64.p + 11, 1, ncclUint64, ncclMax, c->comm, c->st);
+        if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce(displacement): ") + api.GetErrorString(r));
+      }
       CU(c, cudaMemcpyAsync(c->h_u64 + 2, c->d_u64.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
       c->stats.kernel_launches += 1;
@@ -523,8 +631,15 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   if (rc) return rc;
   launch_sort(d_pos, c->n, c->n_a, c->two_groups ? 2 : 1, c->grid, c->d_cell_of_slot.p, c->d_ccount.p, c->d_cstart.p,
               c->d_cursor.p, c->d_tmp.p, c->d_perm.p, c->d_scell.p, c->d_bsum.p, c->st);
-  c->stats.kernel_launches += 4;
+  launch_invert_perm(c->d_perm.p, c->n, c->d_inv.p, c->st);
+  c->stats.kernel_launches += 5;
   c->sorted_valid = true;
+  if (mode == B200COORD_NL_CLASSIC) {
+    rc = compute_needed(c);
+    if (rc) return rc;
+  } else {
+    needed_all(c);
+  }
   c->sq_valid = false;  // new permutation
   c->stype_valid = false;
   c->super_valid = false;
@@ -641,14 +756,19 @@ int combine_ranks(b200coord_ctx* c) {
 // the whole per-step device pipeline on c->st; d_pos device positions, result left in c->d_out
 // out: where the 3n derivatives go (null = c->d_out; the 10 tail doubles always land in c->d_out);
 // [slot_lo, slot_lo+slot_cnt): the slots of the derivative array the caller is going to read
+// d_pos: the whole position array on this device, or null on a step of the distributed engine that keeps its list and
+// pulls positions from the owners' slice buffers (`src`)
 int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, unsigned slot_lo = 0u,
-               unsigned slot_cnt = 0xffffffffu) {
+               unsigned slot_cnt = 0xffffffffu, const PosSrc* src_in = nullptr) {
+  const PosSrc src = src_in ? *src_in : pos_src_local(d_pos);
   if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
   if (c->dsw.type == B200COORD_PAIR_DHENERGY && !c->have_charges)
     return fail(c, B200COORD_ERR_STATE, "b200coord_set_charges must be called before calculate (DHENERGY)");
   if (c->dsw.type == B200COORD_PAIR_GHBFIX && !c->have_types)
     return fail(c, B200COORD_ERR_STATE, "b200coord_set_types must be called before calculate (GHBFIX)");
   const bool need_rebuild = !c->list_valid || (c->cfg.nl_mode != B200COORD_NL_NONE && c->invalidate);
+  if (!d_pos && (need_rebuild || c->cfg.style == B200COORD_STYLE_PAIR))
+    return fail(c, B200COORD_ERR_STATE, "internal: a rebuild step needs the whole position array");
   if (need_rebuild) {
     int rc = rebuild(c, d_pos);
     if (rc) return rc;
@@ -680,12 +800,14 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     const bool classic = (c->cfg.nl_mode == B200COORD_NL_CLASSIC);
     // box changed since the sort: the continuous coordinates (and the images) no longer mean anything
     const bool u_now = classic && c->u_mode && c->box_epoch == c->sort_box_epoch;
+    if (!d_pos && !(u_now && !need_rebuild))
+      return fail(c, B200COORD_ERR_STATE, "internal: this step needs the whole position array");
     if (classic) {
       if (need_rebuild) {  // rebuild() left records, displacement origin and a zero displacement behind
         CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));
       } else if (u_now) {
         CU(c, cudaMemsetAsync(c->d_u64.p + 10, 0, sizeof(unsigned long long), c->st));
-        launch_gather_u(false, d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_spos.p,
+        launch_gather_u(false, src, c->d_perm.p, c->d_abs.p, c->needed, c->d_wpos.p, c->d_braw.p, c->dpbc, c->d_spos.p,
                         c->d_bpos.p, nullptr, c->d_u64.p + 10, c->st);
       } else if (c->u_mode) {  // far parts are visited anyway (force_far): no displacement needed
         launch_gather(d_pos, c->d_perm.p, c->d_abs.p, c->n, c->d_spos.p, c->st);
@@ -741,7 +863,7 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.force_far = (c->box_epoch != c->build_box_epoch) ? 1 : 0;
     a.idx_mask = c->img_list ? kSuperIndexMask : 0xffffffffu;
     a.row_meta = c->d_meta.p;
-    a.pos = d_pos;
+    a.pos = src;
     a.executed = c->d_u64.p + 12;
     // image sweep: valid while a listed pair cannot have a second image as close as the stored one, i.e. while
     // NL_CUTOFF + 2 * displacement < half the smallest box height (any lattice vector is at least that long)
@@ -771,12 +893,9 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.ccount = c->d_ccount.p;
     a.grid = c->grid;
     double* rows_now = c->d_sderiv.p;
-    if (c->peer_mode) {
+    if (c->peer_mode) {  // rows stay where they are computed; the un-sort of every rank pulls the ones it returns
       c->parity ^= 1u;
       rows_now = c->peer_rows[c->parity][c->cfg.rank];
-      a.npeers = 0;
-      for (int r = 0; r < c->cfg.nranks; ++r)
-        if (r != c->cfg.rank) a.peers[a.npeers++] = c->peer_rows[c->parity][r];
     }
     a.sderiv = rows_now;
     a.evals = c->d_u64.p + 1;
@@ -820,8 +939,13 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     if (rc) return rc;
   }
   if (c->cfg.style != B200COORD_STYLE_PAIR) {
-    launch_unsort_derivs(c->peer_mode ? c->peer_rows[c->parity][c->cfg.rank] : c->d_sderiv.p, c->d_perm.p, c->n,
-                         out ? out : c->d_out.p, slot_lo, slot_cnt, c->st);
+    RowSrc rows;
+    for (int r = 0; r < 8; ++r)
+      rows.base[r] = (c->peer_mode && r < c->cfg.nranks) ? c->peer_rows[c->parity][r] : c->d_sderiv.p;
+    rows.chunk = c->row_chunk ? c->row_chunk : 1u;
+    const unsigned lo = std::min(slot_lo, c->n);
+    const unsigned cnt = std::min(slot_cnt, c->n - lo);
+    launch_unsort_pull(rows, c->d_inv.p, out ? out : c->d_out.p, lo, cnt, c->st);
     c->stats.kernel_launches += 1;
   }
   CU(c, cudaMemcpyAsync(c->h_u64 + 1, c->d_u64.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
@@ -1030,6 +1154,8 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   CREATE_CU(c->d_u64.reserve(16));
   CREATE_CU(c->d_abs.reserve(n));
   CREATE_CU(c->d_perm.reserve(n));
+  CREATE_CU(c->d_inv.reserve(n));
+  CREATE_CU(cudaHostAlloc((void**)&c->h_idx, 32 * sizeof(unsigned), cudaHostAllocDefault));
   CREATE_CU(c->d_scell.reserve(n));
   CREATE_CU(c->d_cell_of_slot.reserve(n));
   CREATE_CU(c->d_tmp.reserve(n));
@@ -1053,6 +1179,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_IMG_VARIANT")) c->img_variant = std::atoi(e);
+  needed_all(c);
   *out = c;
   return B200COORD_OK;
 }
@@ -1100,7 +1227,15 @@ void b200coord_destroy(b200coord_ctx* c) {
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
         if (r != c->cfg.rank && c->peer_rows[par][r]) cudaIpcCloseMemHandle(c->peer_rows[par][r]);
+  if (c->peer_mode)
+    for (int par = 0; par < 2; ++par)
+      for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
+        if (r != c->cfg.rank && c->peer_pos[par][r]) cudaIpcCloseMemHandle(c->peer_pos[par][r]);
   c->d_sderiv_b.release();
+  c->d_pslice[0].release();
+  c->d_pslice[1].release();
+  c->d_inv.release();
+  if (c->h_idx) cudaFreeHost(c->h_idx);
   if (c->h_capinfo) cudaFreeHost(c->h_capinfo);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_u64) cudaFreeHost(c->h_u64);
@@ -1238,23 +1373,52 @@ int b200coord_my_slice(const b200coord_ctx* c, unsigned* slot_begin, unsigned* s
   return B200COORD_OK;
 }
 
+// one barrier over the ranks on the context's stream (a one-element all-reduce)
+static int rank_barrier(b200coord_ctx* c) {
+  NcclApi& api = nccl_api();
+  ncclResult_t r = api.AllReduce(c->d_small.p + 24, c->d_small.p + 24, 1, ncclDouble, ncclSum, c->comm, c->st);
+  if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce(barrier): ") + api.GetErrorString(r));
+  return B200COORD_OK;
+}
+
+// does the coming step keep its list AND its continuous coordinates?  Then a rank only needs the positions of the
+// atoms around its rows, and pulls them from the owners' slice buffers over NVLink instead of receiving everything.
+static bool step_can_pull(const b200coord_ctx* c) {
+  const bool need_rebuild = !c->list_valid || (c->cfg.nl_mode != B200COORD_NL_NONE && c->invalidate);
+  return c->peer_mode && c->comm && !need_rebuild && c->cfg.style != B200COORD_STYLE_PAIR &&
+         c->cfg.nl_mode == B200COORD_NL_CLASSIC && c->u_mode && c->box_epoch == c->sort_box_epoch;
+}
+
 int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, double* value, double* deriv_slice,
                                     double* virial) {
   if (!c || !pos_slice || !value || !deriv_slice || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
   if (c->cfg.nranks > 1 && !c->comm) return fail(c, B200COORD_ERR_STATE, "b200coord_comm_init has not been called");
   CU(c, cudaSetDevice(c->device));
   const size_t off = 3 * (size_t)c->slot_begin, cnt = 3 * (size_t)c->slot_count;
+  const bool sliced = (c->cfg.style != B200COORD_STYLE_PAIR);
+  int rc;
   CU(c, cudaEventRecord(c->ev[0], c->st));
-  if (cnt) CU(c, cudaMemcpyAsync(c->d_pos.p + off, pos_slice, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->st));
-  CU(c, cudaEventRecord(c->ev[1], c->st));
-  if (c->comm) {  // positions of all ranks over NVLink (in place: every rank's slice sits at rank*chunk)
-    NcclApi& api = nccl_api();
-    ncclResult_t r = api.AllGather(c->d_pos.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_pos.p, (size_t)3 * c->row_chunk,
-                                   ncclDouble, c->comm, c->st);
-    if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
+  if (step_can_pull(c)) {
+    c->pos_parity ^= 1u;
+    if (cnt) CU(c, cudaMemcpyAsync(c->d_pslice[c->pos_parity].p, pos_slice, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaEventRecord(c->ev[1], c->st));
+    rc = rank_barrier(c);  // every rank's slice is in place before anybody gathers from it
+    if (rc) return rc;
+    PosSrc src;
+    for (int r = 0; r < 8; ++r) src.base[r] = c->peer_pos[c->pos_parity][r < c->cfg.nranks ? r : 0];
+    src.chunk = c->row_chunk ? c->row_chunk : 1u;
+    rc = run_device(c, nullptr, nullptr, c->slot_begin, c->slot_count, &src);
+  } else {
+    if (cnt) CU(c, cudaMemcpyAsync(c->d_pos.p + off, pos_slice, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaEventRecord(c->ev[1], c->st));
+    if (c->comm) {  // positions of all ranks over NVLink (in place: every rank's slice sits at rank*chunk)
+      NcclApi& api = nccl_api();
+      ncclResult_t r = api.AllGather(c->d_pos.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_pos.p, (size_t)3 * c->row_chunk,
+                                     ncclDouble, c->comm, c->st);
+      if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
+    }
+    rc = run_device(c, c->d_pos.p, nullptr, sliced ? c->slot_begin : 0u, sliced ? c->slot_count : 0xffffffffu);
   }
-  int rc = run_device(c, c->d_pos.p, nullptr, c->cfg.style != B200COORD_STYLE_PAIR ? c->slot_begin : 0u,
-                      c->cfg.style != B200COORD_STYLE_PAIR ? c->slot_count : 0xffffffffu);
   if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[6], c->st));
   if (cnt) CU(c, cudaMemcpyAsync(deriv_slice, c->d_out.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->st));
@@ -1265,6 +1429,20 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
   *value = c->h_small[9];
   refresh_stats(c);
+  return B200COORD_OK;
+}
+
+int b200coord_enqueue_device_distributed(b200coord_ctx* c, const double* d_pos, double* d_out_slice) {
+  if (!c || !d_pos || !d_out_slice) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (c->cfg.nranks > 1 && !c->comm) return fail(c, B200COORD_ERR_STATE, "b200coord_comm_init has not been called");
+  if (c->cfg.style == B200COORD_STYLE_PAIR) return fail(c, B200COORD_ERR_INVALID, "PAIR style returns whole arrays: use b200coord_enqueue_device");
+  CU(c, cudaSetDevice(c->device));
+  // the un-sort writes slots [slot_begin, +slot_count) of an array that starts slot_begin slots before the caller's
+  double* base = d_out_slice - 3 * (size_t)c->slot_begin;
+  int rc = run_device(c, d_pos, base, c->slot_begin, c->slot_count);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(d_out_slice + 3 * (size_t)c->slot_count, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10,
+                        cudaMemcpyDeviceToDevice, c->st));
   return B200COORD_OK;
 }
 
@@ -1446,16 +1624,24 @@ int b200coord_comm_init(b200coord_ctx* c, const char id[B200COORD_UNIQUE_ID_BYTE
 
 int b200coord_peer_export(b200coord_ctx* c, char handle[B200COORD_PEER_HANDLE_BYTES]) {
   if (!c || !handle) return fail(c, B200COORD_ERR_INVALID, "null argument");
-  static_assert(2 * sizeof(cudaIpcMemHandle_t) == B200COORD_PEER_HANDLE_BYTES, "IPC handle size");
+  static_assert(4 * sizeof(cudaIpcMemHandle_t) == B200COORD_PEER_HANDLE_BYTES, "IPC handle size");
   if (c->cfg.style == B200COORD_STYLE_PAIR) return fail(c, B200COORD_ERR_INVALID, "PAIR style has no row exchange");
   CU(c, cudaSetDevice(c->device));
   const size_t padded = (size_t)3 * c->row_chunk * (size_t)c->cfg.nranks;
   CU(c, c->d_sderiv_b.reserve(padded));
   CU(c, cudaMemsetAsync(c->d_sderiv_b.p, 0, sizeof(double) * padded, c->st));
   CU(c, cudaStreamSynchronize(c->st));
-  cudaIpcMemHandle_t h[2];
+  // the two slice buffers of this rank's positions (3 * row_chunk doubles each)
+  for (int par = 0; par < 2; ++par) {
+    CU(c, c->d_pslice[par].reserve((size_t)3 * c->row_chunk + 3));
+    CU(c, cudaMemsetAsync(c->d_pslice[par].p, 0, sizeof(double) * ((size_t)3 * c->row_chunk + 3), c->st));
+  }
+  CU(c, cudaStreamSynchronize(c->st));
+  cudaIpcMemHandle_t h[4];
   CU(c, cudaIpcGetMemHandle(&h[0], c->d_sderiv.p));
   CU(c, cudaIpcGetMemHandle(&h[1], c->d_sderiv_b.p));
+  CU(c, cudaIpcGetMemHandle(&h[2], c->d_pslice[0].p));
+  CU(c, cudaIpcGetMemHandle(&h[3], c->d_pslice[1].p));
   std::memcpy(handle, h, sizeof(h));
   return B200COORD_OK;
 }
@@ -1470,14 +1656,19 @@ int b200coord_peer_attach(b200coord_ctx* c, const char* all) {
     if (r == c->cfg.rank) {
       c->peer_rows[0][r] = c->d_sderiv.p;
       c->peer_rows[1][r] = c->d_sderiv_b.p;
+      c->peer_pos[0][r] = c->d_pslice[0].p;
+      c->peer_pos[1][r] = c->d_pslice[1].p;
       continue;
     }
-    cudaIpcMemHandle_t h[2];
+    cudaIpcMemHandle_t h[4];
     std::memcpy(h, all + (size_t)r * B200COORD_PEER_HANDLE_BYTES, sizeof(h));
     for (int par = 0; par < 2; ++par) {
       void* ptr = nullptr;
       CU(c, cudaIpcOpenMemHandle(&ptr, h[par], cudaIpcMemLazyEnablePeerAccess));
       c->peer_rows[par][r] = static_cast<double*>(ptr);
+      ptr = nullptr;
+      CU(c, cudaIpcOpenMemHandle(&ptr, h[2 + par], cudaIpcMemLazyEnablePeerAccess));
+      c->peer_pos[par][r] = static_cast<double*>(ptr);
     }
   }
   c->peer_mode = true;

@@ -79,6 +79,36 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, unsigned lan
   return x - v;
 }
 
+// ---- where things live when the atoms are spread over several GPUs of one node (NVLink peer memory)
+// The caller's positions: slot s is at base[s / chunk] + 3 * (s % chunk).  One rank: base[0] = the whole array and
+// chunk = 0xffffffff.  Several ranks (b200coord_calculate_distributed): base[r] = rank r's slice buffer, mapped into
+// this process, and a gather PULLS what it needs from the owners.
+struct PosSrc {
+  const double* base[8];
+  unsigned chunk;
+};
+__device__ __forceinline__ const double* pos_at(const PosSrc& p, uint32_t slot) {
+  const unsigned o = slot / p.chunk;
+  return p.base[o] + 3 * (size_t)(slot - o * p.chunk);
+}
+static inline PosSrc pos_src_local(const double* pos) {
+  PosSrc p;
+  for (int i = 0; i < 8; ++i) p.base[i] = pos;
+  p.chunk = 0xffffffffu;
+  return p;
+}
+// Derivative rows (3 doubles per sorted atom, global sorted index): row k is in base[k / chunk].
+struct RowSrc {
+  const double* base[8];
+  unsigned chunk;
+};
+// up to six intervals of sorted indices: the atoms a rank needs (its own rows and every possible partner of them)
+struct IdxRanges {
+  unsigned n;
+  unsigned lo[6], len[6];
+  unsigned total;
+};
+
 // ---- build
 void launch_bbox(const double* pos, unsigned n, double* out6, unsigned long long* scratch6, cudaStream_t st);
 void launch_sort(const double* pos, unsigned n, unsigned n_a, int ngroups, const DevGrid& g, uint32_t* cell_of_slot,
@@ -102,9 +132,11 @@ void launch_nl_rows(bool fill, const SPos* spos, const uint32_t* scell, const ui
 void launch_sort_init(const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n, const DevGrid& g,
                       const DevPbc& box, bool use_wrapped, float4* lpos, double* wpos, double* braw, SPos* spos, double* ubuild,
                       cudaStream_t st);
-void launch_gather_u(bool build, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+void launch_gather_u(bool build, const PosSrc& pos, const uint32_t* perm, const uint32_t* abs_index, const IdxRanges& rng,
                      const double* wpos, const double* braw, const DevPbc& pbc, SPos* spos, double* ubuild, float4* lpos,
                      unsigned long long* disp2, cudaStream_t st);
+// inv[perm[k]] = k
+void launch_invert_perm(const uint32_t* perm, unsigned n, uint32_t* inv, cudaStream_t st);
 void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
                       const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st);
 // ---- super-list: a list with cutoff NL_CUTOFF + delta whose rows are the candidate sets of the following rebuilds
@@ -155,7 +187,7 @@ struct SweepArgs {
   const uint32_t* nbr;
   uint32_t idx_mask;       // sorted index of an entry = entry & idx_mask (image-mode lists keep the image above bit 26)
   const uint4* row_meta;   // image mode: {row start / 4, near count, far offset, far count} per row (k_pack_meta)
-  const double* pos;       // the caller's positions (slot order): exact boundary patch
+  PosSrc pos;              // the caller's positions (slot order): exact boundary patch
   double img_disp2_max;    // image mode is valid while the squared displacement since the rebuild is below this
   unsigned rows_per_block; // image mode: both kernels use this block shape (0: the kernel picks)
   // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)
@@ -184,9 +216,6 @@ struct SweepArgs {
   // box and switch parameters in global memory, for the out-of-line row patch (sweep_math.cuh: row_fixup_*)
   const DevPbc* pbc_g;
   const DevSwitch* sw_g;
-  // fused exchange: the same row is also stored into the row buffers of the other ranks (NVLink peer memory)
-  int npeers;
-  double* peers[7];
 };
 
 // returns the number of blocks launched (= number of partial records), or -1 for an unsupported switch
@@ -207,9 +236,10 @@ int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DH
 // sum the per-block partials in a fixed order and write virial (9) + value behind the 3n derivatives;
 // weight = 0.5 when every pair was visited from both sides (SingleList), 1 otherwise
 void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail /*[10]*/, cudaStream_t st);
-// out[3*slot+c] = sderiv[3*k+c] for the sorted rows k in [0,n) whose slot lies in [slot_lo, slot_lo+slot_cnt)
-void launch_unsort_derivs(const double* sderiv, const uint32_t* perm /*sorted -> slot*/, unsigned n, double* out,
-                          unsigned slot_lo, unsigned slot_cnt /*slots to write*/, cudaStream_t st);
+// out[3*slot+c] = row inv[slot], component c, for the slots [slot_lo, slot_lo+slot_cnt): every rank PULLS the rows of its
+// own atoms from whoever swept them (NVLink peer loads; one rank: a local gather)
+void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv /*slot -> sorted*/, double* out, unsigned slot_lo,
+                        unsigned slot_cnt, cudaStream_t st);
 
 // ---- util
 double measure_dfma_tflops(cudaStream_t st, int sm_count, int reps);

@@ -382,15 +382,29 @@ __global__ void k_sort_init(const double* __restrict__ pos, const uint32_t* __re
 // !BUILD: the largest squared displacement since the list was built (far-part skip, validity of the images).
 template <int PBC, bool BUILD>
 __global__ void __launch_bounds__(256)
-    k_gather_u(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ abs_index,
-               unsigned n, const double* __restrict__ wpos, const double* __restrict__ braw, DevPbc pbc,
+    k_gather_u(PosSrc pos, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ abs_index, IdxRanges rng,
+               const double* __restrict__ wpos, const double* __restrict__ braw, DevPbc pbc,
                SPos* __restrict__ spos, double* __restrict__ ubuild, float4* __restrict__ lpos,
                unsigned long long* __restrict__ disp2) {
-  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   double d2 = 0.0;
-  if (k < n) {
+  if (t < rng.total) {
+    unsigned k = 0, rem = t;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {  // thread t -> the t-th sorted index of the intervals
+      if (!found && q < (int)rng.n) {
+        if (rem < rng.len[q]) {
+          k = rng.lo[q] + rem;
+          found = true;
+        } else {
+          rem -= rng.len[q];
+        }
+      }
+    }
     const uint32_t slot = perm[k];
-    const double qx = pos[3 * (size_t)slot], qy = pos[3 * (size_t)slot + 1], qz = pos[3 * (size_t)slot + 2];
+    const double* __restrict__ q3 = pos_at(pos, slot);
+    const double qx = q3[0], qy = q3[1], qz = q3[2];
     double dx = qx - braw[3 * (size_t)k], dy = qy - braw[3 * (size_t)k + 1], dz = qz - braw[3 * (size_t)k + 2];
     min_image_fast<PBC>(pbc, dx, dy, dz);
     const double wx = wpos[3 * (size_t)k] + dx, wy = wpos[3 * (size_t)k + 1] + dy, wz = wpos[3 * (size_t)k + 2] + dz;
@@ -882,12 +896,12 @@ void launch_sort_init(const double* pos, const uint32_t* perm, const uint32_t* a
     k_sort_init<<<(n + 255) / 256, 256, 0, st>>>(pos, perm, abs_index, n, g, box, use_wrapped ? 1 : 0, lpos, wpos, braw, spos,
                                                   ubuild);
 }
-void launch_gather_u(bool build, const double* pos, const uint32_t* perm, const uint32_t* abs_index, unsigned n,
+void launch_gather_u(bool build, const PosSrc& pos, const uint32_t* perm, const uint32_t* abs_index, const IdxRanges& rng,
                      const double* wpos, const double* braw, const DevPbc& pbc, SPos* spos, double* ubuild, float4* lpos,
                      unsigned long long* disp2, cudaStream_t st) {
-  if (!n) return;
-  const unsigned blocks = (n + 255) / 256;
-#define B200_GU(P, B) k_gather_u<P, B><<<blocks, 256, 0, st>>>(pos, perm, abs_index, n, wpos, braw, pbc, spos, ubuild, lpos, disp2)
+  if (!rng.total) return;
+  const unsigned blocks = (rng.total + 255) / 256;
+#define B200_GU(P, B) k_gather_u<P, B><<<blocks, 256, 0, st>>>(pos, perm, abs_index, rng, wpos, braw, pbc, spos, ubuild, lpos, disp2)
   if (build) {
     switch (pbc.type) {
       case 0: B200_GU(0, true); break;
@@ -903,6 +917,14 @@ void launch_gather_u(bool build, const double* pos, const uint32_t* perm, const 
   }
 #undef B200_GU
 }
+__global__ void k_invert_perm(const uint32_t* __restrict__ perm, unsigned n, uint32_t* __restrict__ inv) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) inv[perm[k]] = k;
+}
+void launch_invert_perm(const uint32_t* perm, unsigned n, uint32_t* inv, cudaStream_t st) {
+  if (n) k_invert_perm<<<(n + 255) / 256, 256, 0, st>>>(perm, n, inv);
+}
+
 void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
                       const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st) {
   cudaMemsetAsync(listed, 0, sizeof(unsigned long long), st);

@@ -104,17 +104,20 @@ __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ pa
   }
 }
 
-// only the slots [slot_lo, slot_lo + slot_cnt) are written (a rank that returns just its slice to the host)
-__global__ void k_unsort_derivs(const double* __restrict__ sderiv, const uint32_t* __restrict__ perm, unsigned n,
-                                double* __restrict__ out, unsigned slot_lo, unsigned slot_cnt) {
-  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t slot = perm[k];
-  if (slot - slot_lo >= slot_cnt) return;
+// Derivatives back in the caller's order: slot s <- row inv[s].  With several ranks the row lives in the buffer of the
+// rank that swept it (rows.base[owner], peer memory over NVLink): every rank pulls exactly the rows of the atoms it
+// returns, 24 bytes each, instead of every rank receiving every row.
+__global__ void __launch_bounds__(256)
+    k_unsort_pull(RowSrc rows, const uint32_t* __restrict__ inv, double* __restrict__ out, unsigned slot_lo, unsigned slot_cnt) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= slot_cnt) return;
+  const unsigned slot = slot_lo + t;
+  const uint32_t k = inv[slot];
+  const double* __restrict__ src = rows.base[k / rows.chunk] + 3 * (size_t)k;
   const size_t o = 3 * (size_t)slot;
-  out[o] = sderiv[3 * (size_t)k];
-  out[o + 1] = sderiv[3 * (size_t)k + 1];
-  out[o + 2] = sderiv[3 * (size_t)k + 2];
+  out[o] = src[0];
+  out[o + 1] = src[1];
+  out[o + 2] = src[2];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,9 +179,9 @@ void launch_finalize(const double* partials, int nblocks, double weight, double*
   k_finalize<<<1, 1024, 0, st>>>(partials, nblocks, weight, out_tail);
 }
 
-void launch_unsort_derivs(const double* sderiv, const uint32_t* perm, unsigned n, double* out, unsigned slot_lo,
-                          unsigned slot_cnt, cudaStream_t st) {
-  if (n) k_unsort_derivs<<<(n + 255) / 256, 256, 0, st>>>(sderiv, perm, n, out, slot_lo, slot_cnt);
+void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv, double* out, unsigned slot_lo, unsigned slot_cnt,
+                        cudaStream_t st) {
+  if (slot_cnt) k_unsort_pull<<<(slot_cnt + 255) / 256, 256, 0, st>>>(rows, inv, out, slot_lo, slot_cnt);
 }
 
 }  // namespace b200

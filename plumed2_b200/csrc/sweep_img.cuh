@@ -97,7 +97,7 @@ struct RowFixImg {
 };
 template <int K>
 __device__ __noinline__ RowFixImg row_fixup_img(const DevPbc* __restrict__ pbc_g, const DevSwitch* __restrict__ sw_g,
-                                                const SPos* __restrict__ spos, const double* __restrict__ pos,
+                                                const SPos* __restrict__ spos, PosSrc pos,
                                                 const uint32_t* __restrict__ nbr, uint4 m, bool far_on,
                                                 const double* shifts /*shared*/, unsigned k, unsigned lane, int two_groups,
                                                 bool row_is_b, bool acc) {
@@ -119,8 +119,8 @@ __device__ __noinline__ RowFixImg row_fixup_img(const DevPbc* __restrict__ pbc_g
     double s, df;
     eval_switch<K>(sw, r2, s, df);  // what the hot loop added (same formulas; rounding differences are 1e-16)
     const bool flip = two_groups ? row_is_b : (pi.slot > pj.slot);
-    const double* ri = pos + 3 * (size_t)pi.slot;
-    const double* rj = pos + 3 * (size_t)pj.slot;
+    const double* ri = pos_at(pos, pi.slot);
+    const double* rj = pos_at(pos, pj.slot);
     const ExactPair o = exact_pair<K>(*pbc_g, sw, ri[0], ri[1], ri[2], rj[0], rj[1], rj[2], flip);
     // the exact vector in this row's orientation (from i to the image of j), g = df * e
     const double sg = flip ? -1.0 : 1.0;
@@ -309,8 +309,14 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
     const unsigned long long wb = (unsigned long long)__double_as_longlong(cur.pb.w);
     const double qa = cur.qa, qb = cur.qb;
     const uint32_t ta = cur.ta, tb = cur.tb;
-    request(nxt);  // records of the next trip (L1/L2 gather, one trip ahead)
-    refill(cur);   // entries of the trip after next (HBM stream, two trips ahead)
+    // The issue side of the pipeline -- records of the next trip (L1/L2 gather, one trip ahead), entries of the trip
+    // after next (HBM stream, two trips ahead) -- is ~35 integer / load instructions that depend on nothing computed
+    // here.  It is placed INSIDE the block that evaluates the switching function, so that ptxas can interleave it
+    // with the two dependent FP64 chains (8 cycles per link) instead of leaving those gaps to the other warps.
+    auto issue_side = [&]() {
+      request(nxt);
+      refill(cur);
+    };
     const unsigned rem = m & kRem;
     const bool va = lane < rem, vb = lane + 32u < rem;
     // everything after the vector: same for both flavours of the trip
@@ -319,8 +325,12 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       const double ra = fma(az, az, fma(ay, ay, ax * ax));
       const double rb = fma(bz, bz, fma(by, by, bx * bx));
       if (m & kFar) {  // far part: every pair of the trip beyond D_MAX -> nothing to add
-        if (__all_sync(0xffffffffu, (!va || ra > a.far_skip2) && (!vb || rb > a.far_skip2))) return;
+        if (__all_sync(0xffffffffu, (!va || ra > a.far_skip2) && (!vb || rb > a.far_skip2))) {
+          issue_side();
+          return;
+        }
       }
+      issue_side();
       double sa, dfa, sb, dfb;
       img_eval<K>(sw, ra, va, sa, dfa, nin);
       img_eval<K>(sw, rb, vb, sb, dfb, nin);
@@ -396,17 +406,6 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       a.sderiv[3 * (size_t)kf] += hx;
       a.sderiv[3 * (size_t)kf + 1] += hy;
       a.sderiv[3 * (size_t)kf + 2] += hz;
-    }
-  }
-  if (a.npeers) {
-    // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
-    // them over NVLink with coalesced stores while other blocks keep computing
-    __syncthreads();
-    if ((int)wid < a.npeers && last > first) {
-      double* __restrict__ q = a.peers[wid] + 3 * (size_t)first;
-      const double* __restrict__ mine = a.sderiv + 3 * (size_t)first;
-      const unsigned m = 3u * (last - first);
-      for (unsigned t = lane; t < m; t += 32) q[t] = mine[t];
     }
   }
   // ---- block epilogue: one partial record {value, c[9]}

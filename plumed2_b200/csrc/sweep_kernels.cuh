@@ -159,17 +159,6 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       a.sderiv[3 * (size_t)kf + 2] += gz;
     }
   }
-  if (a.npeers) {
-    // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
-    // them over NVLink with coalesced stores while other blocks keep computing
-    __syncthreads();  // the rows written above by this block are visible to the whole block now
-    if ((int)wid < a.npeers && last > first) {
-      double* __restrict__ q = a.peers[wid] + 3 * (size_t)first;
-      const double* __restrict__ mine = a.sderiv + 3 * (size_t)first;
-      const unsigned m = 3u * (last - first);
-      for (unsigned t = lane; t < m; t += 32) q[t] = mine[t];
-    }
-  }
   if (ACC)
     block_store_partials(acc, evals, a.partials, a.evals);
   else if (lane == 0 && evals)
@@ -230,17 +219,6 @@ __global__ void __launch_bounds__(kSweepThreads)
     }
   }
   if (lane == 0 && evals) atomicAdd(a.executed, evals);
-  if (a.npeers) {
-    // fused exchange: the block's rows are contiguous in every rank's row buffer -> one warp per peer streams
-    // them over NVLink with coalesced stores while other blocks keep computing
-    __syncthreads();  // the rows written above by this block are visible to the whole block now
-    if ((int)wid < a.npeers && last > first) {
-      double* __restrict__ q = a.peers[wid] + 3 * (size_t)first;
-      const double* __restrict__ mine = a.sderiv + 3 * (size_t)first;
-      const unsigned m = 3u * (last - first);
-      for (unsigned t = lane; t < m; t += 32) q[t] = mine[t];
-    }
-  }
   if (ACC)
     block_store_partials(acc, evals, a.partials, a.evals);
   else if (lane == 0 && evals)

@@ -526,7 +526,7 @@ __device__ __forceinline__ void fix_one(const DevPbc& pbc, const DevSwitch& sw, 
 }
 template <int K, int PBC>
 __device__ __noinline__ RowFix row_fixup_list(const DevPbc* __restrict__ pbc_g, const DevSwitch* __restrict__ sw_g,
-                                              const SPos* __restrict__ spos, const double* __restrict__ pos,
+                                              const SPos* __restrict__ spos, PosSrc pos,
                                               uint32_t idx_mask, const uint32_t* __restrict__ row, unsigned cnt,
                                               const uint32_t* __restrict__ far_row, unsigned far_cnt, unsigned k,
                                               unsigned lane, int two_groups, bool row_is_b) {
@@ -534,7 +534,7 @@ __device__ __noinline__ RowFix row_fixup_list(const DevPbc* __restrict__ pbc_g, 
   const SPos pi = spos[k];
   for (unsigned e = lane; e < cnt + far_cnt; e += 32) {
     const SPos pj = spos[(e < cnt ? row[e] : far_row[e - cnt]) & idx_mask];
-    fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, pos + 3 * (size_t)pi.slot, pos + 3 * (size_t)pj.slot,
+    fix_one<K, PBC>(*pbc_g, *sw_g, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, pos_at(pos, pi.slot), pos_at(pos, pj.slot),
                     two_groups ? row_is_b : (pi.slot > pj.slot), f);
   }
   return f;
