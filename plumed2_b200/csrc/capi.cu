@@ -187,6 +187,13 @@ struct b200coord_ctx {
   double* peer_pos[2][8] = {{nullptr}};
   unsigned pos_parity = 0;
   DevBuf<uint32_t> d_inv;             // slot -> sorted index (inverse of d_perm)
+  // cell-tile sweep (NLISTCELLS / no list): work list of (cell, row chunk) items, rebuilt with the sort
+  DevBuf<unsigned char> d_tilework;
+  DevBuf<uint32_t> d_tilecnt;
+  DevBuf<unsigned long long> d_tilestart;
+  unsigned tile_bound_a = 0, tile_bound_b = 0, tile_nseg = 0;
+  bool tile_ok = false;               // the current sort has a work list
+  bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
   IdxRanges needed;                   // sorted indices this rank's rows can touch (its rows + every possible partner)
   unsigned* h_idx = nullptr;          // pinned scratch for compute_needed
   b200coord_stats stats;
@@ -352,6 +359,7 @@ int ensure_cell_arrays(b200coord_ctx* c) {
 }
 
 void needed_all(b200coord_ctx* c);
+int build_tile_work(b200coord_ctx* c);
 
 // no neighbour list: one "cell" per group holding every atom in slot order (NeighborList.cpp:133-140 order)
 int setup_all_pairs(b200coord_ctx* c) {
@@ -373,6 +381,8 @@ int setup_all_pairs(b200coord_ctx* c) {
   CU(c, cudaStreamSynchronize(c->st));  // starts/counts live on this stack frame
   CU_LAST(c, "identity perm");
   c->sorted_valid = true;
+  rc = build_tile_work(c);
+  if (rc) return rc;
   for (int k = 0; k < 3; ++k) c->stats.ncells[k] = 1;
   return B200COORD_OK;
 }
@@ -463,6 +473,33 @@ int compute_needed(b200coord_ctx* c) {
     }
   if (out.n == 0) return B200COORD_OK;
   c->needed = out;
+  return B200COORD_OK;
+}
+
+// work list of the cell-tile sweep for the current sort (cells / no list, FP64, untyped pairings)
+int build_tile_work(b200coord_ctx* c) {
+  c->tile_ok = false;
+  if (!c->tile_on || c->cfg.precision != B200COORD_FP64 || !sweep_tile_supports(c->dsw.type)) return B200COORD_OK;
+  const unsigned ngroups = c->two_groups ? 2u : 1u;
+  const unsigned nseg = ngroups * (unsigned)c->grid.ncell;
+  const unsigned rows = c->row_end - c->row_begin;
+  if (!rows) return B200COORD_OK;
+  const unsigned rpi = tile_rows_per_item(rows);
+  const unsigned split = c->two_groups ? c->n_a : c->n;
+  const unsigned rows_a = std::min(c->row_end, split) > c->row_begin ? std::min(c->row_end, split) - c->row_begin : 0u;
+  const unsigned rows_b = rows - rows_a;
+  c->tile_bound_a = rows_a ? tile_items_bound(rows_a, (unsigned)c->grid.ncell, rpi) : 0u;
+  c->tile_bound_b = rows_b ? tile_items_bound(rows_b, (unsigned)c->grid.ncell, rpi) : 0u;
+  c->tile_nseg = nseg;
+  CU(c, c->d_tilecnt.reserve(nseg + 1));
+  CU(c, c->d_tilestart.reserve(nseg + 2));
+  CU(c, c->d_tilework.reserve(16 * ((size_t)c->tile_bound_a + c->tile_bound_b + 2)));
+  CU(c, c->d_bsum.reserve(nseg / 1024 + 4));
+  launch_tile_work(nseg, c->d_cstart.p, c->d_ccount.p, c->row_begin, c->row_end, rpi, c->d_tilecnt.p, c->d_tilestart.p,
+                   c->d_bsum.p, reinterpret_cast<TileWork*>(c->d_tilework.p), c->st);
+  c->stats.kernel_launches += 5;
+  CU_LAST(c, "tile work list");
+  c->tile_ok = true;
   return B200COORD_OK;
 }
 
@@ -639,6 +676,8 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     if (rc) return rc;
   } else {
     needed_all(c);
+    rc = build_tile_work(c);
+    if (rc) return rc;
   }
   c->sq_valid = false;  // new permutation
   c->stype_valid = false;
@@ -919,6 +958,17 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
       } else {
         nblocks = launch_sweep_list(a, c->dpbc, c->dsw, c->st);
       }
+    } else if (c->tile_ok) {
+      // cell-tile sweep: the launch covers an upper bound of the item count, blocks past the end leave at once and
+      // write no partial record
+      CU(c, c->d_partials.reserve((size_t)kPartialStride * ((size_t)c->tile_bound_a + 2)));
+      a.partials = c->d_partials.p;
+      CU(c, cudaMemsetAsync(c->d_partials.p, 0, sizeof(double) * kPartialStride * ((size_t)c->tile_bound_a + 2), c->st));
+      CU(c, cudaMemsetAsync(c->d_u64.p + 15, 0, sizeof(unsigned long long), c->st));
+      const unsigned long long* total_dev = c->d_tilestart.p + c->tile_nseg;
+      const unsigned long long* split_dev = c->d_tilestart.p + (unsigned)c->grid.ncell;
+      nblocks = launch_sweep_tile(a, c->dpbc, c->dsw, reinterpret_cast<const TileWork*>(c->d_tilework.p), c->d_u64.p + 15,
+                                  split_dev, total_dev, c->tile_bound_a, c->tile_bound_b, c->st);
     } else {
       nblocks = launch_sweep_cells(a, c->dpbc, c->dsw, c->st);
     }
@@ -1178,6 +1228,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_NO_TILE_SWEEP")) c->tile_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_IMG_VARIANT")) c->img_variant = std::atoi(e);
   needed_all(c);
   *out = c;
@@ -1235,6 +1286,9 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pslice[0].release();
   c->d_pslice[1].release();
   c->d_inv.release();
+  c->d_tilework.release();
+  c->d_tilecnt.release();
+  c->d_tilestart.release();
   if (c->h_idx) cudaFreeHost(c->h_idx);
   if (c->h_capinfo) cudaFreeHost(c->h_capinfo);
   if (c->h_small) cudaFreeHost(c->h_small);

@@ -233,6 +233,20 @@ int launch_sweep_pairs(const double* pos, const double* charges /*slot order, DH
                        unsigned pair_begin, unsigned pair_end, const DevPbc& pbc, const DevSwitch& sw, double* out,
                        double* partials, unsigned long long* evals, cudaStream_t st);
 
+// cell-tile sweep (sweep_tile.cuh): NLISTCELLS / no list, FP64, all kinds but DHENERGY / GHBFIX
+struct TileWork;
+bool sweep_tile_supports(int sw_type);
+unsigned tile_rows_per_item(unsigned rows);
+unsigned tile_items_bound(unsigned rows, unsigned nseg, unsigned rows_per_item);
+void launch_tile_work(unsigned nseg, const uint32_t* cstart, const uint32_t* ccount, unsigned row_begin, unsigned row_end,
+                      unsigned rows_per_item, uint32_t* nitems /*nseg*/, unsigned long long* item_start /*nseg + 1*/,
+                      unsigned long long* bsum, TileWork* work, cudaStream_t st);
+// zero_dev / split_dev / total_dev: device words holding 0, the first GROUPB item, the item count;
+// bound_a / bound_b: blocks to launch (upper bounds).  Returns the number of partial records (= bound_a), -1: unsupported
+int launch_sweep_tile(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, const TileWork* work,
+                      const unsigned long long* zero_dev, const unsigned long long* split_dev, const unsigned long long* total_dev,
+                      unsigned bound_a, unsigned bound_b, cudaStream_t st);
+
 // sum the per-block partials in a fixed order and write virial (9) + value behind the 3n derivatives;
 // weight = 0.5 when every pair was visited from both sides (SingleList), 1 otherwise
 void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail /*[10]*/, cudaStream_t st);

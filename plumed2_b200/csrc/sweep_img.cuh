@@ -148,7 +148,7 @@ constexpr int kImgTripCap = 208;  // trips per warp the table holds: 16 rows x 1
 constexpr unsigned kImgMaxRow = 65535u;  // longest row the 16-bit count of a trip descriptor can describe
 
 template <int K, bool ACC, int MINB>
-__global__ void __launch_bounds__(kSweepThreads, MINB)
+__global__ void __launch_bounds__(kSweepThreads, 2)
     k_sweep_img(SweepArgs a, DevSwitch sw, ImgShifts sh, NearBands nb, unsigned rows_per_block, unsigned seg_begin,
                 unsigned seg_end) {
   const double disp2 = __longlong_as_double((long long)*a.disp2_bits);
@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       request(nxt);
       refill(cur);
     };
+    constexpr bool kLateIssue = (MINB == 2);  // variant 3 (A/B switch): the issue side up front, before the arithmetic
+    if (!kLateIssue) issue_side();
     const unsigned rem = m & kRem;
     const bool va = lane < rem, vb = lane + 32u < rem;
     // everything after the vector: same for both flavours of the trip
@@ -326,11 +328,11 @@ __global__ void __launch_bounds__(kSweepThreads, MINB)
       const double rb = fma(bz, bz, fma(by, by, bx * bx));
       if (m & kFar) {  // far part: every pair of the trip beyond D_MAX -> nothing to add
         if (__all_sync(0xffffffffu, (!va || ra > a.far_skip2) && (!vb || rb > a.far_skip2))) {
-          issue_side();
+          if (kLateIssue) issue_side();
           return;
         }
       }
-      issue_side();
+      if (kLateIssue) issue_side();
       double sa, dfa, sb, dfb;
       img_eval<K>(sw, ra, va, sa, dfa, nin);
       img_eval<K>(sw, rb, vb, sb, dfb, nin);
