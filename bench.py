@@ -33,6 +33,8 @@ reference's NLIST list); evaluating a pair from both ends on the GPU does not co
           duration of the kernel, peak = FP64 FMA rate measured in this run with a DFMA microbenchmark.
   other_configs : BASELINE.json configs[0], [2] (both list flavours), [3] (through plumed_cmd) and [4] (strong
           scaling over the N GPUs of this run), a few steps each.
+  cuda_baseline : (1 GPU) the reference's own CUDA prototype plugins/cudaCoord, unchanged, next to our plugin in one
+          PLUMED input (100k and 1M atoms): time in calculate() of each action.
   cpu_baseline : the REAL reference (oracle/_ref) timed on this box's host cores on a bounded sample.
 
 --impl reference times the reference's own CPU COORDINATION (oracle/_ref through plumed_cmd, all host threads) at
@@ -567,6 +569,61 @@ def plumed_e2e(E, line, box, frames, W, K):
 
 
 # ------------------------------------------------------------------------------------------------
+def _action_timers(logfile, labels):
+    """per-action calculate() times from PLUMED's DETAILED_TIMERS table: label -> (cycles, avg s, min s)"""
+    out = {}
+    try:
+        for ln in open(logfile):
+            t = ln.split()
+            if len(t) >= 9 and t[0] == "PLUMED:" and t[1] == "4A" and t[3] in labels:
+                out[t[3]] = (int(t[4]), float(t[6]), float(t[7]))
+    except Exception:
+        pass
+    return out
+
+
+def cuda_baseline(E):
+    """The reference's own CUDA prototype (plugins/cudaCoord, unchanged, compiled for sm_100a by oracle/Makefile) next to
+    our plugin in ONE PLUMED input on the cases it supports (orthorhombic PBC, rational switch): both actions are
+    driven by the same unmodified PlumedMain on the same frames, and PLUMED's own DETAILED_TIMERS give the time each
+    spends in calculate() (host<->device copies included, PLUMED's shared host work excluded)."""
+    from oracle import refplumed as R
+    plugin = os.path.join(os.path.dirname(E.capi.LIB_PATH), "libb200coord_plumed.so")
+    cudacoord = os.path.join(ROOT, "oracle", "_ref", "lib", "CudaCoordination.so")
+    if not (R.available() and os.path.exists(plugin) and os.path.exists(cudacoord)):
+        return {"unavailable": "oracle/_ref (with CudaCoordination.so) or the plugin .so is not present on this box"}
+    os.environ["PLUMED_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["PLUMED_IGNORE_NL_MEMORY_ERROR"] = "1"
+    os.environ["B200COORD_DEVICE"] = str(E.local)
+    os.environ["B200COORD_PIN_HOST"] = "1"
+    out = {"what": "calculate() per step from PLUMED's DETAILED_TIMERS, both actions in one input, %d threads" % (os.cpu_count() or 1)}
+    for n in (100000, 1000000):
+        W, K = 10, 30
+        frames, box = make_frames(n, W + K, seed=SEED + 11, drift=DRIFT)
+        log = "/tmp/bench_cuda_baseline_%d.log" % n
+        lines = ["LOAD FILE=" + cudacoord, "LOAD FILE=" + plugin, "DEBUG DETAILED_TIMERS",
+                 "ref: CUDACOORDINATION GROUPA=1-%d R_0=0.3 NN=6 MM=12 D_MAX=0.8 NL_CUTOFF=%r NL_STRIDE=%d" % (n, NL_CUTOFF, NL_STRIDE),
+                 "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE),
+                 "RESTRAINT ARG=c,ref AT=0,0 KAPPA=0,0 SLOPE=1,1"]
+        try:
+            p = R.Plumed(n, lines, log=log, watch=("c", "ref"))
+            for s in range(W + K):
+                p.calc(s, frames[s], box)
+            vc, vr = p.value("c"), p.value("ref")
+            p.close()
+            tm = _action_timers(log, ("c", "ref"))
+            r = {"steps": W + K, "cv_ours": vc, "cv_cudacoord": vr, "rel_diff": abs(vc - vr) / abs(vr) if vr else None}
+            if "c" in tm and "ref" in tm:
+                r.update({"ours_ms_avg": 1e3 * tm["c"][1], "ours_ms_min": 1e3 * tm["c"][2],
+                          "cudacoord_ms_avg": 1e3 * tm["ref"][1], "cudacoord_ms_min": 1e3 * tm["ref"][2],
+                          "speedup_avg": tm["ref"][1] / tm["c"][1], "speedup_min": tm["ref"][2] / tm["c"][2]})
+            out["%d atoms" % n] = r
+        except Exception as e:  # cudaCoord refuses some sizes ("try by reducing the cell dimensions ...")
+            out["%d atoms" % n] = {"failed": str(e)[:300]}
+        del frames
+    return out
+
+
 def other_configs(E, peak_tflops, args):
     """BASELINE.json configs[0], [2], [3], [4]: a few device-resident steps each (jittering frames: these lines are
     here for coverage of the kernels they run, not for the displacement-conditioned shortcuts)"""
@@ -599,6 +656,21 @@ def other_configs(E, peak_tflops, args):
         torch.cuda.empty_cache()
         out[name] = r
 
+    only = getattr(args, "only_other", None)
+    if E.world == 1 and only:
+        # one configuration alone (profiling runs): configs[0] | configs[2]-NLIST | configs[2]-NLISTCELLS
+        if only == "configs[0]":
+            run("configs[0]", "c: COORDINATION GROUPA=1-1000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12}", 1000,
+                np.diag([box_edge(1000)] * 3), 68.0, steps=20)
+        else:
+            na, nb = 10000, 1000000
+            n = na + nb
+            L2 = box_edge(n)
+            tri = L2 * np.array([[1.0, 0.0, 0.0], [0.2, 1.0, 0.0], [0.1, 0.3, 1.0]])
+            flavour = only.split("-")[1]
+            run(only, "c: COORDINATION GROUPA=1-%d GROUPB=%d-%d SWITCH={EXP R_0=0.2 D_MAX=0.9} %s NL_CUTOFF=1.0 NL_STRIDE=1"
+                % (na, na + 1, n, flavour), n, tri, 102.0)
+        return out
     if E.world == 1:
         # configs[0]: plumed driver, 1k atoms, no NL
         n = 1000
@@ -665,6 +737,9 @@ def run_b200(args):
     E = Engine(args)
     torch, capi, L = E.torch, E.capi, E.L
     world, rank, local = E.world, E.rank, E.local
+    if args.only_other:
+        print(json.dumps(other_configs(E, 34.2, args)))
+        return
     n = args.natoms_per_gpu * world
     K, W = args.steps, args.warmup
     line = "c: COORDINATION GROUPA=1-%d SWITCH={%s} NLIST NL_CUTOFF=%r NL_STRIDE=%d" % (n, SWITCH, NL_CUTOFF, NL_STRIDE)
@@ -724,6 +799,9 @@ def run_b200(args):
     torch.cuda.empty_cache()
     if not args.no_other_configs:
         others = other_configs(E, peak.value, args)
+    cuda_base = None
+    if world == 1 and not args.no_cuda_baseline:
+        cuda_base = cuda_baseline(E)
 
     if rank == 0:
         sweep_ms = typ["sweep_ms"]
@@ -773,6 +851,8 @@ def run_b200(args):
             out["parity_check"] = parity
         if others is not None:
             out["other_configs"] = others
+        if cuda_base is not None:
+            out["cuda_baseline"] = cuda_base
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = reference_cpu(args.ref_sample_atoms, 12 * NL_STRIDE, 1, threads, steps_cells=NL_STRIDE)
@@ -806,13 +886,15 @@ def main():
     ap.add_argument("--no-regimes", action="store_true", help="skip the best / worst regime runs")
     ap.add_argument("--no-plumed-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-cuda-baseline", action="store_true", help="skip the plugins/cudaCoord comparison")
+    ap.add_argument("--only-other", default=None, help="profiling: run only this entry of other_configs and print it")
     ap.add_argument("--quick", action="store_true", help="only value + e2e (profiling runs)")
     ap.add_argument("--no-peer", action="store_true", help="combine with NCCL all-gather instead of NVLink peer memory")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.quick:
-        args.no_cpu_baseline = args.no_regimes = args.no_plumed_e2e = args.no_other_configs = True
+        args.no_cpu_baseline = args.no_regimes = args.no_plumed_e2e = args.no_other_configs = args.no_cuda_baseline = True
     if args.impl == "reference":
         run_reference(args)
     else:

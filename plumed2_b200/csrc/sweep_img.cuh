@@ -309,15 +309,15 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     const unsigned long long wb = (unsigned long long)__double_as_longlong(cur.pb.w);
     const double qa = cur.qa, qb = cur.qb;
     const uint32_t ta = cur.ta, tb = cur.tb;
-    // The issue side of the pipeline -- records of the next trip (L1/L2 gather, one trip ahead), entries of the trip
-    // after next (HBM stream, two trips ahead) -- is ~35 integer / load instructions that depend on nothing computed
-    // here.  It is placed INSIDE the block that evaluates the switching function, so that ptxas can interleave it
-    // with the two dependent FP64 chains (8 cycles per link) instead of leaving those gaps to the other warps.
+    // The issue side of the pipeline: records of the next trip (L1/L2 gather, one trip ahead), entries of the trip
+    // after next (HBM stream, two trips ahead).  ~35 integer / load instructions that depend on nothing computed here.
     auto issue_side = [&]() {
       request(nxt);
       refill(cur);
     };
-    constexpr bool kLateIssue = (MINB == 2);  // variant 3 (A/B switch): the issue side up front, before the arithmetic
+    // Measured (1 M atoms): issuing up front 1.075 ms, issuing between the two FP64 chains (variant 3, A/B switch
+    // B200COORD_IMG_VARIANT=3) 1.126 ms -- the interleaved loads get their turn later and the next trip waits for them.
+    constexpr bool kLateIssue = (MINB == 3);
     if (!kLateIssue) issue_side();
     const unsigned rem = m & kRem;
     const bool va = lane < rem, vb = lane + 32u < rem;

@@ -37,12 +37,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Waits for the phase; a transfer that never completes (a bug, not a load) traps instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(
-          smem_u32(bar)),
-      "r"(phase)
-      : "memory");
+  for (unsigned spins = 0;; ++spins) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) __trap();
+  }
 }
 // 1-D bulk copy global -> shared, bytes a multiple of 16, both addresses 16-byte aligned; completes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
@@ -58,7 +64,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   extern __shared__ __align__(128) unsigned char tile_raw[];
   SPos* tile = reinterpret_cast<SPos*>(tile_raw);
   __shared__ uint64_t bar;
-  __shared__ uint32_t s_rs[10], s_rm[10];  // stencil ranges: first sorted index, count
+  // stencil ranges (first sorted index, count): 9 (y,z) columns, each one run or two where it wraps around the box
+  constexpr int kMaxRanges = 20;
+  __shared__ uint32_t s_rs[kMaxRanges], s_rm[kMaxRanges];
   __shared__ int s_nr;
   __shared__ double s_part[kTileUnitsMax][3];
   __shared__ double s_row[kTileRows][3];
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     cell_coords(g, (int)(w.seg % (unsigned)g.ncell), c);
     int nr = 0;
     for_each_stencil_range(g, c, other * (unsigned)g.ncell, a.cstart, a.ccount, [&](uint32_t s0, uint32_t m, int, int, int) {
-      if (m) {
+      if (m && nr < kMaxRanges) {
         s_rs[nr] = s0;
         s_rm[nr] = m;
         ++nr;
