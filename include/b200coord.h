@@ -199,6 +199,14 @@ int b200coord_get_stats(const b200coord_ctx* ctx, b200coord_stats* out);
  * reference lists them.  *n receives the number of pairs; pairs may be NULL to query the size only. */
 int b200coord_nl_pairs(b200coord_ctx* ctx, unsigned* pairs, unsigned long long capacity, unsigned long long* n);
 
+/* The neighbour list as a tool for other consumers -- what the reference's NeighborList is to ContactMap
+ * (src/colvar/ContactMap.cpp:190-260), isdb/NOE.cpp, PRE.cpp, piv/PIV.cpp: the list of this context's rows (NLIST,
+ * not PAIR) as (i0,i1) index pairs into the position array, each pair once in the reference's orientation
+ * (NeighborList::getClosePair: GROUPA atom first, resp. lower index first), written to DEVICE memory in row order.
+ * d_pairs = 2*capacity unsigned on this context's device, or NULL to query the count.  Pairs of one and the same atom
+ * (groups that share atoms) are not in the list.  Rebuild with b200coord_update_list or the schedule of prepare(). */
+int b200coord_nl_pairs_device(b200coord_ctx* ctx, unsigned* d_pairs, unsigned long long capacity, unsigned long long* n);
+
 /* ---- multi-GPU (one context per GPU/process; i-atoms sharded by cfg.rank/nranks) */
 #define B200COORD_UNIQUE_ID_BYTES 128
 int b200coord_comm_unique_id(char id[B200COORD_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */

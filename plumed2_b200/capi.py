@@ -32,7 +32,8 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
             "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach",
             "b200coord_pairing_dhenergy", "b200coord_set_charges", "b200coord_pairing_ghbfix",
-            "b200coord_set_types", "b200coord_device_count", "b200coord_enqueue_device_distributed"]
+            "b200coord_set_types", "b200coord_device_count", "b200coord_enqueue_device_distributed",
+            "b200coord_nl_pairs_device"]
 
 
 class B200CoordError(RuntimeError):
@@ -116,6 +117,7 @@ def lib():
     L.b200coord_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.b200coord_device_count.argtypes = [C.POINTER(C.c_int)]
     L.b200coord_enqueue_device_distributed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200coord_nl_pairs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     L.b200coord_peer_export.argtypes = [C.c_void_p, C.c_char_p]
     L.b200coord_peer_attach.argtypes = [C.c_void_p, C.c_char_p]
     if L.b200coord_abi_version() != ABI_VERSION:

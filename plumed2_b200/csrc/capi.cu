@@ -116,7 +116,7 @@ struct b200coord_ctx {
   unsigned row_begin = 0, row_end = 0, row_chunk = 0;
   unsigned slot_begin = 0, slot_count = 0;  // this rank's slice of the position array (distributed step)
 
-  DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small;
+  DevBuf<double> d_pos, d_out, d_sderiv, d_partials, d_small, d_fin;
   DevBuf<uint32_t> d_abs, d_perm, d_scell, d_cell_of_slot, d_tmp, d_ccount, d_cstart, d_cursor, d_rowcount, d_nbr;
   DevBuf<unsigned long long> d_rowstart, d_bsum, d_u64;  // d_u64: [0] grand total, [1] evals, [2..7] bbox scratch, [10] max displacement^2 since the list build (bits),
                                                           // [11] the same since the super-list build
@@ -157,6 +157,7 @@ struct b200coord_ctx {
   DevBuf<uint4> d_meta;               // per row {start / 4, near count, far offset, far count}
   int img_variant = 2;                // resident blocks per SM the image sweep is compiled for (B200COORD_IMG_VARIANT)
   bool img_on = true;                 // B200COORD_NO_IMG_SWEEP=1: always the general kernel
+  bool scatter_on = true;             // B200COORD_NO_SCATTER=1: sweep GROUPB rows even when they are short
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
   DevBuf<unsigned> d_capinfo;  // [0] max row count seen, [1] overflow flag
   unsigned* h_capinfo = nullptr;
@@ -926,6 +927,8 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
       const unsigned rows_b = c->row_end - std::max(c->row_begin, acc_end);
       a.rows_per_block = sweep_img_rows_per_block(rows_a, rows_b, c->max_row);
       if (a.rows_per_block == 0u) a.img_disp2_max = 0.0;  // rows too long for the image sweep's trip table
+      // few GROUPA atoms among many GROUPB atoms (a solute in its solvent): GROUPB rows are a handful of entries each
+      a.scatter_b = (c->two_groups && c->cfg.nranks == 1 && c->scatter_on && (unsigned long long)c->n_a * 8ull <= c->n_b) ? 1 : 0;
     }
     a.scell = c->d_scell.p;
     a.cstart = c->d_cstart.p;
@@ -940,7 +943,7 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.evals = c->d_u64.p + 1;
     a.pbc_g = pbc_g;
     a.sw_g = sw_g;
-    const size_t npart = (size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 8);
+    const size_t npart = (size_t)kPartialStride * ((c->row_end - c->row_begin) / 8 + 8 + 148);
     CU(c, c->d_partials.reserve(npart));
     a.partials = c->d_partials.p;
     CU(c, cudaEventRecord(c->ev[2], c->st));
@@ -982,8 +985,9 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
   if (nblocks < 0) return fail(c, B200COORD_ERR_UNSUPPORTED, "switching function type has no GPU kernel");
   CU_LAST(c, "pair sweep launch");
   c->sweep_blocks = nblocks;
-  launch_finalize(c->d_partials.p, nblocks, weight, c->d_out.p + (size_t)3 * c->n, c->st);
-  c->stats.kernel_launches += 1;
+  CU(c, c->d_fin.reserve(16 * ((size_t)nblocks / 256 + 2)));
+  launch_finalize(c->d_partials.p, nblocks, weight, c->d_out.p + (size_t)3 * c->n, c->d_fin.p, c->st);
+  c->stats.kernel_launches += 2;
   if (c->comm) {
     int rc = combine_ranks(c);
     if (rc) return rc;
@@ -1229,6 +1233,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_TILE_SWEEP")) c->tile_on = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("B200COORD_NO_SCATTER")) c->scatter_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_IMG_VARIANT")) c->img_variant = std::atoi(e);
   needed_all(c);
   *out = c;
@@ -1286,6 +1291,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pslice[0].release();
   c->d_pslice[1].release();
   c->d_inv.release();
+  c->d_fin.release();
   c->d_tilework.release();
   c->d_tilecnt.release();
   c->d_tilestart.release();
@@ -1646,6 +1652,38 @@ int b200coord_nl_pairs(b200coord_ctx* c, unsigned* pairs, unsigned long long cap
       pairs[2 * i + 1] = out[i].second;
     }
   }
+  return B200COORD_OK;
+}
+
+int b200coord_nl_pairs_device(b200coord_ctx* c, unsigned* d_pairs, unsigned long long capacity, unsigned long long* npairs) {
+  if (!c || !npairs) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->list_valid) return fail(c, B200COORD_ERR_STATE, "no neighbour list has been built yet");
+  if (c->cfg.nl_mode != B200COORD_NL_CLASSIC || c->cfg.style == B200COORD_STYLE_PAIR)
+    return fail(c, B200COORD_ERR_UNSUPPORTED, "nl_pairs_device hands out the distance-filtered list (NLIST, not PAIR)");
+  CU(c, cudaSetDevice(c->device));
+  const unsigned rows = c->row_end - c->row_begin;
+  DevBuf<uint32_t> cnt;
+  DevBuf<unsigned long long> start;
+  CU(c, cnt.reserve(rows + 1));
+  CU(c, start.reserve(rows + 2));
+  CU(c, c->d_bsum.reserve(rows / 1024 + 4));
+  const uint32_t mask = c->img_list ? kSuperIndexMask : 0xffffffffu;
+  launch_export_pairs(false, rows, c->row_begin, c->n_a, c->two_groups, c->d_perm.p, c->d_rowstart.p, c->d_rowcount.p,
+                      c->d_rowfar.p, c->d_rowfar.p + c->far_rows, c->d_nbr.p, mask, cnt.p, nullptr, nullptr, 0ull, c->st);
+  launch_scan_rows(cnt.p, rows, 0u, c->d_bsum.p, start.p, start.p + rows, c->st);
+  unsigned long long total = 0;
+  CU(c, cudaMemcpyAsync(&total, start.p + rows, sizeof(total), cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  *npairs = total;
+  if (d_pairs && capacity) {
+    launch_export_pairs(true, rows, c->row_begin, c->n_a, c->two_groups, c->d_perm.p, c->d_rowstart.p, c->d_rowcount.p,
+                        c->d_rowfar.p, c->d_rowfar.p + c->far_rows, c->d_nbr.p, mask, cnt.p, start.p, d_pairs, capacity, c->st);
+    CU(c, cudaStreamSynchronize(c->st));
+  }
+  c->stats.kernel_launches += 5;
+  CU_LAST(c, "nl_pairs_device");
+  cnt.release();
+  start.release();
   return B200COORD_OK;
 }
 

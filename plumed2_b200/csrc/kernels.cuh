@@ -137,6 +137,11 @@ void launch_gather_u(bool build, const PosSrc& pos, const uint32_t* perm, const 
                      unsigned long long* disp2, cudaStream_t st);
 // inv[perm[k]] = k
 void launch_invert_perm(const uint32_t* perm, unsigned n, uint32_t* inv, cudaStream_t st);
+// the list as (i0, i1) index pairs on the device (b200coord_nl_pairs_device): count pass, scan, fill pass
+void launch_export_pairs(bool fill, unsigned rows, unsigned row_begin, unsigned n_a, int two_groups, const uint32_t* perm,
+                         const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
+                         const uint32_t* far_cnt, const uint32_t* nbr, uint32_t idx_mask, uint32_t* emit_count,
+                         const unsigned long long* emit_start, unsigned* pairs, unsigned long long capacity, cudaStream_t st);
 void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
                       const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st);
 // ---- super-list: a list with cutoff NL_CUTOFF + delta whose rows are the candidate sets of the following rebuilds
@@ -190,6 +195,8 @@ struct SweepArgs {
   PosSrc pos;              // the caller's positions (slot order): exact boundary patch
   double img_disp2_max;    // image mode is valid while the squared displacement since the rebuild is below this
   unsigned rows_per_block; // image mode: both kernels use this block shape (0: the kernel picks)
+  int scatter_b;           // image mode, two groups with few GROUPA atoms on one rank: the GROUPA rows add +dd to their
+                           // partners' derivative rows (RED.ADD.F64) and the GROUPB rows are not swept at all
   // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)
   // when the list was built, [row_start + row_far_off, +row_far_cnt) the rest (filled from the end of the row's
   // allocation).  A trip of the far part whose 32 pairs are all beyond D_MAX contributes exactly zero and stops
@@ -249,7 +256,9 @@ int launch_sweep_tile(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw
 
 // sum the per-block partials in a fixed order and write virial (9) + value behind the 3n derivatives;
 // weight = 0.5 when every pair was visited from both sides (SingleList), 1 otherwise
-void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail /*[10]*/, cudaStream_t st);
+// scratch: 16 doubles per 256 partial records
+void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail /*[10]*/, double* scratch,
+                     cudaStream_t st);
 // out[3*slot+c] = row inv[slot], component c, for the slots [slot_lo, slot_lo+slot_cnt): every rank PULLS the rows of its
 // own atoms from whoever swept them (NVLink peer loads; one rank: a local gather)
 void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv /*slot -> sorted*/, double* out, unsigned slot_lo,

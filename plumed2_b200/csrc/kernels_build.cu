@@ -925,6 +925,61 @@ void launch_invert_perm(const uint32_t* perm, unsigned n, uint32_t* inv, cudaStr
   if (n) k_invert_perm<<<(n + 255) / 256, 256, 0, st>>>(perm, n, inv);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The list as a tool for other consumers: (i0, i1) pairs of indices into the caller's position array, each pair once
+// in the reference's orientation (NeighborList::getIndexPair: GROUPA atom first, resp. lower index first).
+// One warp per row; FILL = false counts the pairs a row emits, FILL = true writes them at the row's offset.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+    k_export_pairs(unsigned rows, unsigned row_begin, unsigned n_a, int two_groups, const uint32_t* __restrict__ perm,
+                   const unsigned long long* __restrict__ row_start, const uint32_t* __restrict__ row_count,
+                   const uint32_t* __restrict__ far_off, const uint32_t* __restrict__ far_cnt, const uint32_t* __restrict__ nbr,
+                   uint32_t idx_mask, uint32_t* __restrict__ emit_count, const unsigned long long* __restrict__ emit_start,
+                   unsigned* __restrict__ pairs, unsigned long long capacity) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const unsigned k = row_begin + warp;
+  const uint32_t si = perm[k];
+  const uint32_t* __restrict__ row = nbr + row_start[warp];
+  const unsigned near = row_count[warp], far = far_cnt ? far_cnt[warp] : 0u, foff = far_off ? far_off[warp] : 0u;
+  unsigned total = 0;
+  const unsigned long long base = FILL ? emit_start[warp] : 0ull;
+  for (unsigned e0 = 0; e0 < near + far; e0 += 32) {
+    const unsigned e = e0 + lane;
+    bool keep = false;
+    uint32_t sj = 0;
+    if (e < near + far) {
+      const uint32_t j = (e < near ? row[e] : row[foff + (e - near)]) & idx_mask;
+      sj = perm[j];
+      keep = two_groups ? (k < n_a) : (si < sj);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (FILL && keep) {
+      const unsigned long long at = base + total + __popc(mask & ((1u << lane) - 1u));
+      if (at < capacity) {
+        pairs[2 * at] = si;
+        pairs[2 * at + 1] = sj;
+      }
+    }
+    total += __popc(mask);
+  }
+  if (!FILL && lane == 0) emit_count[warp] = total;
+}
+
+void launch_export_pairs(bool fill, unsigned rows, unsigned row_begin, unsigned n_a, int two_groups, const uint32_t* perm,
+                         const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
+                         const uint32_t* far_cnt, const uint32_t* nbr, uint32_t idx_mask, uint32_t* emit_count,
+                         const unsigned long long* emit_start, unsigned* pairs, unsigned long long capacity, cudaStream_t st) {
+  if (!rows) return;
+  const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
+  if (fill)
+    k_export_pairs<true><<<blocks, 256, 0, st>>>(rows, row_begin, n_a, two_groups, perm, row_start, row_count, far_off, far_cnt,
+                                                 nbr, idx_mask, emit_count, emit_start, pairs, capacity);
+  else
+    k_export_pairs<false><<<blocks, 256, 0, st>>>(rows, row_begin, n_a, two_groups, perm, row_start, row_count, far_off, far_cnt,
+                                                  nbr, idx_mask, emit_count, emit_start, pairs, capacity);
+}
+
 void launch_pack_meta(unsigned rows, const unsigned long long* row_start, const uint32_t* row_count, const uint32_t* far_off,
                       const uint32_t* far_cnt, uint4* meta, unsigned long long* listed, cudaStream_t st) {
   cudaMemsetAsync(listed, 0, sizeof(unsigned long long), st);

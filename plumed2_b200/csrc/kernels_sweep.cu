@@ -85,20 +85,28 @@ __global__ void __launch_bounds__(kSweepThreads)
 
 // ------------------------------------------------------------------------------------------------
 // fixed-order sum of the block partials; virial = -weight * sum(c), value = weight * sum(s).
-// 1024 threads = 64 groups x 16 components; group g adds records g, g+64, ... and the 64 group sums are
-// added in index order, so the result does not depend on scheduling.
-__global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int nblocks, double weight,
-                                                   double* __restrict__ tail) {
+// Level 1: block b adds the records [b * 256, (b + 1) * 256) -- 64 groups x 16 components, group g takes records g, g + 64,
+// ... and the 64 group sums are added in index order.  Level 2 (one block) adds the level-1 sums in index order.  The
+// result does not depend on scheduling.
+__global__ void __launch_bounds__(1024) k_finalize1(const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
   __shared__ double sm[64][16];
   const int comp = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const int b0 = blockIdx.x * 256, b1 = min(nblocks, b0 + 256);
   double t = 0.0;
   if (comp < 10)
-    for (int b = grp; b < nblocks; b += 64) t += partials[(size_t)b * kPartialStride + comp];
+    for (int b = b0 + grp; b < b1; b += 64) t += partials[(size_t)b * kPartialStride + comp];
   sm[grp][comp] = t;
   __syncthreads();
   if (threadIdx.x < 10) {
     double r = 0.0;
     for (int g2 = 0; g2 < 64; ++g2) r += sm[g2][threadIdx.x];
+    sums[(size_t)blockIdx.x * 16 + threadIdx.x] = r;
+  }
+}
+__global__ void __launch_bounds__(32) k_finalize2(const double* __restrict__ sums, int n, double weight, double* __restrict__ tail) {
+  if (threadIdx.x < 10) {
+    double r = 0.0;
+    for (int b = 0; b < n; ++b) r += sums[(size_t)b * 16 + threadIdx.x];
     if (threadIdx.x == 0) tail[9] = r * weight;
     else tail[threadIdx.x - 1] = -(r * weight);
   }
@@ -175,8 +183,10 @@ int launch_sweep_pairs(const double* pos, const double* charges, const uint32_t*
 #undef B200_PAIR_CASE
 }
 
-void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail, cudaStream_t st) {
-  k_finalize<<<1, 1024, 0, st>>>(partials, nblocks, weight, out_tail);
+void launch_finalize(const double* partials, int nblocks, double weight, double* out_tail, double* scratch, cudaStream_t st) {
+  const int n1 = nblocks > 0 ? (nblocks + 255) / 256 : 1;
+  k_finalize1<<<n1, 1024, 0, st>>>(partials, nblocks, scratch);
+  k_finalize2<<<1, 32, 0, st>>>(scratch, n1, weight, out_tail);
 }
 
 void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv, double* out, unsigned slot_lo, unsigned slot_cnt,

@@ -7,7 +7,7 @@
 namespace b200 {
 
 unsigned tile_rows_per_item(unsigned rows) {
-  unsigned r = rows / (148u * 4u);
+  unsigned r = rows / (148u * 4u);  // small systems: enough items for every SM
   if (r < 4u) r = 4u;
   if (r > (unsigned)kTileRows) r = (unsigned)kTileRows;
   return r;

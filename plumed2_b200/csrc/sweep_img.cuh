@@ -100,7 +100,7 @@ __device__ __noinline__ RowFixImg row_fixup_img(const DevPbc* __restrict__ pbc_g
                                                 const SPos* __restrict__ spos, PosSrc pos,
                                                 const uint32_t* __restrict__ nbr, uint4 m, bool far_on,
                                                 const double* shifts /*shared*/, unsigned k, unsigned lane, int two_groups,
-                                                bool row_is_b, bool acc) {
+                                                bool row_is_b, bool acc, double* scatter /*null or the derivative rows*/) {
   RowFixImg f;
   f.fx = f.fy = f.fz = f.val = 0.0;
 #pragma unroll
@@ -128,6 +128,12 @@ __device__ __noinline__ RowFixImg row_fixup_img(const DevPbc* __restrict__ pbc_g
     f.fx -= gx;
     f.fy -= gy;
     f.fz -= gz;
+    if (scatter) {  // the partner's row is not swept: it gets its share of the correction here
+      double* dj = scatter + 3 * (size_t)(ent & kSuperIndexMask);
+      atomicAdd(dj, gx);
+      atomicAdd(dj + 1, gy);
+      atomicAdd(dj + 2, gz);
+    }
     if (acc) {
       f.val += o.s - s;
       f.c[0] += gx * S[0]; f.c[1] += gx * S[1]; f.c[2] += gx * S[2];
@@ -356,6 +362,23 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
       fx = fma(-dfa, ax, fma(-dfb, bx, fx));
       fy = fma(-dfa, ay, fma(-dfb, by, fy));
       fz = fma(-dfa, az, fma(-dfb, bz, fz));
+      if (ACC && a.scatter_b) {
+        // few GROUPA atoms in a sea of GROUPB atoms: a GROUPB row holds a handful of entries, and sweeping a million of
+        // them costs ten times the GROUPA rows.  Instead this (GROUPA) row hands +dd to its partners: deriv[i1] += dd
+        // (CoordinationBase.cpp:201), three reductions per contributing pair, no second evaluation.
+        if (dfa != 0.0) {
+          double* dj = a.sderiv + 3 * (size_t)(ia & kSuperIndexMask);
+          atomicAdd(dj, dfa * ax);
+          atomicAdd(dj + 1, dfa * ay);
+          atomicAdd(dj + 2, dfa * az);
+        }
+        if (dfb != 0.0) {
+          double* dj = a.sderiv + 3 * (size_t)(ib & kSuperIndexMask);
+          atomicAdd(dj, dfb * bx);
+          atomicAdd(dj + 1, dfb * by);
+          atomicAdd(dj + 2, dfb * bz);
+        }
+      }
       if (ACC) {
         val += sa + sb;
         if (SHIFTED) {  // g (x) S of this trip, g = df * e
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     const unsigned rf = wid + kSweepWarps * m;
     const unsigned kf = first + rf;
     const RowFixImg f = row_fixup_img<K>(a.pbc_g, a.sw_g, a.spos, a.pos, a.nbr, s_meta[rf], far_on, s_shift, kf, lane,
-                                         a.two_groups, kf >= a.n_a, ACC);
+                                         a.two_groups, kf >= a.n_a, ACC, (ACC && a.scatter_b) ? a.sderiv : nullptr);
     const RecBuf own = s_own[rf];
     const double gx = f.fx * winv, gy = f.fy * winv, gz = f.fz * winv;  // per lane: the sums are linear
     double* sc = &s_c[0][threadIdx.x];
@@ -445,6 +468,35 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   }
 }
 
+// position part of the virial for rows that were not swept (scatter_b): one partial record per block with
+// c = sum deriv_k (x) u_k over the block's share of rows [begin, end); gated like k_sweep_img
+__global__ void __launch_bounds__(256)
+    k_posvir_rows(SweepArgs a, unsigned begin, unsigned end, unsigned record0) {
+  if (!(__longlong_as_double((long long)*a.disp2_bits) < a.img_disp2_max)) return;
+  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (unsigned k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += gridDim.x * blockDim.x) {
+    const SPos p = load_spos(a.spos + k);
+    const double dx = a.sderiv[3 * (size_t)k], dy = a.sderiv[3 * (size_t)k + 1], dz = a.sderiv[3 * (size_t)k + 2];
+    c[0] = fma(dx, p.x, c[0]); c[1] = fma(dx, p.y, c[1]); c[2] = fma(dx, p.z, c[2]);
+    c[3] = fma(dy, p.x, c[3]); c[4] = fma(dy, p.y, c[4]); c[5] = fma(dy, p.z, c[5]);
+    c[6] = fma(dz, p.x, c[6]); c[7] = fma(dz, p.y, c[7]); c[8] = fma(dz, p.z, c[8]);
+  }
+  __shared__ double sm[8][9];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const double t = warp_sum(c[q]);
+    if (lane == 0) sm[wid][q] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+    if (threadIdx.x > 0)
+      for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x - 1];
+    a.partials[(size_t)(record0 + blockIdx.x) * kPartialStride + threadIdx.x] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dispatch.  Same grid shape as run_sweep (sweep_kernels.cuh): whichever of the two kernels takes the step fills
 // the same partial records.
@@ -472,7 +524,12 @@ static int run_sweep_img(const SweepArgs& a, const DevSwitch& sw, const ImgShift
     k_sweep_img<K, true, MINB><<<nblocks, kSweepThreads, 0, st>>>(a, sw, sh, nb, rpb, a.row_begin, acc_end);
   }
   const unsigned b_begin = max(a.row_begin, acc_end);
-  if (b_begin < a.row_end) {
+  if (b_begin < a.row_end && a.scatter_b) {
+    // the GROUPA rows have added +dd to their partners: only the position part of the virial is left to do
+    const int nb2 = 148;
+    k_posvir_rows<<<nb2, 256, 0, st>>>(a, b_begin, a.row_end, (unsigned)nblocks);
+    nblocks += nb2;
+  } else if (b_begin < a.row_end) {
     const unsigned rows = a.row_end - b_begin;
     const unsigned rpb = a.rows_per_block;
     const int nb2 = (int)((rows + rpb - 1) / rpb);

@@ -13,15 +13,14 @@ namespace b200 {
 //
 // 128 registers / 2 blocks per SM on purpose: with fewer registers ptxas sinks the record loads of the next trip
 // down to their first use (and spills the accumulators), which exposes the L2 latency of the gather in every trip.
+// one block's worth of rows: rows [seg_begin + vb * rows_per_block, +rows_per_block), partial record vb
 template <int K, int PBC, bool ACC, typename T>
-__global__ void __launch_bounds__(kSweepThreads, 2)
-    k_sweep_list(SweepArgs a, DevPbc pbc, DevSwitchT<T> sw, unsigned rows_per_block, unsigned seg_begin, unsigned seg_end) {
-  // image mode: k_sweep_img does the step while its displacement bound holds (img_disp2_max = 0: it never runs)
-  if (__longlong_as_double((long long)*a.disp2_bits) < a.img_disp2_max) return;
+__device__ __forceinline__ void sweep_list_block(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>& sw,
+                                                 unsigned rows_per_block, unsigned seg_begin, unsigned seg_end, unsigned vb) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LaneAcc acc = {0, 0, 0, 0, 0, 0, 0};
   unsigned long long evals = 0, execd = 0;
-  const unsigned first = seg_begin + blockIdx.x * rows_per_block;
+  const unsigned first = seg_begin + vb * rows_per_block;
   const unsigned last = min(first + rows_per_block, seg_end);
   unsigned fixmask = 0u;  // rows of this warp with a pair on a D_MAX / D_0 boundary (rows_per_block <= 32 warps' worth)
   const T far_skip2 = (T)a.far_skip2;
@@ -160,9 +159,24 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     }
   }
   if (ACC)
-    block_store_partials(acc, evals, a.partials, a.evals);
+    block_store_partials(acc, evals, a.partials, a.evals, vb);
   else if (lane == 0 && evals)
     atomicAdd(a.evals, evals);
+}
+
+// In image mode this kernel is launched every step next to k_sweep_img and one of the two returns at once (device-side
+// gate on the displacement).  The one that returns should cost nothing: the launch then has only as many blocks as
+// fit the machine at once, and a block that does run walks its share of the `nvb` virtual blocks.
+template <int K, int PBC, bool ACC, typename T>
+__global__ void __launch_bounds__(kSweepThreads, 2)
+    k_sweep_list(SweepArgs a, DevPbc pbc, DevSwitchT<T> sw, unsigned rows_per_block, unsigned seg_begin, unsigned seg_end,
+                 unsigned nvb) {
+  // image mode: k_sweep_img does the step while its displacement bound holds (img_disp2_max = 0: it never runs)
+  if (__longlong_as_double((long long)*a.disp2_bits) < a.img_disp2_max) return;
+  for (unsigned vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+    sweep_list_block<K, PBC, ACC, T>(a, pbc, sw, rows_per_block, seg_begin, seg_end, vb);
+    __syncthreads();  // the shared arrays of the block epilogue are reused by the next virtual block
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +241,12 @@ __global__ void __launch_bounds__(kSweepThreads)
 
 // ------------------------------------------------------------------------------------------------
 // dispatch
+// blocks to launch for `nblocks` virtual blocks: all of them normally; in image mode (the kernel is the fall-back that
+// usually returns at once) one wave, 2 resident blocks on each of the 148 SMs
+static inline int list_grid(const SweepArgs& a, int nblocks) {
+  return (a.img_disp2_max > 0.0 && nblocks > 296) ? 296 : nblocks;
+}
+
 template <int K, int PBC, bool LIST, typename T>
 static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>& sw, cudaStream_t st) {
   // rows that accumulate value+virial: SingleList -> all; TwoList -> only the A rows
@@ -237,7 +257,8 @@ static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>&
     const unsigned rpb = a.rows_per_block ? a.rows_per_block : pick_rows_per_block(rows);
     nblocks = (int)((rows + rpb - 1) / rpb);
     if (LIST)
-      k_sweep_list<K, PBC, true, T><<<nblocks, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, a.row_begin, acc_end);
+      k_sweep_list<K, PBC, true, T><<<list_grid(a, nblocks), kSweepThreads, 0, st>>>(a, pbc, sw, rpb, a.row_begin, acc_end,
+                                                                                      (unsigned)nblocks);
     else
       k_sweep_cells<K, PBC, true, T><<<nblocks, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, a.row_begin, acc_end);
   }
@@ -247,7 +268,7 @@ static int run_sweep(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<T>&
     const unsigned rpb = a.rows_per_block ? a.rows_per_block : pick_rows_per_block(rows);
     const int nb = (int)((rows + rpb - 1) / rpb);
     if (LIST)
-      k_sweep_list<K, PBC, false, T><<<nb, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, b_begin, a.row_end);
+      k_sweep_list<K, PBC, false, T><<<list_grid(a, nb), kSweepThreads, 0, st>>>(a, pbc, sw, rpb, b_begin, a.row_end, (unsigned)nb);
     else
       k_sweep_cells<K, PBC, false, T><<<nb, kSweepThreads, 0, st>>>(a, pbc, sw, rpb, b_begin, a.row_end);
   }

@@ -581,7 +581,8 @@ static inline unsigned pick_rows_per_block(unsigned rows) {
 // block epilogue: reduce the lane accumulators of all warps and store one partial record
 // {value, c[3][3]} with c = sum df d (x) d (symmetric here; the image sweep stores a general 3x3 sum)
 __device__ __forceinline__ void block_store_partials(const LaneAcc& a, unsigned long long evals, double* partials,
-                                                     unsigned long long* evals_out) {
+                                                     unsigned long long* evals_out, unsigned record = 0xffffffffu) {
+  if (record == 0xffffffffu) record = blockIdx.x;
   constexpr int kMaxWarps = 32;  // blocks of up to 1024 threads
   __shared__ double sm[kMaxWarps][8];
   __shared__ unsigned long long sev[kMaxWarps];
@@ -607,7 +608,7 @@ __device__ __forceinline__ void block_store_partials(const LaneAcc& a, unsigned 
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < nwarps; ++w) t += sm[w][src];
-    partials[(size_t)blockIdx.x * kPartialStride + threadIdx.x] = t;
+    partials[(size_t)record * kPartialStride + threadIdx.x] = t;
   }
   if (threadIdx.x == 32) {
     unsigned long long t = 0;

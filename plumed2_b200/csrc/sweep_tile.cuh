@@ -1,7 +1,7 @@
 // Cell-tile sweep for NLISTCELLS and "no list" (the reference's superset semantics: every pair of the <= 27 stencil
 // cells of the frozen binning, resp. every pair; NeighborList.cpp:177-236, :133-140; CoordinationBase.cpp:177-208).
 //
-// One block = one chunk of <= 32 rows (i-atoms) of ONE cell.  All rows of a cell see the same partners -- the <= 9
+// One block = one chunk of <= 128 rows (i-atoms) of ONE cell.  All rows of a cell see the same partners -- the <= 9
 // contiguous sorted ranges of the stencil cells (kernels.cuh: for_each_stencil_range) -- so the block stages them ONCE
 // into shared memory with 1-D bulk copies (cp.async.bulk, completion on an mbarrier: the TMA engine moves the bytes, no
 // thread touches them) and every row reuses them from there.  The warp-per-row kernel this replaces re-gathered the
@@ -16,10 +16,11 @@
 
 namespace b200 {
 
-constexpr int kTileRows = 32;        // rows per block at most
+constexpr int kTileRows = 128;       // rows per block at most (a whole cell of water)
+constexpr int kTileSub = 32;         // rows whose units are in flight together
 constexpr int kTileCap = 2048;       // staged partner records per pass (64 KB)
 constexpr int kTileUnit = 128;       // partners per unit
-constexpr int kTileUnitsMax = kTileRows * (kTileCap / kTileUnit);
+constexpr int kTileUnitsMax = kTileSub * (kTileCap / kTileUnit);
 
 struct TileWork {
   uint32_t seg;    // group * ncell + cell
@@ -78,19 +79,49 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   const DevGrid& g = a.grid;
   const unsigned my_grp = w.seg / (unsigned)g.ncell;
   const unsigned other = a.two_groups ? (1u - my_grp) : 0u;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    int c[3];
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (wid == 0) {
+    // range table: lane = one (y, z) column of the stencil; its x-run is one sorted range, or two where it wraps around
+    // the box.  All the dependent cstart / ccount loads of the block are in flight at once (a serial walk costs ~27
+    // L2 round trips per block).
+    int c[3], lo[3], hi[3];
     cell_coords(g, (int)(w.seg % (unsigned)g.ncell), c);
-    int nr = 0;
-    for_each_stencil_range(g, c, other * (unsigned)g.ncell, a.cstart, a.ccount, [&](uint32_t s0, uint32_t m, int, int, int) {
-      if (m && nr < kMaxRanges) {
-        s_rs[nr] = s0;
-        s_rm[nr] = m;
-        ++nr;
+    stencil_bounds(g, c, lo, hi);
+    const int nyn = hi[1] - lo[1], nzn = hi[2] - lo[2];
+    uint32_t sA = 0, mA = 0, sB = 0, mB = 0;
+    if ((int)lane < nyn * nzn) {
+      const int ny = lo[1] + (int)lane / nzn, nz = lo[2] + (int)lane % nzn;
+      const unsigned cbase = other * (unsigned)g.ncell + (unsigned)(wrap_cell(ny, g.n[1]) * g.n[0] + wrap_cell(nz, g.n[2]) * g.n[0] * g.n[1]);
+      int x = lo[0];
+      {
+        const int xw = wrap_cell(x, g.n[0]);
+        const int run = min(hi[0] - x, g.n[0] - xw);
+        const unsigned f0 = cbase + (unsigned)xw, l0 = f0 + (unsigned)run - 1u;
+        sA = a.cstart[f0];
+        mA = a.cstart[l0] + a.ccount[l0] - sA;
+        x += run;
       }
-    });
-    s_nr = nr;
+      if (x < hi[0]) {
+        const int xw = wrap_cell(x, g.n[0]);
+        const int run = min(hi[0] - x, g.n[0] - xw);
+        const unsigned f0 = cbase + (unsigned)xw, l0 = f0 + (unsigned)run - 1u;
+        sB = a.cstart[f0];
+        mB = a.cstart[l0] + a.ccount[l0] - sB;
+      }
+    }
+    // compact the non-empty ranges in lane order (A before B): same order as for_each_stencil_range
+    const unsigned hasA = __ballot_sync(0xffffffffu, mA != 0u), hasB = __ballot_sync(0xffffffffu, mB != 0u);
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned posA = __popc(hasA & below) + __popc(hasB & below);
+    if (mA && posA < (unsigned)kMaxRanges) {
+      s_rs[posA] = sA;
+      s_rm[posA] = mA;
+    }
+    if (mB && posA + (mA ? 1u : 0u) < (unsigned)kMaxRanges) {
+      s_rs[posA + (mA ? 1u : 0u)] = sB;
+      s_rm[posA + (mA ? 1u : 0u)] = mB;
+    }
+    if (lane == 0) s_nr = min(__popc(hasA) + __popc(hasB), kMaxRanges);
   }
   for (unsigned t = threadIdx.x; t < (unsigned)kTileRows * 3u; t += kSweepThreads) (&s_row[0][0])[t] = 0.0;
   __syncthreads();
@@ -116,10 +147,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     mbar_wait(&bar, phase);
     phase ^= 1u;
     const unsigned nq = (np + kTileUnit - 1) / kTileUnit;
-    const unsigned units = w.nrows * nq;
+    for (unsigned r0 = 0; r0 < w.nrows; r0 += kTileSub) {  // the staged partners serve every row of the cell
+    const unsigned nsub = min((unsigned)kTileSub, w.nrows - r0);
+    const unsigned units = nsub * nq;
     for (unsigned u = wid; u < units; u += kSweepWarps) {
       const unsigned r = u / nq, q = u - r * nq;
-      const SPos pi = load_spos(a.spos + w.row0 + r);
+      const SPos pi = load_spos(a.spos + w.row0 + r0 + r);
       const unsigned long long wi = ((unsigned long long)pi.slot << 32) | pi.abs_index;
       double fx = 0.0, fy = 0.0, fz = 0.0;
       bool unused_near = false;
@@ -142,15 +175,16 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     }
     __syncthreads();
     // fixed-order combine: thread (r, c) adds the units of row r
-    if (threadIdx.x < w.nrows * 3u) {
+    if (threadIdx.x < nsub * 3u) {
       const unsigned r = threadIdx.x / 3u, c = threadIdx.x - 3u * r;
-      double t = s_row[r][c];
+      double t = s_row[r0 + r][c];
       for (unsigned q = 0; q < nq; ++q) t += s_part[r * nq + q][c];
-      s_row[r][c] = t;
+      s_row[r0 + r][c] = t;
     }
     __syncthreads();
+    }
   }
-  if (threadIdx.x < w.nrows * 3u) a.sderiv[3 * (size_t)w.row0 + threadIdx.x] = (&s_row[0][0])[threadIdx.x];
+  for (unsigned t = threadIdx.x; t < w.nrows * 3u; t += kSweepThreads) a.sderiv[3 * (size_t)w.row0 + t] = (&s_row[0][0])[t];
   const unsigned long long evals = (threadIdx.x == 0) ? (unsigned long long)w.nrows * P : 0ull;
   if (threadIdx.x == 0 && evals) atomicAdd(a.executed, evals);
   if (ACC) {

@@ -554,3 +554,72 @@ def test_update_list_then_calculate_uses_the_new_list_and_its_displacement_origi
     assert_parity(c, ref, "after update_list")
     np.testing.assert_array_equal(c.neighbor_pairs(), sort_pairs(ref["pairs"]))
     c.close()
+
+
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("sw", ["SWITCH={EXP R_0=0.2 D_MAX=0.7}", "SWITCH={RATIONAL R_0=0.3 D_MAX=0.7}", "R_0=0.25"])
+def test_few_group_a_atoms_scatter_to_their_partners(sw, tri):
+    """A solute in its solvent (GROUPA 8x smaller than GROUPB or less): the GROUPB rows hold a handful of entries each, so
+    the image sweep does not visit them -- the GROUPA rows add +dd to their partners' derivatives instead.  Against the
+    oracle, and against the same steps with B200COORD_NO_SCATTER=1 (every GROUPB row swept)."""
+    n, na = 6000, 300
+    pos0, box = water_box(n, 100.0, seed=81, triclinic=tri)
+    line = "c: COORDINATION GROUPA=1-%d GROUPB=%d-%d %s NLIST NL_CUTOFF=0.8 NL_STRIDE=3" % (na, na + 1, n, sw)
+    runs = []
+    for env in ({}, {"B200COORD_NO_SCATTER": "1"}):
+        os.environ.update(env)
+        try:
+            c = P.Coordination.from_input(line)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        rng = np.random.default_rng(19)
+        pos, out, list_pos = pos0.copy(), [], None
+        for step in range(5):
+            pos = pos + 0.005 * rng.standard_normal(pos.shape)
+            if c.prepare(step):
+                list_pos = pos.copy()
+            c.calculate(pos, box)
+            if not env:
+                assert_parity(c, oracle_from_line(line, pos, box, list_positions=list_pos, nthreads=8, fast_list=True), "step %d" % step)
+            out.append((c.value, c.derivatives.copy(), c.virial.copy()))
+        runs.append(out)
+        c.close()
+    for (v0, d0, w0), (v1, d1, w1) in zip(*runs):
+        assert abs(v0 - v1) <= 1e-12 * abs(v0) and rel_err(d0, d1) <= 1e-11 and rel_err(w0, w1) <= 1e-11
+
+
+@pytest.mark.parametrize("groups", ["GROUPA=1-4000", "GROUPA=1-700 GROUPB=501-4000"])
+def test_neighbour_list_as_a_tool_device_pairs(groups):
+    """b200coord_nl_pairs_device: the list handed out on the DEVICE as (i0,i1) index pairs, what the reference's
+    NeighborList is to ContactMap (src/colvar/ContactMap.cpp:190-260).  The pair set must be the oracle's (minus pairs of one
+    and the same atom), and a consumer that sums a switching function over the pairs -- a CONTACTMAP SUM -- must reproduce
+    COORDINATION's value."""
+    import torch
+    n = 4000
+    pos, box = water_box(n, 100.0, seed=91)
+    line = "c: COORDINATION %s SWITCH={RATIONAL R_0=0.3 D_MAX=0.7} NLIST NL_CUTOFF=0.8 NL_STRIDE=5" % groups
+    c = gpu_eval(line, pos, box)
+    L = capi.lib()
+    npairs = C.c_ulonglong(0)
+    capi.check(L.b200coord_nl_pairs_device(c._ctx, None, 0, C.byref(npairs)), c._ctx)
+    buf = torch.empty((npairs.value, 2), dtype=torch.int32, device="cuda")
+    capi.check(L.b200coord_nl_pairs_device(c._ctx, C.c_void_p(buf.data_ptr()), npairs.value, C.byref(npairs)), c._ctx)
+    ref = oracle_from_line(line, pos, box, nthreads=8, fast_list=True)
+    atoms = ref["atoms"]
+    mine = buf.cpu().numpy().astype(np.uint32)
+    rp = sort_pairs(ref["pairs"])
+    rp = rp[atoms[rp[:, 0]] != atoms[rp[:, 1]]]  # the groups share atoms 501-700: the reference lists those self pairs
+    np.testing.assert_array_equal(sort_pairs(mine), rp)
+    np.testing.assert_array_equal(sort_pairs(mine), c.neighbor_pairs()[atoms[c.neighbor_pairs()[:, 0]] != atoms[c.neighbor_pairs()[:, 1]]])
+    # the consumer: sum of s(r) over the pairs, on the device
+    x = torch.tensor(pos[atoms], device="cuda")
+    Ld = torch.tensor(np.diag(box), device="cuda")
+    d = x[buf[:, 1].long()] - x[buf[:, 0].long()]
+    d = d - torch.round(d / Ld) * Ld
+    r2 = (d * d).sum(1)
+    sw = O.make_switch("RATIONAL R_0=0.3 D_MAX=0.7")
+    y = r2 * sw.invr0_2
+    s = torch.where(r2 <= sw.dmax_2, (1.0 / (1.0 + y ** 3)) * sw.stretch + sw.shift, torch.zeros_like(r2))
+    assert abs(float(s.sum().item()) - c.value) <= 1e-10 * abs(c.value)
+    c.close()
