@@ -130,6 +130,7 @@ struct b200coord_ctx {
   double band_rel = 0.0;
   unsigned row_cap = 0;        // per-row capacity learnt from the last rebuild (0: unknown -> two-pass build)
   unsigned max_row = 0;        // longest row (near + far entries) of the current list
+  unsigned super_cap = 0;      // the same capacity for the rows of the super-list
   DevBuf<double> d_q, d_sq;    // charges in slot order / sorted order (DHENERGY)
   bool have_charges = false, sq_valid = false;
   DevBuf<uint32_t> d_types, d_stype;  // interaction types in slot order / sorted order (GHBFIX)
@@ -709,16 +710,34 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
       auto super_pass = [&](int m) {
         launch_nl_rows_f32(m, true, true, d_pos, c->d_perm.p, c->d_lpos.p, c->d_scell.p, c->d_cstart.p, c->d_ccount.p, c->grid, pbc_g,
                            c->dbox, sc2, c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_srowcount.p,
-                           c->d_srowstart.p, m ? c->d_snbr.p : nullptr, 0u, c->d_capinfo.p, INFINITY, nullptr, nullptr, c->st);
+                           c->d_srowstart.p, m ? c->d_snbr.p : nullptr, m == 2 ? c->super_cap : 0u, c->d_capinfo.p, INFINITY,
+                           nullptr, nullptr, c->st);
       };
-      super_pass(0);
-      launch_scan_rows(c->d_srowcount.p, rows, 3u, c->d_bsum.p, c->d_srowstart.p, c->d_u64.p, c->st);
-      CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
-      CU(c, cudaStreamSynchronize(c->st));
-      CU_LAST(c, "super-list count");
-      CU(c, c->d_snbr.reserve((size_t)c->h_u64[0] + 4));
-      super_pass(1);
-      c->stats.kernel_launches += 5;
+      // like the working list: one pass into fixed-capacity rows once a capacity is known (1.2 x the longest row of the
+      // previous build), the exact count + scan + fill on the first build and after an overflow
+      bool sdone = false;
+      if (c->super_cap > 0) {
+        CU(c, c->d_snbr.reserve((size_t)rows * c->super_cap + 4));
+        super_pass(2);
+        CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        CU_LAST(c, "super-list single-pass build");
+        c->stats.kernel_launches += 2;
+        sdone = (c->h_capinfo[1] == 0);
+        if (!sdone) CU(c, cudaMemsetAsync(c->d_capinfo.p, 0, 3 * sizeof(unsigned), c->st));
+      }
+      if (!sdone) {
+        super_pass(0);
+        launch_scan_rows(c->d_srowcount.p, rows, 3u, c->d_bsum.p, c->d_srowstart.p, c->d_u64.p, c->st);
+        CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        CU_LAST(c, "super-list count");
+        CU(c, c->d_snbr.reserve(std::max((size_t)c->h_u64[0], (size_t)rows * next_row_cap(c->h_capinfo[0], 0u)) + 4));
+        super_pass(1);
+        c->stats.kernel_launches += 5;
+      }
+      c->super_cap = next_row_cap(c->h_capinfo[0], c->super_cap);
       c->super_valid = true;
       c->super_box_epoch = c->box_epoch;
       c->super_builds++;

@@ -1002,9 +1002,10 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
 #define B200_F32_ARGS pos, perm, lpos, scell, cstart, ccount, g, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (super) {  // super-list rows: two passes only, always with images
+  if (super) {  // super-list rows: always with images
     if (mode == 0) k_nl_rows_f32<false, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else if (mode == 1) k_nl_rows_f32<true, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
+    else k_nl_rows_f32<true, true, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
   } else if (mode == 0) k_nl_rows_f32<false, false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
   else if (images) {
     if (mode == 1) k_nl_rows_f32<true, false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
