@@ -987,6 +987,11 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
       a.partials = c->d_partials.p;
       CU(c, cudaMemsetAsync(c->d_partials.p, 0, sizeof(double) * kPartialStride * ((size_t)c->tile_bound_a + 2), c->st));
       CU(c, cudaMemsetAsync(c->d_u64.p + 15, 0, sizeof(unsigned long long), c->st));
+      // a solute in its solvent: GROUPA rows scatter to their partners, GROUPB rows (zeroed here) are not swept
+      a.scatter_b = (c->two_groups && c->cfg.nranks == 1 && c->scatter_on && (unsigned long long)c->n_a * 8ull <= c->n_b) ? 1 : 0;
+      a.inv = c->d_inv.p;
+      if (a.scatter_b)
+        CU(c, cudaMemsetAsync(rows_now + 3 * (size_t)c->n_a, 0, sizeof(double) * 3 * (size_t)c->n_b, c->st));
       const unsigned long long* total_dev = c->d_tilestart.p + c->tile_nseg;
       const unsigned long long* split_dev = c->d_tilestart.p + (unsigned)c->grid.ncell;
       nblocks = launch_sweep_tile(a, c->dpbc, c->dsw, reinterpret_cast<const TileWork*>(c->d_tilework.p), c->d_u64.p + 15,

@@ -195,6 +195,7 @@ struct SweepArgs {
   PosSrc pos;              // the caller's positions (slot order): exact boundary patch
   double img_disp2_max;    // image mode is valid while the squared displacement since the rebuild is below this
   unsigned rows_per_block; // image mode: both kernels use this block shape (0: the kernel picks)
+  const uint32_t* inv;     // slot -> sorted index (scatter_b in the cell-tile sweep)
   int scatter_b;           // image mode, two groups with few GROUPA atoms on one rank: the GROUPA rows add +dd to their
                            // partners' derivative rows (RED.ADD.F64) and the GROUPB rows are not swept at all
   // every row is stored in two parts: [row_start, +row_count) holds the partners that were inside D_MAX (+ a skin)

@@ -46,7 +46,8 @@ static int run_tile(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& sw, 
                     unsigned bound_a, unsigned bound_b, cudaStream_t st) {
   // GROUPA items (all items of a single group) accumulate value + virial: one partial record per block
   launch_one<K, PBC, true>(a, pbc, sw, work, zero_dev, a.two_groups ? split_dev : total_dev, bound_a, st);
-  if (a.two_groups) launch_one<K, PBC, false>(a, pbc, sw, work, split_dev, total_dev, bound_b, st);
+  // scatter_b: the GROUPA rows have added +dd to their partners; the virial is complete (df d (x) d per pair)
+  if (a.two_groups && !a.scatter_b) launch_one<K, PBC, false>(a, pbc, sw, work, split_dev, total_dev, bound_b, st);
   return (int)bound_a;
 }
 

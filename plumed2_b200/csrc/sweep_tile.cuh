@@ -162,7 +162,25 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
         const unsigned long long wj = ((unsigned long long)pj.slot << 32) | pj.abs_index;
         const bool valid = (wj != wi) && (!a.check_abs || pj.abs_index != pi.abs_index);
         const bool flip = a.two_groups ? (my_grp == 1u) : (pi.slot > pj.slot);
-        if (valid) pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
+        if (valid) {
+          if (ACC && a.scatter_b) {
+            // few GROUPA atoms among many GROUPB atoms (kernels.cuh: scatter_b): this GROUPA row hands +dd to its
+            // partner (deriv[i1] += dd, CoordinationBase.cpp:201) and the GROUPB rows are not swept
+            double tx = 0.0, ty = 0.0, tz = 0.0;
+            pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, tx, ty, tz, acc);
+            fx += tx;
+            fy += ty;
+            fz += tz;
+            if (tx != 0.0 || ty != 0.0 || tz != 0.0) {
+              double* dj = a.sderiv + 3 * (size_t)a.inv[pj.slot];
+              atomicAdd(dj, -tx);
+              atomicAdd(dj + 1, -ty);
+              atomicAdd(dj + 2, -tz);
+            }
+          } else {
+            pair_term<K, PBC, ACC, true>(pbc, sw, unused_near, pi.x, pi.y, pi.z, pj, flip, fx, fy, fz, acc);
+          }
+        }
       }
       fx = warp_sum(fx);
       fy = warp_sum(fy);

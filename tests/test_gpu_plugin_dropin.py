@@ -196,3 +196,28 @@ def test_plumed_driver_cli(tmp_path):
     assert np.all(np.abs(rows[:, 3]) <= 1e-10 * np.abs(rows[:, 1]))
     der = np.loadtxt(tmp_path / "DERIV", comments="#")
     assert rel_err(der[:, 3], der[:, 2]) <= 1e-10
+
+
+def test_top_level_d_max_keeps_every_digit():
+    """the plugin's additive top-level D_MAX (cudaCoord semantics) builds `RATIONAL R_0= D_0= NN= MM= D_MAX=` from the
+    parsed doubles: values that need more than six decimals must arrive intact (the same line through the CPU action's
+    SWITCH={...} form is the reference)"""
+    _need()
+    n = 1500
+    frames, box = trajectory(n, 4, seed=23)
+    outs = []
+    for load in (False, True):
+        body = ("GROUPA=1-%d R_0=0.2512345678 D_0=0.0000004321 NN=6 MM=12 D_MAX=0.7654321987" % n) if load else \
+               ("GROUPA=1-%d SWITCH={RATIONAL R_0=0.2512345678 D_0=0.0000004321 NN=6 MM=12 D_MAX=0.7654321987}" % n)
+        pre = ["LOAD FILE=" + PLUGIN] if load else []
+        p = R.Plumed(n, pre + ["c: COORDINATION " + body, "RESTRAINT ARG=c AT=100 KAPPA=0.01 SLOPE=0.5"], watch=("c",),
+                     log="/tmp/plumed_dmax_%d.log" % load)
+        res = []
+        for step, pos in enumerate(frames):
+            r = p.calc(step, pos, box)
+            r["values"] = {"c": p.value("c")}
+            res.append(r)
+        p.close()
+        outs.append(res)
+    compare(outs[0], outs[1])
+    assert "on CUDA device" in open("/tmp/plumed_dmax_1.log").read() or "on the current CUDA device" in open("/tmp/plumed_dmax_1.log").read()
