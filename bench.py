@@ -181,7 +181,33 @@ def pin_to_gpu_numa_node(local):
             return node
     except Exception:
         pass
-    return None
+    return _pin_from_topo(local)
+
+
+def _pin_from_topo(local):
+    """sysfs has no NUMA node for the device (containers, VMs): take the CPU / NUMA affinity `nvidia-smi topo -m` prints"""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        lines = [l for l in out.splitlines() if l.strip()]
+        hdr = next(l for l in lines if "CPU Affinity" in l)
+        cols = [c.strip() for c in hdr.split("\t")]
+        row = next(l for l in lines if l.split("\t")[0].strip() == "GPU%d" % local)
+        cells = [c.strip() for c in row.split("\t")]
+        # the header has one leading empty cell per row label
+        off = len(cells) - len(cols)
+        cpu_aff = cells[cols.index("CPU Affinity") + off]
+        numa = cells[cols.index("NUMA Affinity") + off] if "NUMA Affinity" in cols else None
+        cpus = set()
+        for part in cpu_aff.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return "numa %s (cpus %s, nvidia-smi topo)" % (numa, cpu_aff)
+        return "numa %s (cpus %s, nvidia-smi topo; not narrower than the current affinity)" % (numa, cpu_aff)
+    except Exception:
+        return None
 
 
 def pinned_array(L, shape):

@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): one process per GPU, i-atoms sharded by rank,
-positions all-gathered and derivative rows all-gathered + value/virial all-reduced over NCCL inside the library.
+positions and derivative rows exchanged inside the library -- NCCL all-gathers, or (peer-pull) NVLink peer memory: rows
+pulled by the rank that returns them, positions pulled by the gather on steps that keep the list -- value/virial all-reduced.
 Every rank must end up with the single-GPU result (= the oracle's) for its slice."""
 import ctypes as C
 import os
@@ -81,12 +82,12 @@ def _worker(rank, world, port, out_dir, peer):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", [False, True], ids=["nccl-allgather", "peer-stores"])
-def test_two_gpu_distributed_step_matches_oracle(tmp_path, peer):
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl-allgather", "peer-pull"])
+def test_multi_gpu_distributed_step_matches_oracle(tmp_path, peer, world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
     import torch.multiprocessing as mp
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), peer), nprocs=world, join=True)
     _, box = water_box(6000, 100.0, seed=31, triclinic=True)
     for li, line in enumerate(LINES):
