@@ -498,7 +498,21 @@ def e2e_run(E, c, frames, step, W, K, sampler):
     E.barrier()
     e2e_ms = E.allmax(max(float(ms.value), wall_ms))
     pairs = E.allsum(float(c.stats()["nl_size"]))
+    # what the copies alone cost on this box: the same H2D + D2H per step on every rank at once, no kernels in between
+    scratch = C.c_void_p()
+    capi.check(L.b200coord_device_alloc(max(cnt, 1) * 24, C.byref(scratch)))
+    E.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        capi.check(L.b200coord_memcpy_h2d(scratch, h_frames[i % F].ctypes.data_as(C.c_void_p), cnt * 24))
+        capi.check(L.b200coord_memcpy_d2h(h_deriv.ctypes.data_as(C.c_void_p), scratch, cnt * 24))
+    copy_ms = E.allmax(1e3 * (time.perf_counter() - t0)) / K
+    E.barrier()
+    L.b200coord_device_free(scratch)
     res = {"value": pairs * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
+           "copies_alone_ms_per_step": copy_ms,
+           "copies_alone_note": "the same %d-byte upload + download per rank and step with nothing in between, all ranks at "
+                                "once: the share of e2e that is the host <-> device link of this box" % (cnt * 24),
            "h2d_bytes_per_step": int(cnt * 24), "d2h_bytes_per_step": int(cnt * 24 + 80),
            "api": "b200coord_calculate_distributed" if E.world > 1 else "b200coord_calculate",
            "numa_node_of_rank0": E.numa_node}

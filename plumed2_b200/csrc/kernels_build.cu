@@ -672,6 +672,9 @@ __global__ void __launch_bounds__(256, 3)
   float4 l1 = __ldg(lpos + (c1 & kSuperIndexMask)), l2 = __ldg(lpos + (c2 & kSuperIndexMask));
   uint32_t n1 = entry_at(64), n2 = entry_at(96);
   for (uint32_t e0 = 0; e0 < m; e0 += 64) {
+    // the entries stream from HBM and a warp only lives for ~9 trips: ask L2 for the piece four trips down the row
+    // (8 bytes per lane cover its 256 bytes; past the end of the row the request is harmless)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(srow + e0 + 256u + lane));
     const uint32_t a1 = c1, a2 = c2;
     const float4 p1 = l1, p2 = l2;
     c1 = n1;
