@@ -427,6 +427,25 @@ def test_config3_solute_solvent_triclinic_exp():
     b.close()
 
 
+def test_one_million_atoms_full_oracle_comparison():
+    """headline size, the whole thing: value, 3 M derivatives and virial of 1 M atoms against the oracle (its O(N) list on all
+    host cores), on the rebuild step and on a step of the drifting trajectory that keeps the list; pair count from the list"""
+    n = 1000000
+    pos, box = water_box(n, 100.0, seed=123)
+    line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=10" % n
+    c = gpu_eval(line, pos, box)
+    ref = oracle_from_line(line, pos, box, nthreads=NCPU, fast_list=True)
+    assert_parity(c, ref, "1M rebuild step")
+    assert c.stats()["nl_size"] == ref["pairs"].shape[0]
+    del ref
+    pos2 = pos + 0.004 * np.random.default_rng(2).standard_normal(pos.shape)
+    pos2[::9] += box[1]  # the MD engine re-wrapped some molecules
+    assert c.prepare(3) is False
+    c.calculate(pos2, box)
+    assert_parity(c, oracle_from_line(line, pos2, box, list_positions=pos, nthreads=NCPU, fast_list=True), "1M frozen list")
+    c.close()
+
+
 def test_one_million_atoms_properties():
     """headline size (1M atoms, NLIST): properties that need no O(N) oracle run"""
     n = 1000000
