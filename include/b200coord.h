@@ -223,6 +223,28 @@ int b200coord_comm_init(b200coord_ctx* ctx, const char id[B200COORD_UNIQUE_ID_BY
 int b200coord_peer_export(b200coord_ctx* ctx, char handle[B200COORD_PEER_HANDLE_BYTES]);
 int b200coord_peer_attach(b200coord_ctx* ctx, const char* all_handles /* nranks * B200COORD_PEER_HANDLE_BYTES */);
 
+/* the same for contexts that live in ONE process (no IPC): all[r] = the context of rank r, after every context has
+ * called b200coord_comm_init and b200coord_peer_export */
+int b200coord_peer_attach_local(b200coord_ctx* ctx, b200coord_ctx* const* all, int n);
+
+/* ---- several GPUs inside one process (a `plumed driver` run, an MD engine without MPI): one context per device, one
+ * worker thread per context, the i-atoms sharded over them exactly like MPI ranks (CoordinationBase.cpp:152-170), the
+ * Comm::Sum of :218-224 done by NCCL + NVLink peer memory as above.  Same call sequence as a single context; the
+ * positions / derivatives are the whole host arrays, every device uploads and returns its own slice of them.
+ * cfg->device, cfg->rank and cfg->nranks are ignored.  PAIR style: one device only. */
+typedef struct b200coord_group b200coord_group;
+int b200coord_group_create(const b200coord_config* cfg, const b200coord_switch* sw, const unsigned* abs_index,
+                           const int* devices, int ndevices, b200coord_group** out);
+void b200coord_group_destroy(b200coord_group* g);
+int b200coord_group_size(const b200coord_group* g);
+b200coord_ctx* b200coord_group_context(b200coord_group* g, int rank);   /* for b200coord_get_stats etc. */
+const char* b200coord_group_last_error(const b200coord_group* g);
+int b200coord_group_set_box(b200coord_group* g, const double box[9]);
+int b200coord_group_prepare(b200coord_group* g, long step, int exchange_step, int* will_rebuild);
+int b200coord_group_set_charges(b200coord_group* g, const double* charges);
+int b200coord_group_set_types(b200coord_group* g, const unsigned* types, unsigned ntypes, const double* etas);
+int b200coord_group_calculate(b200coord_group* g, const double* pos, double* value, double* deriv, double* virial);
+
 /* ---- pinned host memory for callers that want full-speed copies */
 int b200coord_host_alloc(size_t bytes, void** ptr);
 int b200coord_host_free(void* ptr);

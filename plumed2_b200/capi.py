@@ -33,7 +33,10 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_measure_fp64_peak", "b200coord_peer_export", "b200coord_peer_attach",
             "b200coord_pairing_dhenergy", "b200coord_set_charges", "b200coord_pairing_ghbfix",
             "b200coord_set_types", "b200coord_device_count", "b200coord_enqueue_device_distributed",
-            "b200coord_nl_pairs_device"]
+            "b200coord_nl_pairs_device", "b200coord_peer_attach_local", "b200coord_group_create",
+            "b200coord_group_destroy", "b200coord_group_size", "b200coord_group_context", "b200coord_group_last_error",
+            "b200coord_group_set_box", "b200coord_group_prepare", "b200coord_group_set_charges",
+            "b200coord_group_set_types", "b200coord_group_calculate"]
 
 
 class B200CoordError(RuntimeError):
@@ -118,6 +121,20 @@ def lib():
     L.b200coord_device_count.argtypes = [C.POINTER(C.c_int)]
     L.b200coord_enqueue_device_distributed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200coord_nl_pairs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    L.b200coord_group_create.argtypes = [C.POINTER(Config), C.POINTER(Switch), C.POINTER(C.c_uint), C.POINTER(C.c_int), C.c_int,
+                                         C.POINTER(C.c_void_p)]
+    L.b200coord_group_destroy.argtypes = [C.c_void_p]
+    L.b200coord_group_destroy.restype = None
+    L.b200coord_group_size.argtypes = [C.c_void_p]
+    L.b200coord_group_context.argtypes = [C.c_void_p, C.c_int]
+    L.b200coord_group_context.restype = C.c_void_p
+    L.b200coord_group_last_error.argtypes = [C.c_void_p]
+    L.b200coord_group_last_error.restype = C.c_char_p
+    L.b200coord_group_set_box.argtypes = [C.c_void_p, dp]
+    L.b200coord_group_prepare.argtypes = [C.c_void_p, C.c_long, C.c_int, C.POINTER(C.c_int)]
+    L.b200coord_group_set_charges.argtypes = [C.c_void_p, dp]
+    L.b200coord_group_set_types.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_uint, dp]
+    L.b200coord_group_calculate.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_void_p, dp]
     L.b200coord_peer_export.argtypes = [C.c_void_p, C.c_char_p]
     L.b200coord_peer_attach.argtypes = [C.c_void_p, C.c_char_p]
     if L.b200coord_abi_version() != ABI_VERSION:

@@ -14,7 +14,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace b200;
@@ -180,6 +185,7 @@ struct b200coord_ctx {
   ncclComm_t comm = nullptr;
   // fused exchange over peer memory: two row buffers (step parity) per rank, mapped into every process
   bool peer_mode = false;
+  bool peer_ipc = false;              // peer pointers came from cudaIpcOpenMemHandle (other processes), not from this process
   DevBuf<double> d_sderiv_b;          // second parity buffer (d_sderiv is the first)
   double* peer_rows[2][8] = {{nullptr}};  // [parity][rank], own entries point at the local buffers
   unsigned parity = 0;
@@ -1303,11 +1309,11 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
   c->d_rowstart.release(); c->d_bsum.release(); c->d_u64.release(); c->d_spos.release(); c->d_active.release(); c->d_params.release(); c->d_lpos.release(); c->d_capinfo.release(); c->d_rowfar.release(); c->d_bpos.release(); c->d_meta.release(); c->d_srowstart.release(); c->d_srowcount.release(); c->d_snbr.release(); c->d_wpos.release(); c->d_braw.release(); c->d_q.release(); c->d_sq.release(); c->d_types.release(); c->d_stype.release(); c->d_etas.release();
-  if (c->peer_mode)
+  if (c->peer_mode && c->peer_ipc)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
         if (r != c->cfg.rank && c->peer_rows[par][r]) cudaIpcCloseMemHandle(c->peer_rows[par][r]);
-  if (c->peer_mode)
+  if (c->peer_mode && c->peer_ipc)
     for (int par = 0; par < 2; ++par)
       for (int r = 0; r < c->cfg.nranks && r < 8; ++r)
         if (r != c->cfg.rank && c->peer_pos[par][r]) cudaIpcCloseMemHandle(c->peer_pos[par][r]);
@@ -1480,6 +1486,8 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   CU(c, cudaSetDevice(c->device));
   const size_t off = 3 * (size_t)c->slot_begin, cnt = 3 * (size_t)c->slot_count;
   const bool sliced = (c->cfg.style != B200COORD_STYLE_PAIR);
+  maybe_pin(c, 0, pos_slice, sizeof(double) * cnt);
+  maybe_pin(c, 1, deriv_slice, sizeof(double) * cnt);
   int rc;
   CU(c, cudaEventRecord(c->ev[0], c->st));
   if (step_can_pull(c)) {
@@ -1788,7 +1796,196 @@ int b200coord_peer_attach(b200coord_ctx* c, const char* all) {
     }
   }
   c->peer_mode = true;
+  c->peer_ipc = true;
   c->parity = 0;
+  return B200COORD_OK;
+}
+
+int b200coord_peer_attach_local(b200coord_ctx* c, b200coord_ctx* const* all, int n) {
+  if (!c || !all) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->comm) return fail(c, B200COORD_ERR_STATE, "b200coord_comm_init must come first");
+  if (n != c->cfg.nranks || n > 8) return fail(c, B200COORD_ERR_INVALID, "peer exchange supports up to 8 ranks");
+  CU(c, cudaSetDevice(c->device));
+  for (int r = 0; r < n; ++r) {
+    b200coord_ctx* o = all[r];
+    if (!o || !o->d_sderiv_b.p || !o->d_pslice[0].p) return fail(c, B200COORD_ERR_STATE, "b200coord_peer_export must come first on every context");
+    if (r != c->cfg.rank && o->device != c->device) {
+      int can = 0;
+      CU(c, cudaDeviceCanAccessPeer(&can, c->device, o->device));
+      if (!can) return fail(c, B200COORD_ERR_CUDA, "the devices of this group cannot access each other's memory");
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(c, B200COORD_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    c->peer_rows[0][r] = o->d_sderiv.p;
+    c->peer_rows[1][r] = o->d_sderiv_b.p;
+    c->peer_pos[0][r] = o->d_pslice[0].p;
+    c->peer_pos[1][r] = o->d_pslice[1].p;
+  }
+  c->peer_mode = true;
+  c->peer_ipc = false;
+  c->parity = 0;
+  return B200COORD_OK;
+}
+
+// ================================================================================================
+// Several GPUs inside ONE process: one context per device, one worker thread per context (NCCL collectives need every
+// rank to enqueue concurrently), i-atoms sharded over them like MPI ranks (CoordinationBase.cpp:152-170).
+struct b200coord_group {
+  std::vector<b200coord_ctx*> ctx;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<int(int)> task;
+  unsigned long epoch = 0;
+  int pending = 0;
+  bool quit = false;
+  std::vector<int> rc;
+  std::string err;
+  unsigned n = 0;
+};
+
+namespace {
+void group_worker(b200coord_group* g, int r) {
+  unsigned long seen = 0;
+  for (;;) {
+    std::function<int(int)> fn;
+    {
+      std::unique_lock<std::mutex> lk(g->mu);
+      g->cv_go.wait(lk, [&] { return g->quit || g->epoch != seen; });
+      if (g->quit) return;
+      seen = g->epoch;
+      fn = g->task;
+    }
+    const int rc = fn(r);
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->rc[r] = rc;
+      if (--g->pending == 0) g->cv_done.notify_all();
+    }
+  }
+}
+// run fn(rank) on every worker, wait for all; first non-zero code wins
+int group_run(b200coord_group* g, std::function<int(int)> fn) {
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->task = std::move(fn);
+    g->pending = (int)g->ctx.size();
+    g->epoch++;
+  }
+  g->cv_go.notify_all();
+  std::unique_lock<std::mutex> lk(g->mu);
+  g->cv_done.wait(lk, [&] { return g->pending == 0; });
+  for (size_t r = 0; r < g->ctx.size(); ++r)
+    if (g->rc[r]) {
+      g->err = "rank " + std::to_string(r) + ": " + (g->ctx[r] ? g->ctx[r]->err : g_last_error);
+      return g->rc[r];
+    }
+  return B200COORD_OK;
+}
+}  // namespace
+
+int b200coord_group_create(const b200coord_config* cfg, const b200coord_switch* sw, const unsigned* abs_index,
+                           const int* devices, int ndevices, b200coord_group** out) {
+  if (!cfg || !sw || !devices || !out) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (ndevices < 1 || ndevices > 8) return fail(nullptr, B200COORD_ERR_INVALID, "a group holds 1 to 8 devices");
+  if (cfg->style == B200COORD_STYLE_PAIR && ndevices > 1)
+    return fail(nullptr, B200COORD_ERR_INVALID, "PAIR style runs on one device");
+  auto g = std::make_unique<b200coord_group>();
+  g->ctx.assign((size_t)ndevices, nullptr);
+  g->rc.assign((size_t)ndevices, 0);
+  g->n = cfg->n_group_a + cfg->n_group_b;
+  for (int r = 0; r < ndevices; ++r) {
+    b200coord_config c = *cfg;
+    c.device = devices[r];
+    c.rank = r;
+    c.nranks = ndevices;
+    const int rc = b200coord_create(&c, sw, abs_index, &g->ctx[(size_t)r]);
+    if (rc) {
+      for (auto* x : g->ctx) b200coord_destroy(x);
+      return rc;
+    }
+  }
+  for (int r = 0; r < ndevices; ++r) g->workers.emplace_back(group_worker, g.get(), r);
+  b200coord_group* gp = g.release();
+  if (ndevices > 1) {
+    char id[B200COORD_UNIQUE_ID_BYTES];
+    int rc = b200coord_comm_unique_id(id);
+    if (!rc) rc = group_run(gp, [&](int r) { return b200coord_comm_init(gp->ctx[(size_t)r], id); });
+    char scratch[8][B200COORD_PEER_HANDLE_BYTES];
+    if (!rc) rc = group_run(gp, [&](int r) { return b200coord_peer_export(gp->ctx[(size_t)r], scratch[r]); });
+    if (!rc) rc = group_run(gp, [&](int r) { return b200coord_peer_attach_local(gp->ctx[(size_t)r], gp->ctx.data(), (int)gp->ctx.size()); });
+    if (rc) {
+      g_last_error = gp->err;
+      b200coord_group_destroy(gp);
+      return rc;
+    }
+  }
+  *out = gp;
+  return B200COORD_OK;
+}
+
+void b200coord_group_destroy(b200coord_group* g) {
+  if (!g) return;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->quit = true;
+  }
+  g->cv_go.notify_all();
+  for (auto& t : g->workers) t.join();
+  for (auto* c : g->ctx)
+    if (c && c->st) {
+      cudaSetDevice(c->device);
+      cudaStreamSynchronize(c->st);
+    }
+  for (auto* c : g->ctx) b200coord_destroy(c);
+  delete g;
+}
+
+int b200coord_group_size(const b200coord_group* g) { return g ? (int)g->ctx.size() : 0; }
+b200coord_ctx* b200coord_group_context(b200coord_group* g, int rank) {
+  return (g && rank >= 0 && rank < (int)g->ctx.size()) ? g->ctx[(size_t)rank] : nullptr;
+}
+const char* b200coord_group_last_error(const b200coord_group* g) { return g ? g->err.c_str() : g_last_error.c_str(); }
+
+int b200coord_group_set_box(b200coord_group* g, const double box[9]) {
+  if (!g) return B200COORD_ERR_INVALID;
+  for (auto* c : g->ctx) {
+    const int rc = b200coord_set_box(c, box);
+    if (rc) { g->err = c->err; return rc; }
+  }
+  return B200COORD_OK;
+}
+int b200coord_group_prepare(b200coord_group* g, long step, int exchange_step, int* will_rebuild) {
+  if (!g) return B200COORD_ERR_INVALID;
+  int rc = B200COORD_OK;
+  for (auto* c : g->ctx) {
+    const int r = b200coord_prepare(c, step, exchange_step, will_rebuild);
+    if (r) { g->err = c->err; rc = r; }
+  }
+  return rc;
+}
+int b200coord_group_set_charges(b200coord_group* g, const double* charges) {
+  if (!g) return B200COORD_ERR_INVALID;
+  return group_run(g, [&](int r) { return b200coord_set_charges(g->ctx[(size_t)r], charges); });
+}
+int b200coord_group_set_types(b200coord_group* g, const unsigned* types, unsigned ntypes, const double* etas) {
+  if (!g) return B200COORD_ERR_INVALID;
+  return group_run(g, [&](int r) { return b200coord_set_types(g->ctx[(size_t)r], types, ntypes, etas); });
+}
+int b200coord_group_calculate(b200coord_group* g, const double* pos, double* value, double* deriv, double* virial) {
+  if (!g || !pos || !value || !deriv || !virial) return B200COORD_ERR_INVALID;
+  if (g->ctx.size() == 1) return b200coord_calculate(g->ctx[0], pos, value, deriv, virial);
+  double vals[8] = {0}, virs[8][9];
+  const int rc = group_run(g, [&](int r) {
+    b200coord_ctx* c = g->ctx[(size_t)r];
+    return b200coord_calculate_distributed(c, pos + 3 * (size_t)c->slot_begin, &vals[r], deriv + 3 * (size_t)c->slot_begin, virs[r]);
+  });
+  if (rc) return rc;
+  *value = vals[0];  // every rank holds the all-reduced value and virial
+  for (int i = 0; i < 9; ++i) virial[i] = virs[0][i];
   return B200COORD_OK;
 }
 

@@ -33,6 +33,7 @@ namespace colvar {
 class CoordinationBaseB200 : public Colvar {
 protected:
   b200coord_ctx* ctx = nullptr;
+  b200coord_group* group = nullptr;  // GPU_DEVICES=0,1,...: one context per device inside this process
   bool needCharges = false;
   bool pbc = true;
   bool serial = false;
@@ -89,6 +90,7 @@ void CoordinationBaseB200::registerKeywords(Keywords& keys) {
   keys.add("atoms", "GROUPA", "First list of atoms");
   keys.add("atoms", "GROUPB", "Second list of atoms (if empty, N*(N-1)/2 pairs in GROUPA are counted)");
   keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
+  keys.add("optional", "GPU_DEVICES", "comma separated CUDA device ordinals: shard the i-atoms over several GPUs of this node inside this process (NCCL + NVLink peer memory); not with PAIR, not together with several MPI ranks");
   keys.addFlag("GPU_FP32", false, "opt-in FP32 pair arithmetic (1e-5 relative instead of 1e-10; FP64 minimum image and accumulation). Also switched on by the B200COORD_FP32=1 environment variable");
 }
 
@@ -125,7 +127,7 @@ void GHBFIXB200::registerKeywords(Keywords& keys) {  // GHBFIX.cpp:91-103
 
 void CoordinationBaseB200::check(int rc, const char* what) {
   if (rc != B200COORD_OK) {
-    error(std::string(what) + " failed on the GPU: " + b200coord_last_error(ctx));
+    error(std::string(what) + " failed on the GPU: " + (group ? b200coord_group_last_error(group) : b200coord_last_error(ctx)));
   }
 }
 
@@ -253,7 +255,8 @@ GHBFIXB200::GHBFIXB200(const ActionOptions& ao) : Action(ao), CoordinationBaseB2
                                          << " atoms, but you are trying to access atom number " << (a + 1);
     mine[i] = typesTable[a];
   }
-  check(b200coord_set_types(ctx, mine.data(), nt, etas.data()), "set_types");
+  check(group ? b200coord_group_set_types(group, mine.data(), nt, etas.data()) : b200coord_set_types(ctx, mine.data(), nt, etas.data()),
+        "set_types");
   log.printf("  %u interaction types from %s, scaling parameters from %s\n", nt, types.c_str(), params.c_str());
 }
 
@@ -313,6 +316,22 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
     }
   }
   parse("GPU_DEVICE", device);
+  std::vector<int> devices;
+  {
+    std::string list;
+    parse("GPU_DEVICES", list);
+    std::size_t at = 0;
+    while (at < list.size()) {
+      std::size_t comma = list.find(',', at);
+      if (comma == std::string::npos) {
+        comma = list.size();
+      }
+      if (comma > at) {
+        devices.push_back(std::atoi(list.substr(at, comma - at).c_str()));
+      }
+      at = comma + 1;
+    }
+  }
   bool fp32 = false;
   if (const char* env = std::getenv("B200COORD_FP32")) {
     fp32 = std::atoi(env) != 0;
@@ -351,9 +370,25 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   combineWithMpi = !serial && comm.Get_size() > 1;
   cfg.rank = combineWithMpi ? comm.Get_rank() : 0;
   cfg.nranks = combineWithMpi ? comm.Get_size() : 1;
-  const int rc = b200coord_create(&cfg, &sw, absIndex.data(), &ctx);
-  if (rc != B200COORD_OK) {
-    error(std::string("cannot set up the B200 ") + what + " engine: " + b200coord_last_error(nullptr));
+  if (devices.size() > 1) {
+    if (combineWithMpi) {
+      error("GPU_DEVICES shards the atoms over the GPUs of one process; with several MPI ranks give each rank one device (GPU_DEVICE)");
+    }
+    if (dopair) {
+      error("GPU_DEVICES is not available with PAIR");
+    }
+    const int rc = b200coord_group_create(&cfg, &sw, absIndex.data(), devices.data(), static_cast<int>(devices.size()), &group);
+    if (rc != B200COORD_OK) {
+      error(std::string("cannot set up the B200 ") + what + " engine on the given GPU_DEVICES: " + b200coord_last_error(nullptr));
+    }
+  } else {
+    if (devices.size() == 1) {
+      cfg.device = device = devices[0];
+    }
+    const int rc = b200coord_create(&cfg, &sw, absIndex.data(), &ctx);
+    if (rc != B200COORD_OK) {
+      error(std::string("cannot set up the B200 ") + what + " engine: " + b200coord_last_error(nullptr));
+    }
   }
   derivBuffer.resize(3 * all.size());
   requestAtoms(all);
@@ -364,7 +399,10 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   char desc[512];
   b200coord_switch_describe(&sw, desc, sizeof(desc));
   log.printf("  B200-native %s (libb200coord, sm_100a kernels)\n", what);
-  if (device >= 0) {
+  if (group) {
+    log.printf("  i-atoms sharded over %d CUDA devices of this process (GPU_DEVICES), derivative rows and positions exchanged over NVLink peer memory\n",
+               b200coord_group_size(group));
+  } else if (device >= 0) {
     log.printf("  on CUDA device %d%s\n", device, deviceFromRank ? " (local MPI rank modulo visible devices)" : "");
   } else {
     log.printf("  on the current CUDA device\n");
@@ -393,6 +431,7 @@ CoordinationBaseB200::~CoordinationBaseB200() {
     std::fprintf(stderr, "B200COORD plugin timers: %lu calls, engine %.3f ms/call, store-to-Value %.3f ms/call\n", nCalls,
                  1e3 * tEngine / nCalls, 1e3 * tStore / nCalls);
   }
+  b200coord_group_destroy(group);
   b200coord_destroy(ctx);
 }
 
@@ -400,9 +439,10 @@ void CoordinationBaseB200::prepare() {
   // NeighborList::prepare (src/tools/NeighborList.cpp:433-456); the full atom list stays requested on
   // every step (legal: the reduced list is only a communication optimisation of the CPU code)
   int willRebuild = 0;
-  const int rc = b200coord_prepare(ctx, static_cast<long>(getStep()), getExchangeStep() ? 1 : 0, &willRebuild);
+  const int rc = group ? b200coord_group_prepare(group, static_cast<long>(getStep()), getExchangeStep() ? 1 : 0, &willRebuild)
+                       : b200coord_prepare(ctx, static_cast<long>(getStep()), getExchangeStep() ? 1 : 0, &willRebuild);
   if (rc != B200COORD_OK) {
-    error(b200coord_last_error(ctx));
+    error(group ? b200coord_group_last_error(group) : b200coord_last_error(ctx));
   }
 }
 
@@ -416,7 +456,8 @@ void CoordinationBaseB200::calculate() {
       changed = changed || chargeBuffer[i] != chargeSent[i];
     }
     if (changed) {
-      check(b200coord_set_charges(ctx, chargeBuffer.data()), "set_charges");
+      check(group ? b200coord_group_set_charges(group, chargeBuffer.data()) : b200coord_set_charges(ctx, chargeBuffer.data()),
+            "set_charges");
       chargeSent = chargeBuffer;
     }
   }
@@ -426,12 +467,14 @@ void CoordinationBaseB200::calculate() {
     for (unsigned j = 0; j < 3; ++j) {
       box[3 * i + j] = b[i][j];
     }
-  check(b200coord_set_box(ctx, box), "set_box");
+  check(group ? b200coord_group_set_box(group, box) : b200coord_set_box(ctx, box), "set_box");
   double value = 0.0;
   double virial[9];
   const double* pos = n ? &getPositions()[0][0] : nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  check(b200coord_calculate(ctx, pos, &value, derivBuffer.data(), virial), "calculate");
+  check(group ? b200coord_group_calculate(group, pos, &value, derivBuffer.data(), virial)
+              : b200coord_calculate(ctx, pos, &value, derivBuffer.data(), virial),
+        "calculate");
   if (combineWithMpi) {
     comm.Sum(value);
     comm.Sum(derivBuffer);

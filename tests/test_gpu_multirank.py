@@ -105,3 +105,49 @@ def test_multi_gpu_distributed_step_matches_oracle(tmp_path, peer, world):
                 assert rel_err(p["virial"], ref["virial"]) <= 1e-10
                 full[int(p["lo"]):int(p["lo"]) + int(p["cnt"])] = p["deriv"]
             assert rel_err(full, ref["deriv"]) <= 1e-10, (line, step)
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_group_of_devices_in_one_process(ndev):
+    """b200coord_group_*: several GPUs inside ONE process (what the plugin's GPU_DEVICES keyword uses): worker thread per
+    device, NCCL + peer memory between the contexts of this process.  Rebuild steps, steps that keep the list (positions
+    pulled over NVLink), two groups; against the oracle."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    import plumed2_b200 as P
+    from plumed2_b200 import capi
+    L = capi.lib()
+    n = 9000
+    pos0, box = water_box(n, 100.0, seed=51, triclinic=True)
+    for line in ["c: COORDINATION GROUPA=1-9000 SWITCH={RATIONAL R_0=0.3 NN=6 MM=12 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+                 "c: COORDINATION GROUPA=1-3000 GROUPB=3001-9000 SWITCH={EXP R_0=0.2 D_MAX=0.8} NLISTCELLS NL_CUTOFF=0.9 NL_STRIDE=2"]:
+        single = P.Coordination.from_input(line, device=0)  # borrows the parsed config / switch
+        cfg = capi.Config.from_buffer_copy(single._cfg)
+        devs = (C.c_int * ndev)(*range(ndev))
+        g = C.c_void_p()
+        absidx = np.ascontiguousarray(single.atoms)
+        capi.check(L.b200coord_group_create(C.byref(cfg), C.byref(single.switch), absidx.ctypes.data_as(C.POINTER(C.c_uint)),
+                                            devs, ndev, C.byref(g)))
+        assert L.b200coord_group_size(g) == ndev
+        rng = np.random.default_rng(4)
+        pos, list_pos = pos0.copy(), None
+        b9 = np.ascontiguousarray(box.reshape(9))
+        for step in range(6):
+            pos = pos + 0.006 * rng.standard_normal(pos.shape)
+            will = C.c_int(0)
+            assert L.b200coord_group_prepare(g, step, 0, C.byref(will)) == 0
+            if will.value or list_pos is None:
+                list_pos = pos.copy()
+            assert L.b200coord_group_set_box(g, b9.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            der = np.zeros((n, 3))
+            vir = np.zeros(9)
+            val = C.c_double(0)
+            p = np.ascontiguousarray(pos)
+            rc = L.b200coord_group_calculate(g, p.ctypes.data_as(C.c_void_p), C.byref(val), der.ctypes.data_as(C.c_void_p),
+                                             vir.ctypes.data_as(C.POINTER(C.c_double)))
+            assert rc == 0, L.b200coord_group_last_error(g)
+            ref = oracle_from_line(line, pos, box, list_positions=list_pos)
+            assert abs(val.value - ref["value"]) <= 1e-10 * abs(ref["value"]), (line, step)
+            assert rel_err(der, ref["deriv"]) <= 1e-10 and rel_err(vir.reshape(3, 3), ref["virial"]) <= 1e-10, (line, step)
+        L.b200coord_group_destroy(g)
+        single.close()

@@ -221,3 +221,29 @@ def test_top_level_d_max_keeps_every_digit():
         outs.append(res)
     compare(outs[0], outs[1])
     assert "on CUDA device" in open("/tmp/plumed_dmax_1.log").read() or "on the current CUDA device" in open("/tmp/plumed_dmax_1.log").read()
+
+
+def test_gpu_devices_keyword_shards_one_process_over_two_gpus():
+    """GPU_DEVICES=0,1 on the input line: `plumed driver`-style single process, the plugin shards the i-atoms over two
+    devices (b200coord_group_*).  Same numbers as the reference's CPU action, forces and virial included."""
+    _need()
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 6000
+    frames, box = trajectory(n, 6, seed=29, triclinic=True)
+    outs = []
+    for load in (False, True):
+        body = "GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3" % n
+        pre = ["LOAD FILE=" + PLUGIN] if load else []
+        p = R.Plumed(n, pre + ["c: COORDINATION " + body + (" GPU_DEVICES=0,1" if load else ""),
+                               "RESTRAINT ARG=c AT=100 KAPPA=0.01 SLOPE=0.5"], watch=("c",), log="/tmp/plumed_devs_%d.log" % load)
+        res = []
+        for step, pos in enumerate(frames):
+            r = p.calc(step, pos, box)
+            r["values"] = {"c": p.value("c")}
+            res.append(r)
+        p.close()
+        outs.append(res)
+    compare(outs[0], outs[1])
+    assert "sharded over 2 CUDA devices" in open("/tmp/plumed_devs_1.log").read()
