@@ -9,6 +9,8 @@
 // on the host; if the CUDA library reports an error the action calls error().
 #include "b200coord.h"
 #include "core/ActionRegister.h"
+#include "core/ActionSet.h"
+#include "core/ActionToPutData.h"
 #include "core/Colvar.h"
 #include "core/PlumedMain.h"
 #include "tools/Communicator.h"
@@ -44,6 +46,18 @@ protected:
   double tEngine = 0.0, tStore = 0.0;
   unsigned long nCalls = 0;
   void check(int rc, const char* what);
+  // Host side of large systems.  PLUMED gathers the requested atoms (ActionAtomistic::retrieveAtoms) and scatters the
+  // forces (ActionWithValue::checkForForces + ActionAtomistic::setForcesOnAtoms) with serial loops: 6 ms + 8 ms per step
+  // at 1 M atoms, against a 1.5 ms GPU step.  When nothing else needs those arrays (no charges, no numerical derivatives,
+  // no virtual atoms, no atom listed twice) the action does both itself with OpenMP: it tells PLUMED not to retrieve
+  // (ActionAtomistic::doNotRetrieve, core/ActionAtomistic.h:169-176), reads the shared position values through
+  // getGlobalPosition() and adds f * derivative to the force arrays of posx / posy / posz with Value::addForce.
+  bool fastHost = false;
+  std::vector<std::pair<std::size_t, std::size_t>> valueIdx;
+  Value* posValue[3] = {nullptr, nullptr, nullptr};
+  std::vector<double> posBuffer;
+  double lastVirial[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  void setupFastHost();
 
   // group / list keywords and engine set-up; `sw` is the pairing the derived constructor parsed
   void setup(const b200coord_switch& sw, const char* what);
@@ -54,6 +68,7 @@ public:
   static void registerKeywords(Keywords& keys);
   void prepare() override;
   void calculate() override;
+  void apply() override;
 };
 
 class CoordinationB200 : public CoordinationBaseB200 {
@@ -392,6 +407,7 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
   }
   derivBuffer.resize(3 * all.size());
   requestAtoms(all);
+  setupFastHost();
   if (const char* env = std::getenv("B200COORD_PLUGIN_TIMERS")) {
     timers = std::atoi(env) != 0;
   }
@@ -424,6 +440,83 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
     log.printf("  update every %d steps and cutoff %f\n", nlStride, nlCut);
   }
   log << "  contacts are counted with cutoff " << desc << "\n";
+}
+
+void CoordinationBaseB200::setupFastHost() {
+  fastHost = false;
+  bool always = false;  // B200COORD_HOST_FAST: 0 = never, 1 (default) = from 50000 atoms on, 2 = always (tests)
+  if (const char* env = std::getenv("B200COORD_HOST_FAST")) {
+    if (std::atoi(env) == 0) {
+      return;
+    }
+    always = std::atoi(env) >= 2;
+  }
+  const unsigned n = getNumberOfAtoms();
+  if (needCharges || checkNumericalDerivatives() || n == 0 || (n < 50000 && !always)) {
+    return;  // small systems: PLUMED's own loops cost nothing
+  }
+  valueIdx.resize(n);
+  std::vector<std::size_t> seen(n);
+  for (unsigned i = 0; i < n; ++i) {
+    valueIdx[i] = getValueIndices(getAbsoluteIndex(i));
+    if (valueIdx[i].first != 0) {
+      return;  // a virtual atom: positions live in another action's values
+    }
+    seen[i] = valueIdx[i].second;
+  }
+  std::sort(seen.begin(), seen.end());
+  if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
+    return;  // an atom listed twice: the parallel scatter would race
+  }
+  const char* names[3] = {"posx", "posy", "posz"};
+  for (int k = 0; k < 3; ++k) {
+    ActionToPutData* a = plumed.getActionSet().selectWithLabel<ActionToPutData*>(names[k]);
+    if (!a || a->getNumberOfComponents() != 1) {
+      return;
+    }
+    posValue[k] = a->copyOutput(0);
+    if (!posValue[k] || posValue[k]->getRank() != 1) {
+      return;
+    }
+  }
+  posBuffer.resize(3 * static_cast<std::size_t>(n));
+  doNotRetrieve();
+  fastHost = true;
+  log.printf("  host side: atoms gathered and forces scattered by the action itself (OpenMP) instead of PLUMED's serial loops\n");
+}
+
+void CoordinationBaseB200::apply() {
+  if (!fastHost) {
+    Colvar::apply();
+    return;
+  }
+  Value* v = getPntrToValue();
+  if (!v->forcesWereAdded()) {
+    return;  // ActionWithValue::checkForForces: nobody pushed a force on the value
+  }
+  const double ff = v->getForce(0);
+  const long n = static_cast<long>(getNumberOfAtoms());
+  const double* d = derivBuffer.data();
+  Value* vx = posValue[0];
+  Value* vy = posValue[1];
+  Value* vz = posValue[2];
+  vx->addForce(valueIdx[0].second, 0.0, false);  // sets hasForce once, outside the parallel region
+  vy->addForce(valueIdx[0].second, 0.0, false);
+  vz->addForce(valueIdx[0].second, 0.0, false);
+  const unsigned nt = OpenMP::getNumThreads();
+  #pragma omp parallel for num_threads(nt) schedule(static)
+  for (long i = 0; i < n; ++i) {  // distinct atoms -> distinct elements of the three force arrays
+    const std::size_t kk = valueIdx[i].second;
+    vx->addForce(kk, ff * d[3 * i], false);
+    vy->addForce(kk, ff * d[3 * i + 1], false);
+    vz->addForce(kk, ff * d[3 * i + 2], false);
+  }
+  double f9[9];
+  for (int j = 0; j < 9; ++j) {
+    f9[j] = ff * lastVirial[j];
+  }
+  unsigned ind = 0;
+  setForcesOnCell(f9, 9, ind);
 }
 
 CoordinationBaseB200::~CoordinationBaseB200() {
@@ -471,6 +564,19 @@ void CoordinationBaseB200::calculate() {
   double value = 0.0;
   double virial[9];
   const double* pos = n ? &getPositions()[0][0] : nullptr;
+  if (fastHost) {  // the shared position values, read in parallel (retrieveAtoms was told not to)
+    double* pb = posBuffer.data();
+    const long nn = static_cast<long>(n);
+    const unsigned ntg = OpenMP::getNumThreads();
+    #pragma omp parallel for num_threads(ntg) schedule(static)
+    for (long i = 0; i < nn; ++i) {
+      const Vector p = getGlobalPosition(valueIdx[i]);
+      pb[3 * i] = p[0];
+      pb[3 * i + 1] = p[1];
+      pb[3 * i + 2] = p[2];
+    }
+    pos = pb;
+  }
   const auto t0 = std::chrono::steady_clock::now();
   check(group ? b200coord_group_calculate(group, pos, &value, derivBuffer.data(), virial)
               : b200coord_calculate(ctx, pos, &value, derivBuffer.data(), virial),
@@ -496,6 +602,9 @@ void CoordinationBaseB200::calculate() {
     tEngine += std::chrono::duration<double>(t1 - t0).count();
     tStore += std::chrono::duration<double>(t2 - t1).count();
     nCalls++;
+  }
+  for (int j = 0; j < 9; ++j) {
+    lastVirial[j] = virial[j];
   }
   setValue(value);
   setBoxDerivatives(Tensor(virial[0], virial[1], virial[2], virial[3], virial[4], virial[5], virial[6], virial[7], virial[8]));

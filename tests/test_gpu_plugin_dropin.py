@@ -247,3 +247,24 @@ def test_gpu_devices_keyword_shards_one_process_over_two_gpus():
         outs.append(res)
     compare(outs[0], outs[1])
     assert "sharded over 2 CUDA devices" in open("/tmp/plumed_devs_1.log").read()
+
+
+@pytest.mark.parametrize("body", [
+    "GROUPA=1-3000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+    "GROUPA=1-500 GROUPB=501-3000 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=2",
+    "GROUPA=1-600 GROUPB=401-3000 R_0=0.3",  # atoms 401-600 are in both groups: the action must fall back to PLUMED's loops
+])
+def test_host_fast_path_gathers_and_scatters_itself(body, monkeypatch):
+    """large systems: the action gathers its atoms and scatters its forces itself (OpenMP) instead of PLUMED's serial
+    retrieveAtoms / setForcesOnAtoms; forced on here for a small system (B200COORD_HOST_FAST=2).  Bias, forces on all atoms
+    and virial must be the CPU action's, with RESTRAINT and with a second action (a function of the CV) pushing forces."""
+    _need()
+    monkeypatch.setenv("B200COORD_HOST_FAST", "2")
+    n = 3000
+    frames, box = trajectory(n, 6, seed=37, triclinic=True)
+    lines = ["c: COORDINATION " + body, "f: CUSTOM ARG=c FUNC=0.001*x*x PERIODIC=NO",
+             "RESTRAINT ARG=c,f AT=100,3 KAPPA=0.01,0.5 SLOPE=0.5,0.1"]
+    cpu, gpu = run_both(n, lines, frames, box)
+    compare(cpu, gpu)
+    said = "gathered and forces scattered by the action itself" in open("/tmp/plumed_gpu.log").read()
+    assert said == ("GROUPB=401" not in body)
