@@ -560,6 +560,7 @@ def parity_check(E, c, line, box, frame, step, e2e_state):
 
 def plumed_e2e(E, line, box, frames, W, K):
     """the same steps through the unmodified PlumedMain + LOAD plugin (1 GPU); wall clock around plumed_cmd("calc")"""
+    import torch
     from oracle import refplumed as R
     plugin = os.path.join(os.path.dirname(E.capi.LIB_PATH), "libb200coord_plumed.so")
     if not (R.available() and os.path.exists(plugin)):
@@ -589,23 +590,68 @@ def plumed_e2e(E, line, box, frames, W, K):
         p.cmd("calc", None)
         p._keep = p._keep[-64:]
 
-    for s in range(W):
-        one(s)
-    t0 = time.perf_counter()
-    for s in range(W, W + K):
-        one(s)
-    dt = time.perf_counter() - t0
+    def timed(step_fn):
+        for s in range(W):
+            step_fn(s)
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            step_fn(s)
+        return time.perf_counter() - t0
+
+    def read_timers(logfile):
+        timers = []
+        try:
+            for ln in open(logfile):
+                if "PLUMED:" in ln and any(k in ln for k in ("Prepare", "Sharing", "Waiting", "Calculating", "Applying", "4A ", "5A ", "Update")):
+                    timers.append(" ".join(ln.split()[1:]))
+        except Exception:
+            pass
+        return timers[:16]
+
+    dt = timed(one)
     p.close()
-    timers = []
+    out = {"ms_per_step": 1e3 * dt / K, "threads": os.cpu_count() or 1, "plumed_timers": read_timers("/tmp/bench_plumed_e2e.log"),
+           "path": "plumed_cmd(setPositions..calc) -> PlumedMain -> CoordinationB200 (LOAD) -> libb200coord; forces and "
+                   "virial returned to the caller every step; the action gathers positions / adds forces itself over OpenMP "
+                   "threads (B200COORD_HOST_FAST) through page-locked buffers"}
+
+    # the engine's positions and forces stay on the device (GPU_COUPLING); PLUMED is still handed host
+    # arrays (zeros: nobody reads them) and does its own per-atom bookkeeping on them
     try:
-        for ln in open("/tmp/bench_plumed_e2e.log"):
-            if "PLUMED:" in ln and any(k in ln for k in ("Prepare", "Sharing", "Waiting", "Calculating", "Applying", "4A ", "5A ", "Update")):
-                timers.append(" ".join(ln.split()[1:]))
-    except Exception:
-        pass
-    return {"ms_per_step": 1e3 * dt / K, "threads": os.cpu_count() or 1, "plumed_timers": timers[:16],
-            "path": "plumed_cmd(setPositions..calc) -> PlumedMain -> CoordinationB200 (LOAD) -> libb200coord; forces and "
-                    "virial returned to the caller every step; pageable caller arrays registered once (B200COORD_PIN_HOST)"}
+        L = E.capi.lib()
+        d_pos = torch.empty((n, 3), dtype=torch.float64, device=frames[0].device)
+        d_force = torch.zeros((n, 3), dtype=torch.float64, device=frames[0].device)
+        key = b"bench_engine"
+        if L.b200coord_coupling_publish(key, E.local, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_force.data_ptr()), n) != 0:
+            raise RuntimeError("coupling_publish failed")
+        p = R.Plumed(n, ["LOAD FILE=" + plugin, "DEBUG DETAILED_TIMERS", line + " GPU_COUPLING=bench_engine",
+                         "RESTRAINT ARG=c AT=0 KAPPA=0 SLOPE=1"], log="/tmp/bench_plumed_e2e_dev.log")
+        hostpos = np.zeros((n, 3))
+
+        def one_dev(s):
+            d_pos.copy_(frames[s % F])  # the engine's integrator wrote new positions
+            torch.cuda.current_stream().synchronize()
+            p.cmd("setStep", C.c_int(int(s)))
+            p.cmd("setPositions", hostpos)
+            p.cmd("setMasses", p.masses)
+            p.cmd("setCharges", p.charges)
+            p.cmd("setBox", boxm)
+            p.cmd("setForces", forces)
+            p.cmd("setVirial", virial)
+            p.cmd("calc", None)
+            p._keep = p._keep[-64:]
+
+        dt = timed(one_dev)
+        p.close()
+        L.b200coord_coupling_withdraw(key)
+        out["device_coupled"] = {
+            "ms_per_step": 1e3 * dt / K, "plumed_timers": read_timers("/tmp/bench_plumed_e2e_dev.log"),
+            "force_checksum": float(d_force.abs().sum().item()),
+            "path": "as above with GPU_COUPLING: positions read from and forces added to device arrays the caller "
+                    "published (b200coord_coupling_publish); no per-atom data crosses the host link"}
+    except Exception as ex:  # noqa: BLE001
+        out["device_coupled"] = {"unavailable": repr(ex)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -835,6 +881,10 @@ def run_b200(args):
         if "ms_per_step" in e2e_pl:
             e2e_pl["value"] = typ["pairs_per_step"] / (e2e_pl["ms_per_step"] * 1e-3)
             e2e_pl["unit"] = UNIT
+            dc = e2e_pl.get("device_coupled") or {}
+            if "ms_per_step" in dc:
+                dc["value"] = typ["pairs_per_step"] / (dc["ms_per_step"] * 1e-3)
+                dc["unit"] = UNIT
     del frames
     torch.cuda.empty_cache()
     if not args.no_other_configs:

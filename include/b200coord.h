@@ -245,6 +245,22 @@ int b200coord_group_set_charges(b200coord_group* g, const double* charges);
 int b200coord_group_set_types(b200coord_group* g, const unsigned* types, unsigned ntypes, const double* etas);
 int b200coord_group_calculate(b200coord_group* g, const double* pos, double* value, double* deriv, double* virial);
 
+/* ---- an MD engine that keeps positions and forces on the GPU. The reference's engines hand host
+   pointers to plumed_cmd (patches/gromacs-2025.0.diff/src/gromacs/applied_forces/plumed/plumedforceprovider.cpp:171-204)
+   and PLUMED copies them in and out (src/core/ActionAtomistic.cpp:444-537). Here the engine publishes its device
+   arrays (double[3*natoms], PLUMED's internal units) under a name; the action that carries GPU_COUPLING=<name> reads the
+   positions where they are and adds (force on the CV) x dCV/dx to the force array -- Colvar::apply
+   (src/core/Colvar.cpp:50-60) on the device. Value and virial are returned on the host, derivatives stay on the device.
+   The positions must be complete when calculate_coupled is called; the forces are complete when apply_coupled returns. */
+int b200coord_coupling_publish(const char* key, int device, const double* d_pos, double* d_force, size_t natoms);
+int b200coord_coupling_withdraw(const char* key);
+int b200coord_coupling_lookup(const char* key, int* device, const double** d_pos, double** d_force, size_t* natoms);
+/* index[i] = where atom i of the context (GROUPA then GROUPB) sits in the engine's arrays; NULL: atom i is atom i */
+int b200coord_coupled_set_index(b200coord_ctx* ctx, const unsigned* index);
+int b200coord_calculate_coupled(b200coord_ctx* ctx, const double* d_pos_all, double* value, double* virial);
+int b200coord_apply_coupled(b200coord_ctx* ctx, double factor, double* d_force_all);
+int b200coord_coupled_derivatives(b200coord_ctx* ctx, double* deriv /* host, 3n: for tests and DUMPDERIVATIVES-like needs */);
+
 /* ---- pinned host memory for callers that want full-speed copies */
 int b200coord_host_alloc(size_t bytes, void** ptr);
 int b200coord_host_free(void* ptr);

@@ -27,6 +27,9 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_set_box", "b200coord_prepare", "b200coord_update_list", "b200coord_calculate",
             "b200coord_calculate_device", "b200coord_get_stats", "b200coord_nl_pairs",
             "b200coord_comm_unique_id", "b200coord_comm_init", "b200coord_host_alloc", "b200coord_host_free",
+            "b200coord_coupling_publish", "b200coord_coupling_withdraw", "b200coord_coupling_lookup",
+            "b200coord_coupled_set_index", "b200coord_calculate_coupled", "b200coord_apply_coupled",
+            "b200coord_coupled_derivatives",
             "b200coord_device_alloc", "b200coord_device_free", "b200coord_memcpy_h2d", "b200coord_memcpy_d2h",
             "b200coord_device_synchronize", "b200coord_enqueue_device", "b200coord_stream_mark",
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
@@ -105,6 +108,14 @@ def lib():
     L.b200coord_nl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     L.b200coord_comm_unique_id.argtypes = [C.c_char_p]
     L.b200coord_comm_init.argtypes = [C.c_void_p, C.c_char_p]
+    L.b200coord_coupling_publish.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.b200coord_coupling_withdraw.argtypes = [C.c_char_p]
+    L.b200coord_coupling_lookup.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_size_t)]
+    L.b200coord_coupled_set_index.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200coord_calculate_coupled.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.b200coord_apply_coupled.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    L.b200coord_coupled_derivatives.argtypes = [C.c_void_p, C.c_void_p]
     L.b200coord_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.b200coord_host_free.argtypes = [C.c_void_p]
     L.b200coord_device_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]

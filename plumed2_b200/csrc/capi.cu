@@ -16,6 +16,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -202,6 +203,10 @@ struct b200coord_ctx {
   unsigned tile_bound_a = 0, tile_bound_b = 0, tile_nseg = 0;
   bool tile_ok = false;               // the current sort has a work list
   bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
+  // coupling with an engine whose arrays live on the device: where the action's atoms sit in the engine's arrays
+  DevBuf<uint32_t> d_cidx;
+  bool cidx_set = false;              // false: atom i of the action is atom i of the engine
+  bool coupled_fresh = false;         // d_out holds the derivatives of the last b200coord_calculate_coupled
   IdxRanges needed;                   // sorted indices this rank's rows can touch (its rows + every possible partner)
   unsigned* h_idx = nullptr;          // pinned scratch for compute_needed
   b200coord_stats stats;
@@ -826,6 +831,7 @@ int combine_ranks(b200coord_ctx* c) {
 int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, unsigned slot_lo = 0u,
                unsigned slot_cnt = 0xffffffffu, const PosSrc* src_in = nullptr) {
   const PosSrc src = src_in ? *src_in : pos_src_local(d_pos);
+  c->coupled_fresh = false;
   if (c->cfg.pbc && !c->box_set) return fail(c, B200COORD_ERR_STATE, "b200coord_set_box must be called before calculate");
   if (c->dsw.type == B200COORD_PAIR_DHENERGY && !c->have_charges)
     return fail(c, B200COORD_ERR_STATE, "b200coord_set_charges must be called before calculate (DHENERGY)");
@@ -1321,6 +1327,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   c->d_pslice[0].release();
   c->d_pslice[1].release();
   c->d_inv.release();
+  c->d_cidx.release();
   c->d_fin.release();
   c->d_tilework.release();
   c->d_tilecnt.release();
@@ -1986,6 +1993,116 @@ int b200coord_group_calculate(b200coord_group* g, const double* pos, double* val
   if (rc) return rc;
   *value = vals[0];  // every rank holds the all-reduced value and virial
   for (int i = 0; i < 9; ++i) virial[i] = virs[0][i];
+  return B200COORD_OK;
+}
+
+// ---- coupling with an MD engine that keeps positions and forces on the device. The reference passes
+// host pointers through plumed_cmd (patches/gromacs-2025.0.diff/.../plumedforceprovider.cpp:171-204); here the engine
+// publishes its device arrays under a name, the action that carries GPU_COUPLING=<name> looks them up, reads the
+// positions where they are and adds force-on-CV x derivative to the engine's force array (Colvar::apply,
+// src/core/Colvar.cpp:50-60) without either array visiting the host.
+namespace {
+struct CouplingEntry {
+  int device = 0;
+  const double* d_pos = nullptr;
+  double* d_force = nullptr;
+  size_t natoms = 0;
+};
+std::mutex g_coupling_mutex;
+std::map<std::string, CouplingEntry>& coupling_table() {
+  static std::map<std::string, CouplingEntry> t;
+  return t;
+}
+}  // namespace
+
+int b200coord_coupling_publish(const char* key, int device, const double* d_pos, double* d_force, size_t natoms) {
+  if (!key || !*key || !d_pos || !d_force || natoms == 0) return fail(nullptr, B200COORD_ERR_INVALID, "coupling_publish: null or empty argument");
+  cudaPointerAttributes at;
+  for (const void* q : {static_cast<const void*>(d_pos), static_cast<const void*>(d_force)}) {
+    if (cudaPointerGetAttributes(&at, q) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != device) {
+      cudaGetLastError();
+      return fail(nullptr, B200COORD_ERR_INVALID, "coupling_publish: not a device pointer of the stated device");
+    }
+  }
+  std::lock_guard<std::mutex> lk(g_coupling_mutex);
+  CouplingEntry& e = coupling_table()[key];
+  e.device = device;
+  e.d_pos = d_pos;
+  e.d_force = d_force;
+  e.natoms = natoms;
+  return B200COORD_OK;
+}
+
+int b200coord_coupling_withdraw(const char* key) {
+  if (!key) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_coupling_mutex);
+  return coupling_table().erase(key) ? B200COORD_OK : fail(nullptr, B200COORD_ERR_STATE, std::string("no coupling named ") + key);
+}
+
+int b200coord_coupling_lookup(const char* key, int* device, const double** d_pos, double** d_force, size_t* natoms) {
+  if (!key) return fail(nullptr, B200COORD_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_coupling_mutex);
+  auto it = coupling_table().find(key);
+  if (it == coupling_table().end()) return fail(nullptr, B200COORD_ERR_STATE, std::string("no coupling named ") + key);
+  if (device) *device = it->second.device;
+  if (d_pos) *d_pos = it->second.d_pos;
+  if (d_force) *d_force = it->second.d_force;
+  if (natoms) *natoms = it->second.natoms;
+  return B200COORD_OK;
+}
+
+int b200coord_coupled_set_index(b200coord_ctx* c, const unsigned* index) {
+  if (!c) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  c->coupled_fresh = false;
+  if (!index) {
+    c->cidx_set = false;
+    return B200COORD_OK;
+  }
+  CU(c, c->d_cidx.reserve(c->n));
+  CU(c, cudaMemcpyAsync(c->d_cidx.p, index, sizeof(unsigned) * (size_t)c->n, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  c->cidx_set = true;
+  return B200COORD_OK;
+}
+
+int b200coord_calculate_coupled(b200coord_ctx* c, const double* d_pos_all, double* value, double* virial) {
+  if (!c || !d_pos_all || !value || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (c->cfg.nranks > 1) return fail(c, B200COORD_ERR_UNSUPPORTED, "device coupling is one context on the engine's device");
+  CU(c, cudaSetDevice(c->device));
+  c->coupled_fresh = false;
+  const double* pos = d_pos_all;
+  if (c->cidx_set) {
+    launch_coupled_gather(d_pos_all, c->d_cidx.p, c->n, c->d_pos.p, c->st);
+    pos = c->d_pos.p;
+  }
+  int rc = run_device(c, pos);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_small, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
+  for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
+  *value = c->h_small[9];
+  refresh_stats(c);
+  c->coupled_fresh = true;
+  return B200COORD_OK;
+}
+
+int b200coord_apply_coupled(b200coord_ctx* c, double factor, double* d_force_all) {
+  if (!c || !d_force_all) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->coupled_fresh) return fail(c, B200COORD_ERR_STATE, "apply_coupled needs the derivatives of a b200coord_calculate_coupled");
+  CU(c, cudaSetDevice(c->device));
+  launch_coupled_apply(c->d_out.p, c->cidx_set ? c->d_cidx.p : nullptr, c->n, factor, d_force_all, c->st);
+  CU_LAST(c, "coupled apply");
+  CU(c, cudaStreamSynchronize(c->st));  // the engine may read its forces as soon as this returns
+  return B200COORD_OK;
+}
+
+int b200coord_coupled_derivatives(b200coord_ctx* c, double* deriv) {
+  if (!c || !deriv) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (!c->coupled_fresh) return fail(c, B200COORD_ERR_STATE, "no derivatives of a coupled step on the device");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(deriv, c->d_out.p, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyDeviceToHost, c->st));
+  CU(c, cudaStreamSynchronize(c->st));
   return B200COORD_OK;
 }
 

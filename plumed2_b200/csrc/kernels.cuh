@@ -262,6 +262,9 @@ void launch_finalize(const double* partials, int nblocks, double weight, double*
                      cudaStream_t st);
 // out[3*slot+c] = row inv[slot], component c, for the slots [slot_lo, slot_lo+slot_cnt): every rank PULLS the rows of its
 // own atoms from whoever swept them (NVLink peer loads; one rank: a local gather)
+void launch_coupled_gather(const double* pos_all, const uint32_t* index, unsigned n, double* pos, cudaStream_t st);
+void launch_coupled_apply(const double* deriv, const uint32_t* index /*nullptr: 0..n-1*/, unsigned n, double factor,
+                          double* force_all, cudaStream_t st);
 void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv /*slot -> sorted*/, double* out, unsigned slot_lo,
                         unsigned slot_cnt, cudaStream_t st);
 

@@ -129,6 +129,34 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coupling with an MD engine whose arrays live on the device (capi.cu: b200coord_calculate_coupled / _apply_coupled):
+// the action's atoms are picked out of the engine's position array, and the chain rule of Colvar::apply
+// (src/core/Colvar.cpp:50-60: force on atom = force on the CV x derivative) is added to the engine's force array.
+__global__ void __launch_bounds__(256)
+    k_coupled_gather(const double* __restrict__ pos_all, const uint32_t* __restrict__ index, unsigned n, double* __restrict__ pos) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* __restrict__ src = pos_all + 3 * (size_t)index[t];
+  const size_t o = 3 * (size_t)t;
+  pos[o] = src[0];
+  pos[o + 1] = src[1];
+  pos[o + 2] = src[2];
+}
+
+__global__ void __launch_bounds__(256)
+    k_coupled_apply(const double* __restrict__ deriv, const uint32_t* __restrict__ index, unsigned n, double factor,
+                    double* __restrict__ force_all) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  // an atom listed in both groups owns two derivative rows: atomics keep the two adds apart
+  double* dst = force_all + 3 * (size_t)(index ? index[t] : t);
+  const size_t o = 3 * (size_t)t;
+  atomicAdd(dst, factor * deriv[o]);
+  atomicAdd(dst + 1, factor * deriv[o + 1]);
+  atomicAdd(dst + 2, factor * deriv[o + 2]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch (FP64 here; the FP32 instances live in kernels_sweep_f32.cu)
 int launch_sweep_list_f32(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<float>& sw, cudaStream_t st);
 int launch_sweep_cells_f32(const SweepArgs& a, const DevPbc& pbc, const DevSwitchT<float>& sw, cudaStream_t st);
@@ -192,6 +220,15 @@ void launch_finalize(const double* partials, int nblocks, double weight, double*
 void launch_unsort_pull(const RowSrc& rows, const uint32_t* inv, double* out, unsigned slot_lo, unsigned slot_cnt,
                         cudaStream_t st) {
   if (slot_cnt) k_unsort_pull<<<(slot_cnt + 255) / 256, 256, 0, st>>>(rows, inv, out, slot_lo, slot_cnt);
+}
+
+void launch_coupled_gather(const double* pos_all, const uint32_t* index, unsigned n, double* pos, cudaStream_t st) {
+  if (n) k_coupled_gather<<<(n + 255) / 256, 256, 0, st>>>(pos_all, index, n, pos);
+}
+
+void launch_coupled_apply(const double* deriv, const uint32_t* index, unsigned n, double factor, double* force_all,
+                          cudaStream_t st) {
+  if (n) k_coupled_apply<<<(n + 255) / 256, 256, 0, st>>>(deriv, index, n, factor, force_all);
 }
 
 }  // namespace b200

@@ -84,6 +84,7 @@ protected:
   // no virtual atoms, no atom listed twice) the action does both itself with OpenMP: it tells PLUMED not to retrieve
   // (ActionAtomistic::doNotRetrieve, core/ActionAtomistic.h:169-176), reads the shared position values through
   // getGlobalPosition() and adds f * derivative to the force arrays of posx / posy / posz with Value::addForce.
+  std::string coupling;  // GPU_COUPLING=<name>: positions and forces live in the engine's device arrays
   bool fastHost = false;
   std::vector<std::pair<std::size_t, std::size_t>> valueIdx;
   Value* posValue[3] = {nullptr, nullptr, nullptr};
@@ -140,6 +141,7 @@ void CoordinationBaseB200::registerKeywords(Keywords& keys) {
   keys.add("atoms", "GROUPB", "Second list of atoms (if empty, N*(N-1)/2 pairs in GROUPA are counted)");
   keys.add("optional", "GPU_DEVICE", "CUDA device ordinal to run on (default: the B200COORD_DEVICE environment variable, else the current device)");
   keys.add("optional", "GPU_DEVICES", "comma separated CUDA device ordinals: shard the i-atoms over several GPUs of this node inside this process (NCCL + NVLink peer memory); not with PAIR, not together with several MPI ranks");
+  keys.add("optional", "GPU_COUPLING", "name under which the MD engine published device arrays of positions and forces (b200coord_coupling_publish): the action reads positions from the device array and adds its forces to the device array; nothing is copied through the host. The value and the virial are still returned to PLUMED; the derivatives stay on the device");
   keys.addFlag("GPU_FP32", false, "opt-in FP32 pair arithmetic (1e-5 relative instead of 1e-10; FP64 minimum image and accumulation). Also switched on by the B200COORD_FP32=1 environment variable");
 }
 
@@ -381,6 +383,29 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
       at = comma + 1;
     }
   }
+  parse("GPU_COUPLING", coupling);
+  if (!coupling.empty()) {
+    int cdev = 0;
+    std::size_t cn = 0;
+    if (b200coord_coupling_lookup(coupling.c_str(), &cdev, nullptr, nullptr, &cn) != B200COORD_OK) {
+      error("GPU_COUPLING=" + coupling + ": the engine has not published device arrays under this name (b200coord_coupling_publish)");
+    }
+    if (devices.size() > 1) {
+      error("GPU_COUPLING works on the engine's device; it cannot be combined with GPU_DEVICES");
+    }
+    device = cdev;  // the arrays decide where the action runs
+    devices.clear();
+    for (const AtomNumber& a : ga) {
+      if (a.index() >= cn) {
+        error("GPU_COUPLING=" + coupling + ": an atom of GROUPA is beyond the published arrays");
+      }
+    }
+    for (const AtomNumber& a : gb) {
+      if (a.index() >= cn) {
+        error("GPU_COUPLING=" + coupling + ": an atom of GROUPB is beyond the published arrays");
+      }
+    }
+  }
   bool fp32 = false;
   if (const char* env = std::getenv("B200COORD_FP32")) {
     fp32 = std::atoi(env) != 0;
@@ -439,9 +464,23 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
       error(std::string("cannot set up the B200 ") + what + " engine: " + b200coord_last_error(nullptr));
     }
   }
-  derivBuffer.resize(3 * all.size());
   requestAtoms(all);
-  setupFastHost();
+  if (!coupling.empty()) {
+    if (combineWithMpi || needCharges || checkNumericalDerivatives()) {
+      error("GPU_COUPLING is not available with several MPI ranks, with charges from PLUMED or with NUMERICAL_DERIVATIVES");
+    }
+    bool identity = true;
+    for (unsigned i = 0; i < absIndex.size(); ++i) {
+      identity = identity && absIndex[i] == i;
+    }
+    if (b200coord_coupled_set_index(ctx, identity ? nullptr : absIndex.data()) != B200COORD_OK) {
+      error(b200coord_last_error(ctx));
+    }
+    doNotRetrieve();  // PLUMED's host copy of the positions is not looked at
+  } else {
+    derivBuffer.resize(3 * all.size());
+    setupFastHost();
+  }
   if (const char* env = std::getenv("B200COORD_PLUGIN_TIMERS")) {
     timers = std::atoi(env) != 0;
   }
@@ -456,6 +495,10 @@ void CoordinationBaseB200::setup(const b200coord_switch& sw, const char* what) {
     log.printf("  on CUDA device %d%s\n", device, deviceFromRank ? " (local MPI rank modulo visible devices)" : "");
   } else {
     log.printf("  on the current CUDA device\n");
+  }
+  if (!coupling.empty()) {
+    log.printf("  positions read from and forces added to the device arrays published as '%s' (GPU_COUPLING); derivatives stay on the device\n",
+               coupling.c_str());
   }
   if (combineWithMpi) {
     log.printf("  %d MPI ranks: each computes its share of the i-atoms on its own device, partial results are summed with Comm::Sum on the host\n",
@@ -523,12 +566,31 @@ void CoordinationBaseB200::clearDerivatives(const bool& force) {
   // PlumedMain clears the derivatives of every active action before calculate() (PlumedMain.cpp:1312-1318): one
   // thread filling 3N+10 doubles. calculate() below overwrites every one of them (value, 3N atom derivatives,
   // 9 box derivatives), so on the parallel host path the fill is skipped.
-  if (!fastHost || force) {
+  if ((!fastHost && coupling.empty()) || force) {
     Colvar::clearDerivatives(force);
   }
 }
 
 void CoordinationBaseB200::apply() {
+  if (!coupling.empty()) {
+    Value* v = getPntrToValue();
+    if (!v->forcesWereAdded()) {
+      return;
+    }
+    const double ff = v->getForce(0);
+    double* dForce = nullptr;
+    if (b200coord_coupling_lookup(coupling.c_str(), nullptr, nullptr, &dForce, nullptr) != B200COORD_OK) {
+      error(b200coord_last_error(nullptr));
+    }
+    check(b200coord_apply_coupled(ctx, ff, dForce), "apply_coupled");
+    double f9[9];
+    for (int j = 0; j < 9; ++j) {
+      f9[j] = ff * lastVirial[j];
+    }
+    unsigned ind = 0;
+    setForcesOnCell(f9, 9, ind);
+    return;
+  }
   if (!fastHost) {
     Colvar::apply();
     return;
@@ -621,6 +683,24 @@ void CoordinationBaseB200::calculate() {
   check(group ? b200coord_group_set_box(group, box) : b200coord_set_box(ctx, box), "set_box");
   double value = 0.0;
   double virial[9];
+  if (!coupling.empty()) {
+    const double* dPos = nullptr;
+    if (b200coord_coupling_lookup(coupling.c_str(), nullptr, &dPos, nullptr, nullptr) != B200COORD_OK) {
+      error(b200coord_last_error(nullptr));
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    check(b200coord_calculate_coupled(ctx, dPos, &value, virial), "calculate_coupled");
+    if (timers) {
+      tEngine += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      nCalls++;
+    }
+    for (int j = 0; j < 9; ++j) {
+      lastVirial[j] = virial[j];
+    }
+    setValue(value);
+    setBoxDerivatives(Tensor(virial[0], virial[1], virial[2], virial[3], virial[4], virial[5], virial[6], virial[7], virial[8]));
+    return;
+  }
   const double* pos = n ? &getPositions()[0][0] : nullptr;
   if (fastHost) {  // the shared position values, read in parallel (retrieveAtoms was told not to)
     double* pb = posBuffer.data();

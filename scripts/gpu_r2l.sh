@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call L: plugin host path after the addForces fix
+# round 2, GPU call L: plugin host path after the addForces fix, device coupling
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -13,7 +13,8 @@ import json
 d = json.loads(open("gpurun_out/r2l_bench.json").read().strip().splitlines()[-1])
 print("typical", d["ms_per_step"], d["roofline"]["kernel_ms"], "e2e", d["e2e"]["ms_per_step"])
 e = d.get("e2e_plumed") or {}
-print({k: v for k, v in e.items() if k != "plumed_timers"})
+print({k: v for k, v in e.items() if k not in ("plumed_timers", "device_coupled")})
+print("coupled", e.get("device_coupled"))
 for l in e.get("plumed_timers", []): print(l)
 print(json.dumps(d.get("cuda_baseline"), indent=1))
 PY

@@ -268,3 +268,60 @@ def test_host_fast_path_gathers_and_scatters_itself(body, monkeypatch):
     compare(cpu, gpu)
     said = "gathered and forces scattered by the action itself" in open("/tmp/plumed_gpu.log").read()
     assert said == ("GROUPB=401" not in body)
+
+
+@pytest.mark.parametrize("body", [
+    "GROUPA=1-3000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+    "GROUPA=2-3000:2 GROUPB=1-2999:2 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=2",
+    "GROUPA=1-600 GROUPB=401-2900 R_0=0.3",  # atoms 401-600 own two derivative rows each; atoms 2901-3000 get no force
+])
+def test_engine_arrays_on_the_device(body):
+    """an MD engine that keeps positions and forces on the GPU publishes the two device arrays
+    (b200coord_coupling_publish); the action with GPU_COUPLING=<name> reads positions there and adds force-on-CV x
+    derivative there.  PLUMED itself is handed zeros as host positions, to show they are not looked at.  The device
+    force array, the virial and the bias must be what the CPU action returns through setForces / setVirial."""
+    _need()
+    import ctypes as C
+    L = capi.lib()
+    n = 3000
+    frames, box = trajectory(n, 6, seed=41, triclinic=True)
+    lines = ["c: COORDINATION " + body, "f: CUSTOM ARG=c FUNC=0.001*x*x PERIODIC=NO",
+             "RESTRAINT ARG=c,f AT=100,3 KAPPA=0.01,0.5 SLOPE=0.5,0.1"]
+    p = R.Plumed(n, lines, watch=("c",), log="/tmp/plumed_cpu.log")
+    cpu = []
+    for step, pos in enumerate(frames):
+        r = p.calc(step, pos, box)
+        r["values"] = {"c": p.value("c")}
+        cpu.append(r)
+    p.close()
+
+    d_pos, d_force = C.c_void_p(), C.c_void_p()
+    assert L.b200coord_device_alloc(24 * n, C.byref(d_pos)) == 0
+    assert L.b200coord_device_alloc(24 * n, C.byref(d_force)) == 0
+    try:
+        assert L.b200coord_coupling_publish(b"engine0", 0, d_pos, d_force, n) == 0
+        host = np.zeros((n, 3))
+        with pytest.raises(R.PlumedError):  # a name nobody published
+            R.Plumed(n, ["LOAD FILE=" + PLUGIN, "c: COORDINATION " + body + " GPU_COUPLING=nobody"], log="/tmp/plumed_gpu_bad.log")
+        p = R.Plumed(n, ["LOAD FILE=" + PLUGIN, lines[0] + " GPU_COUPLING=engine0"] + lines[1:], watch=("c",),
+                     log="/tmp/plumed_gpu.log")
+        zeros = np.zeros((n, 3))
+        for step, pos in enumerate(frames):
+            x = np.ascontiguousarray(pos)
+            assert L.b200coord_memcpy_h2d(d_pos, x.ctypes.data_as(C.c_void_p), 24 * n) == 0
+            assert L.b200coord_memcpy_h2d(d_force, zeros.ctypes.data_as(C.c_void_p), 24 * n) == 0
+            r = p.calc(step, host, box)
+            got = np.empty((n, 3))
+            assert L.b200coord_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_force, 24 * n) == 0
+            a = cpu[step]
+            assert abs(p.value("c") - a["values"]["c"]) <= 1e-10 * abs(a["values"]["c"])
+            assert abs(r["bias"] - a["bias"]) <= 1e-10 * abs(a["bias"])
+            assert not np.any(r["forces"])  # nothing came back through the host array
+            assert rel_err(got, a["forces"]) <= 1e-10, (step, rel_err(got, a["forces"]))
+            assert rel_err(r["virial"], a["virial"]) <= 1e-10
+        p.close()
+        assert "GPU_COUPLING" in open("/tmp/plumed_gpu.log").read()
+    finally:
+        L.b200coord_coupling_withdraw(b"engine0")
+        L.b200coord_device_free(d_pos)
+        L.b200coord_device_free(d_force)
