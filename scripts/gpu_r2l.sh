@@ -18,3 +18,6 @@ print("coupled", e.get("device_coupled"))
 for l in e.get("plumed_timers", []): print(l)
 print(json.dumps(d.get("cuda_baseline"), indent=1))
 PY
+# the filter rebuild under ncu (one launch of the fill pass)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nl_filter -s 3 -c 1 -f -o gpurun_out/prof_filter_r2l python bench.py --steps 10 --warmup 3 --quick --no-cpu-baseline --frames 2 > gpurun_out/prof_filter_r2l.log 2>&1
+tail -3 gpurun_out/prof_filter_r2l.log
