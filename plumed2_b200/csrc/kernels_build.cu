@@ -707,6 +707,164 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same filter with ONE pipeline per warp that runs across rows.  A super-list row is ~9 trips long, and the
+// kernel above pays three dependent memory round trips (row header -> entries -> records) at the start of every row.
+// Here a block stages the headers of its <= 128 rows once (coalesced), every warp lists the trips of its <= 16 rows
+// in a shared-memory table (as k_sweep_img does), and the loop runs over that table: entries two trips ahead,
+// records one trip ahead, across row boundaries.  A row switch costs the write of the finished row's three counters.
+constexpr int kFltRowsPerWarp = 16;
+constexpr int kFltTripCap = 208;  // trips per warp the table holds (launch_nl_filter sizes rows_per_block for it)
+
+template <bool FILL, bool CAPPED, bool IMAGES>
+__global__ void __launch_bounds__(256, 3)
+    k_nl_filter_flat(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
+                     const unsigned long long* __restrict__ srow_start, const uint32_t* __restrict__ srow_count,
+                     const uint32_t* __restrict__ snbr, const DevPbc* __restrict__ pbc_g, SearchF32 f, double cutoff2,
+                     unsigned n_a, int two_groups, unsigned row_begin, unsigned row_end, uint32_t* __restrict__ row_count,
+                     const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr, unsigned row_cap,
+                     unsigned* __restrict__ cap_info, float far2, uint32_t* __restrict__ row_far_off,
+                     uint32_t* __restrict__ row_far_cnt, unsigned rows_per_block) {
+  constexpr unsigned kOk = 0x80000000u, kRem = 0xffffu;
+  constexpr int kRows = 8 * kFltRowsPerWarp;
+  __shared__ float4 s_li[kRows];
+  __shared__ uint32_t s_m[kRows], s_off[kRows], s_alloc[kRows];
+  __shared__ unsigned long long s_base[kRows];
+  __shared__ uint2 s_trip[8][kFltTripCap + 6];
+  const unsigned first = row_begin + blockIdx.x * rows_per_block;
+  if (first >= row_end) return;
+  const unsigned nrows = min(rows_per_block, row_end - first);
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long sb0 = srow_start[first - row_begin];
+  for (unsigned t = threadIdx.x; t < nrows; t += 256u) {
+    const unsigned rr = first + t - row_begin;
+    s_li[t] = lpos[first + t];
+    const uint32_t m = srow_count[rr];
+    s_m[t] = m;
+    s_off[t] = (uint32_t)(srow_start[rr] - sb0);
+    const uint32_t alloc = CAPPED ? row_cap : (FILL ? ((row_count[rr] + 3u) & ~3u) : 0u);
+    s_alloc[t] = alloc;
+    s_base[t] = CAPPED ? (unsigned long long)rr * row_cap : (FILL ? row_start[rr] : 0ull);
+    if (m == 0u) {  // no trips: nobody will come by to write this row's counters
+      row_count[rr] = 0u;
+      if (FILL) {
+        row_far_cnt[rr] = 0u;
+        row_far_off[rr] = alloc;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const unsigned rl = wid + 8u * lane;  // this lane's row of the warp (lanes >= 16 never have one)
+    uint32_t m = 0u, off0 = 0u;
+    if (lane < (unsigned)kFltRowsPerWarp && rl < nrows) {
+      m = s_m[rl];
+      off0 = s_off[rl];
+    }
+    const unsigned tn = (m + 63u) >> 6;
+    uint32_t total;
+    unsigned at = warp_exclusive_scan(tn, lane, total);
+    for (unsigned t = 0; t < tn; ++t) s_trip[wid][at++] = make_uint2(off0 + 64u * t, (m - 64u * t) | (lane << 16) | kOk);
+    if (lane < 6u) s_trip[wid][total + lane] = make_uint2(0u, 0u);  // the pipeline looks up to five trips past the end
+    __syncwarp();
+  }
+  const float c2_hi = f.c2_hi, c2_lo = f.c2_lo;
+  // row state
+  unsigned cur_r = 0xffffffffu, k = 0u, my_abs = 0u, alloc = 0u, total = 0u, total_far = 0u;
+  bool grp_a = true;
+  float4 li = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long base = 0ull;
+  auto flush = [&]() {
+    if (lane == 0) {
+      const unsigned rr = k - row_begin;
+      const unsigned all = total + total_far;
+      if (FILL) {
+        row_count[rr] = min(total, alloc);
+        row_far_cnt[rr] = min(total_far, alloc);
+        row_far_off[rr] = alloc - min(total_far, alloc);
+      } else {
+        row_count[rr] = all;
+      }
+      if (CAPPED || !FILL) {
+        if (all > cap_info[0]) atomicMax(&cap_info[0], all);
+      }
+      if (CAPPED && all > row_cap) atomicExch(&cap_info[1], 1u);
+    }
+  };
+  auto test = [&](bool in, uint32_t entry, const float4 lj, bool shifted, bool& far) -> bool {
+    far = false;
+    if (!in) return false;
+    float dx = lj.x - li.x, dy = lj.y - li.y, dz = lj.z - li.z;
+    if (shifted) {
+      const uint32_t code = (entry >> 26) ^ kImageCentre;
+      const float wx = (float)((int)(code & 3u) - 1), wy = (float)((int)((code >> 2) & 3u) - 1),
+                  wz = (float)((int)((code >> 4) & 3u) - 1);
+      dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
+      dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
+      dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+    }
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    bool keep = (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
+    if (keep && r2 > c2_lo) keep = exact_within(pos, perm, pbc_g, k, entry & kSuperIndexMask, two_groups, grp_a, cutoff2);
+    far = r2 > far2;
+    return keep;
+  };
+  auto emit = [&](bool keep, bool far, uint32_t j) {
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned mn = __ballot_sync(0xffffffffu, keep && !far), mf = __ballot_sync(0xffffffffu, keep && far);
+    if (FILL && keep) {
+      const unsigned at = far ? total_far + __popc(mf & below) : total + __popc(mn & below);
+      if (at < alloc) nbr[base + (far ? alloc - 1u - at : at)] = j;
+    }
+    total += __popc(mn);
+    total_far += __popc(mf);
+  };
+  const uint32_t* __restrict__ blk = snbr + sb0 + lane;
+  auto ent = [&](const uint2 d, unsigned off) -> uint32_t { return (off + lane < (d.y & kRem)) ? __ldg(blk + d.x + off) : 0u; };
+  uint2 d0 = s_trip[wid][0], d1 = s_trip[wid][1];
+  uint32_t c1 = ent(d0, 0u), c2 = ent(d0, 32u);
+  uint32_t n1 = ent(d1, 0u), n2 = ent(d1, 32u);
+  float4 l1 = __ldg(lpos + (c1 & kSuperIndexMask)), l2 = __ldg(lpos + (c2 & kSuperIndexMask));
+  for (unsigned it = 0; d0.y & kOk; ++it) {
+    {  // the entries stream from HBM: ask L2 for the piece four trips down the table (8 bytes per lane cover 256)
+      const uint2 pd = s_trip[wid][it + 4];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + pd.x + lane));
+    }
+    const uint32_t a1 = c1, a2 = c2;
+    const float4 p1 = l1, p2 = l2;
+    const uint2 dc = d0;
+    c1 = n1;
+    c2 = n2;
+    d0 = d1;
+    d1 = s_trip[wid][it + 2];
+    l1 = __ldg(lpos + (c1 & kSuperIndexMask));  // entry 0 (a valid atom) when past the end of a row
+    l2 = __ldg(lpos + (c2 & kSuperIndexMask));
+    n1 = ent(d1, 0u);
+    n2 = ent(d1, 32u);
+    const unsigned r = wid + 8u * ((dc.y >> 16) & 15u);
+    if (r != cur_r) {
+      if (cur_r != 0xffffffffu) flush();
+      cur_r = r;
+      k = first + r;
+      li = s_li[r];
+      my_abs = __float_as_uint(li.w);
+      grp_a = (k < n_a);
+      alloc = s_alloc[r];
+      base = s_base[r];
+      total = total_far = 0u;
+    }
+    const unsigned rem = dc.y & kRem;
+    const bool in1 = lane < rem, in2 = lane + 32u < rem;
+    const bool shifted = __any_sync(0xffffffffu, ((a1 | a2) & ~kSuperIndexMask) != 0u);
+    bool f1, f2;
+    const bool k1 = test(in1, a1, p1, shifted, f1);
+    const bool k2 = test(in2, a2, p2, shifted, f2);
+    emit(k1, f1, IMAGES ? a1 : (a1 & kSuperIndexMask));
+    if (rem > 32u) emit(k2, f2, IMAGES ? a2 : (a2 & kSuperIndexMask));
+  }
+  if (cur_r != 0xffffffffu) flush();
+}
+
 __global__ void k_regular_offsets(unsigned rows, unsigned row_cap, unsigned long long* __restrict__ row_start) {
   const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) row_start[r] = (unsigned long long)r * row_cap;
@@ -1025,7 +1183,8 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
                       const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr, const DevPbc* pbc_g,
                       const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
-                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, cudaStream_t st) {
+                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, unsigned max_srow,
+                      cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
@@ -1033,6 +1192,27 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
   for (int i = 0; i < 9; ++i) f.box[i] = (float)box.box[i];
   f.c2_hi = (float)(cutoff2 * (1.0 + band_rel));
   f.c2_lo = (float)(cutoff2 * (1.0 - band_rel));
+  // one pipeline per warp across rows when the rows are short enough for its trip table (max_srow = longest
+  // super-list row, 0 = unknown / switched off)
+  unsigned per_warp = 0u;
+  if (max_srow > 0u && max_srow <= 0xffffu) per_warp = std::min<unsigned>(kFltRowsPerWarp, kFltTripCap / ((max_srow + 63u) / 64u));
+  if (per_warp) {
+    const unsigned rpb = 8u * per_warp;
+    const unsigned fb = (rows + rpb - 1u) / rpb;
+#define B200_FLAT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
+                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt, rpb
+    if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
+    if (mode == 0) k_nl_filter_flat<false, false, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
+    else if (images) {
+      if (mode == 1) k_nl_filter_flat<true, false, true><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
+      else k_nl_filter_flat<true, true, true><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
+    } else {
+      if (mode == 1) k_nl_filter_flat<true, false, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
+      else k_nl_filter_flat<true, true, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
+    }
+#undef B200_FLAT_ARGS
+    return;
+  }
 #define B200_FLT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);

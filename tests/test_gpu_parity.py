@@ -262,12 +262,13 @@ def test_rebuilds_that_filter_the_super_list(groups, tri):
 
 
 def test_switching_the_shortcuts_off_changes_nothing():
-    """B200COORD_NO_SUPERLIST / B200COORD_NO_FAR_SPLIT (A/B switches): same pair sets, same numbers"""
+    """B200COORD_NO_SUPERLIST / B200COORD_NO_FAR_SPLIT / B200COORD_FILTER_FLAT=0 (A/B switches): same pair sets, same
+    numbers (the per-row filter kernel and the one that pipelines across rows write identical rows)"""
     n = 8000
     pos0, box = water_box(n, 100.0, seed=52)
     line = "c: COORDINATION GROUPA=1-%d SWITCH={RATIONAL R_0=0.3 D_MAX=0.6} NLIST NL_CUTOFF=0.8 NL_STRIDE=3" % n
     runs = []
-    for env in ({}, {"B200COORD_NO_SUPERLIST": "1"}, {"B200COORD_NO_FAR_SPLIT": "1"}):
+    for env in ({}, {"B200COORD_NO_SUPERLIST": "1"}, {"B200COORD_NO_FAR_SPLIT": "1"}, {"B200COORD_FILTER_FLAT": "0"}):
         os.environ.update(env)
         try:
             c = P.Coordination.from_input(line)
@@ -284,6 +285,7 @@ def test_switching_the_shortcuts_off_changes_nothing():
         runs.append((out, c.stats()))
         c.close()
     assert runs[0][1]["filter_rebuilds"] >= 2 and runs[1][1]["filter_rebuilds"] == 0 and runs[1][1]["super_builds"] == 0
+    assert runs[3][1]["filter_rebuilds"] == runs[0][1]["filter_rebuilds"]
     for other, _ in runs[1:]:
         for (v0, d0, w0, p0), (v1, d1, w1, p1) in zip(runs[0][0], other):
             assert abs(v0 - v1) <= 1e-12 * abs(v0)
