@@ -424,6 +424,7 @@ def regime_run(E, line, box, frames, W, K, env=None, sampler=None, sustained=Fal
     out = {"ms_per_step": ms / K, "value": pairs * K / (ms * 1e-3), "pairs_per_step": pairs,
            "sweep_ms": st1["sweep_ms_sum"] / max(1, st1["sweep_count"]),
            "rebuild_ms": st1["build_ms_sum"] / max(1, st1["build_count"]), "rebuilds": int(st1["build_count"]),
+           "rebuild_ms_max": st1["build_ms_max"],
            "super_list_builds_total": int(st1["super_builds"]), "filter_rebuilds_total": int(st1["filter_rebuilds"]),
            "rebuilds_total": int(st1["rebuilds"]),
            "entries_evaluated_last_step": int(st1["pair_evals"]), "entries_listed": 2 * int(st1["nl_size"]),

@@ -118,6 +118,7 @@ typedef struct b200coord_stats {
   int f32_search;                    /* 1: the last rebuild used the FP32 candidate search (+ exact FP64 band) */
   unsigned long long super_builds;   /* rebuilds that (re)built the super-list (cutoff + 10 %) from the cells */
   unsigned long long filter_rebuilds;/* rebuilds that only filtered the super-list (displacement bound held) */
+  float build_ms_max;                /* longest single rebuild since the last b200coord_stream_mark(ctx,0) */
 } b200coord_stats;
 
 typedef struct b200coord_ctx b200coord_ctx;

@@ -70,7 +70,7 @@ class Stats(C.Structure):
                 ("last_h2d_ms", C.c_float), ("last_d2h_ms", C.c_float), ("ncells", C.c_uint * 3),
                 ("pbc_type", C.c_int), ("sweep_ms_sum", C.c_float), ("sweep_count", C.c_uint),
                 ("build_ms_sum", C.c_float), ("build_count", C.c_uint), ("f32_search", C.c_int),
-                ("super_builds", C.c_ulonglong), ("filter_rebuilds", C.c_ulonglong)]
+                ("super_builds", C.c_ulonglong), ("filter_rebuilds", C.c_ulonglong), ("build_ms_max", C.c_float)]
 
 
 _lib = None

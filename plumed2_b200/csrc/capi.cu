@@ -104,7 +104,7 @@ struct b200coord_ctx {
   static constexpr int kRing = 64;
   cudaEvent_t sweep_ev[2 * kRing] = {nullptr};  // per-step sweep stopwatch pairs since the last stream_mark(0)
   unsigned sweep_n = 0;
-  float build_ms_acc = 0.f;
+  float build_ms_acc = 0.f, build_ms_max = 0.f;
   unsigned build_n = 0;
 
   HostPbc hpbc;
@@ -791,6 +791,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     CU(c, cudaEventSynchronize(c->ev[5]));
     if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) {
       c->build_ms_acc += ms;
+      c->build_ms_max = std::max(c->build_ms_max, ms);
       c->build_n++;
     }
   }
@@ -1451,7 +1452,7 @@ int b200coord_stream_mark(b200coord_ctx* c, int which) {
   CU(c, cudaSetDevice(c->device));
   if (which == 0) {
     c->sweep_n = 0;
-    c->build_ms_acc = 0.f;
+    c->build_ms_acc = c->build_ms_max = 0.f;
     c->build_n = 0;
   }
   CU(c, cudaEventRecord(c->ev[8 + which], c->st));
@@ -1593,6 +1594,7 @@ int b200coord_get_stats(const b200coord_ctx* cc, b200coord_stats* out) {
     c->stats.sweep_count = got;
     c->stats.build_ms_sum = c->build_ms_acc;
     c->stats.build_count = c->build_n;
+    c->stats.build_ms_max = c->build_ms_max;
     cudaGetLastError();
   }
   *out = c->stats;

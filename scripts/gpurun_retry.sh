@@ -5,7 +5,7 @@ tries=$1; shift
 for i in $(seq 1 $tries); do
   out=$(/usr/local/graft/bin/gpurun "$@" 2>&1); rc=$?
   if echo "$out" | grep -q "status=transient" || [ $rc -eq 3 ]; then
-    echo "[retry $i] transient"; sleep 120; continue
+    echo "[retry $i] transient"; sleep 60; continue
   fi
   echo "$out"; exit $rc
 done
