@@ -607,7 +607,7 @@ def plumed_e2e(E, line, box, frames, W, K):
                     timers.append(" ".join(ln.split()[1:]))
         except Exception:
             pass
-        return timers[:16]
+        return timers[:40]
 
     dt = timed(one)
     p.close()

@@ -153,3 +153,18 @@ def test_create_rejects_bad_configs():
         rc = L.b200coord_create(C.byref(bad), C.byref(sw), ap, C.byref(out))
         assert rc == capi.ERR_INVALID and not out.value
         assert len(L.b200coord_last_error(None)) > 0
+
+
+def test_coupling_table_rejects_what_is_not_device_memory():
+    """b200coord_coupling_publish takes device pointers of the stated device only; a name nobody published is an error
+    for lookup and withdraw (host logic of the device-resident MD coupling, no kernels involved)"""
+    L = capi.lib()
+    host = np.zeros(30)
+    hp = host.ctypes.data_as(C.c_void_p)
+    assert L.b200coord_coupling_publish(b"x", 0, hp, hp, 10) == capi.ERR_INVALID
+    assert L.b200coord_coupling_publish(b"", 0, hp, hp, 10) == capi.ERR_INVALID
+    assert L.b200coord_coupling_publish(b"x", 0, None, None, 10) == capi.ERR_INVALID
+    dev, n = C.c_int(-5), C.c_size_t(0)
+    assert L.b200coord_coupling_lookup(b"x", C.byref(dev), None, None, C.byref(n)) != 0
+    assert dev.value == -5 and b"no coupling named x" in L.b200coord_last_error(None)
+    assert L.b200coord_coupling_withdraw(b"x") != 0
