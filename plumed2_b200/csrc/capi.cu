@@ -204,6 +204,7 @@ struct b200coord_ctx {
   bool tile_ok = false;               // the current sort has a work list
   unsigned super_max_row = 0;         // longest row of the current super-list
   bool filter_flat = true;            // B200COORD_FILTER_FLAT=0: the per-row filter kernel
+  int filter_minb = 2;                // B200COORD_FILTER_MINB=3: the 80-register build of the flat filter (3 blocks per SM)
   bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
   // coupling with an engine whose arrays live on the device: where the action's atoms sit in the engine's arrays
   DevBuf<uint32_t> d_cidx;
@@ -636,7 +637,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     launch_nl_filter(m, c->img_list, d_pos, c->d_perm.p, c->d_lpos.p, c->d_srowstart.p, c->d_srowcount.p, c->d_snbr.p, pbc_g, c->dbox, cut2,
                      c->band_rel, c->n_a, c->two_groups, c->row_begin, c->row_end, c->d_rowcount.p, c->d_rowstart.p,
                      m ? c->d_nbr.p : nullptr, m == 2 ? c->row_cap : 0u, c->d_capinfo.p, far2, c->d_rowfar.p,
-                     c->d_rowfar.p + rows, c->filter_flat ? c->super_max_row : 0u, c->st);
+                     c->d_rowfar.p + rows, c->filter_flat ? c->super_max_row : 0u, c->filter_minb, c->st);
   };
   bool list_done = false;
   if (super_wanted && c->super_valid) {
@@ -1270,6 +1271,7 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   to_dev_pbc(c->hpbc, false, c->dpbc);
   if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
   if (const char* e = std::getenv("B200COORD_FILTER_FLAT")) c->filter_flat = (std::atoi(e) != 0);
+  if (const char* e = std::getenv("B200COORD_FILTER_MINB")) c->filter_minb = (std::atoi(e) == 3) ? 3 : 2;
   if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);

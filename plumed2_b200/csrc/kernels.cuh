@@ -158,7 +158,8 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
                       const unsigned long long* srow_start, const uint32_t* srow_count, const uint32_t* snbr,
                       const DevPbc* pbc_g /*box parameters in global memory*/, const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
-                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, unsigned max_srow /*longest super-list row; 0: per-row kernel*/, cudaStream_t st);
+                      unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, unsigned max_srow /*longest super-list row; 0: per-row kernel*/, int flat_minb /*2 or 3 blocks per SM*/,
+                      cudaStream_t st);
 // FP32 candidate search on the local copy; the thin band around the cutoff falls back to the exact FP64 test
 void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool super /*super-list rows*/,
                         bool images /*entries carry the periodic image in their top 6 bits*/, const double* pos,

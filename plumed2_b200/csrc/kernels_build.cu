@@ -714,10 +714,29 @@ __global__ void __launch_bounds__(256, 3)
 // in a shared-memory table (as k_sweep_img does), and the loop runs over that table: entries two trips ahead,
 // records one trip ahead, across row boundaries.  A row switch costs the write of the finished row's three counters.
 constexpr int kFltRowsPerWarp = 16;
-constexpr int kFltTripCap = 208;  // trips per warp the table holds (launch_nl_filter sizes rows_per_block for it)
+constexpr int kFltTripCap = 208;
+constexpr int kFltMinBlocks = 2;   // resident blocks per SM the register allocation is sized for  // trips per warp the table holds (launch_nl_filter sizes rows_per_block for it)
 
-template <bool FILL, bool CAPPED, bool IMAGES>
-__global__ void __launch_bounds__(256, 3)
+// float4 record `idx`: address = one IMAD.WIDE (index * 16 + base), one 128-bit load
+__device__ __forceinline__ float4 load_f4_idx(const float4* __restrict__ base, uint32_t idx) {
+  float4 v;
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %4, 16, %5;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [p];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(idx), "l"(base));
+  return v;
+}
+// 32-bit word `idx` of a block-uniform array: one IMAD.WIDE + load, no per-lane 64-bit pointer to keep alive
+__device__ __forceinline__ uint32_t load_u32_idx(const uint32_t* __restrict__ base, uint32_t idx) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %1, 4, %2;\n\tld.global.nc.u32 %0, [p];\n\t}" : "=r"(v) : "r"(idx), "l"(base));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_idx(const uint32_t* __restrict__ base, uint32_t idx) {
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %0, 4, %1;\n\tprefetch.global.L2 [p];\n\t}" ::"r"(idx), "l"(base));
+}
+
+template <bool FILL, bool CAPPED, bool IMAGES, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     k_nl_filter_flat(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
                      const unsigned long long* __restrict__ srow_start, const uint32_t* __restrict__ srow_count,
                      const uint32_t* __restrict__ snbr, const DevPbc* __restrict__ pbc_g, SearchF32 f, double cutoff2,
@@ -725,7 +744,9 @@ __global__ void __launch_bounds__(256, 3)
                      const unsigned long long* __restrict__ row_start, uint32_t* __restrict__ nbr, unsigned row_cap,
                      unsigned* __restrict__ cap_info, float far2, uint32_t* __restrict__ row_far_off,
                      uint32_t* __restrict__ row_far_cnt, unsigned rows_per_block) {
-  constexpr unsigned kOk = 0x80000000u, kRem = 0xffffu;
+  // trip descriptor: .x = first entry of the trip relative to the block's first super-list row,
+  //                  .y = entries left in the row | row slot of the warp << 16 | kNew (first trip of a row) | kOk
+  constexpr unsigned kOk = 0x80000000u, kNew = 0x40000000u, kRem = 0xffffu;
   constexpr int kRows = 8 * kFltRowsPerWarp;
   __shared__ float4 s_li[kRows];
   __shared__ uint32_t s_m[kRows], s_off[kRows], s_alloc[kRows];
@@ -764,16 +785,19 @@ __global__ void __launch_bounds__(256, 3)
     const unsigned tn = (m + 63u) >> 6;
     uint32_t total;
     unsigned at = warp_exclusive_scan(tn, lane, total);
-    for (unsigned t = 0; t < tn; ++t) s_trip[wid][at++] = make_uint2(off0 + 64u * t, (m - 64u * t) | (lane << 16) | kOk);
+    for (unsigned t = 0; t < tn; ++t)
+      s_trip[wid][at++] = make_uint2(off0 + 64u * t, (m - 64u * t) | (lane << 16) | kOk | (t == 0u ? kNew : 0u));
     if (lane < 6u) s_trip[wid][total + lane] = make_uint2(0u, 0u);  // the pipeline looks up to five trips past the end
     __syncwarp();
   }
   const float c2_hi = f.c2_hi, c2_lo = f.c2_lo;
+  unsigned lt;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
   // row state
-  unsigned cur_r = 0xffffffffu, k = 0u, my_abs = 0u, alloc = 0u, total = 0u, total_far = 0u;
-  bool grp_a = true;
-  float4 li = make_float4(0.f, 0.f, 0.f, 0.f);
-  unsigned long long base = 0ull;
+  unsigned k = 0u, my_abs = 0u, alloc = 0u, total = 0u, total_far = 0u;
+  bool grp_a = true, have_row = false;
+  float lix = 0.f, liy = 0.f, liz = 0.f;
+  uint32_t* __restrict__ rowp = nbr;  // start of the current row's allocation
   auto flush = [&]() {
     if (lane == 0) {
       const unsigned rr = k - row_begin;
@@ -791,78 +815,102 @@ __global__ void __launch_bounds__(256, 3)
       if (CAPPED && all > row_cap) atomicExch(&cap_info[1], 1u);
     }
   };
-  auto test = [&](bool in, uint32_t entry, const float4 lj, bool shifted, bool& far) -> bool {
-    far = false;
-    if (!in) return false;
-    float dx = lj.x - li.x, dy = lj.y - li.y, dz = lj.z - li.z;
-    if (shifted) {
-      const uint32_t code = (entry >> 26) ^ kImageCentre;
-      const float wx = (float)((int)(code & 3u) - 1), wy = (float)((int)((code >> 2) & 3u) - 1),
-                  wz = (float)((int)((code >> 4) & 3u) - 1);
-      dx = lj.x - (li.x - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
-      dy = lj.y - (li.y - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
-      dz = lj.z - (li.z - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+  // One batch = 32 candidates, one per lane.  The kernel is bound by instruction issue (ncu, per-row kernel: 72 % of
+  // the issue slots, 206 instructions per 64-candidate trip), so a batch has no divergent branch: predicates, two
+  // ballots, one predicated store.  Only a candidate inside the FP32 rounding band of the cutoff (a few per 10^4)
+  // takes the warp through the exact FP64 decision.
+  auto batch = [&](bool keep, float r2, uint32_t entry) {
+    const bool band = keep & (r2 > c2_lo);
+    if (__any_sync(0xffffffffu, band)) {
+      if (band) keep = exact_within(pos, perm, pbc_g, k, entry & kSuperIndexMask, two_groups, grp_a, cutoff2);
     }
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    bool keep = (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
-    if (keep && r2 > c2_lo) keep = exact_within(pos, perm, pbc_g, k, entry & kSuperIndexMask, two_groups, grp_a, cutoff2);
-    far = r2 > far2;
-    return keep;
-  };
-  auto emit = [&](bool keep, bool far, uint32_t j) {
-    const unsigned below = (1u << lane) - 1u;
-    const unsigned mn = __ballot_sync(0xffffffffu, keep && !far), mf = __ballot_sync(0xffffffffu, keep && far);
-    if (FILL && keep) {
-      const unsigned at = far ? total_far + __popc(mf & below) : total + __popc(mn & below);
-      if (at < alloc) nbr[base + (far ? alloc - 1u - at : at)] = j;
+    const bool far = r2 > far2;
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    const unsigned mf = __ballot_sync(0xffffffffu, keep & far);
+    const unsigned mn = mk & ~mf;
+    if (FILL) {
+      const unsigned at = (far ? total_far : total) + __popc((far ? mf : mn) & lt);
+      const unsigned idx = far ? alloc - 1u - at : at;
+      if (keep & (at < alloc)) rowp[idx] = IMAGES ? entry : (entry & kSuperIndexMask);
     }
     total += __popc(mn);
     total_far += __popc(mf);
   };
-  const uint32_t* __restrict__ blk = snbr + sb0 + lane;
-  auto ent = [&](const uint2 d, unsigned off) -> uint32_t { return (off + lane < (d.y & kRem)) ? __ldg(blk + d.x + off) : 0u; };
-  uint2 d0 = s_trip[wid][0], d1 = s_trip[wid][1];
-  uint32_t c1 = ent(d0, 0u), c2 = ent(d0, 32u);
-  uint32_t n1 = ent(d1, 0u), n2 = ent(d1, 32u);
-  float4 l1 = __ldg(lpos + (c1 & kSuperIndexMask)), l2 = __ldg(lpos + (c2 & kSuperIndexMask));
-  for (unsigned it = 0; d0.y & kOk; ++it) {
-    {  // the entries stream from HBM: ask L2 for the piece four trips down the table (8 bytes per lane cover 256)
-      const uint2 pd = s_trip[wid][it + 4];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + pd.x + lane));
-    }
-    const uint32_t a1 = c1, a2 = c2;
-    const float4 p1 = l1, p2 = l2;
-    const uint2 dc = d0;
-    c1 = n1;
-    c2 = n2;
-    d0 = d1;
-    d1 = s_trip[wid][it + 2];
-    l1 = __ldg(lpos + (c1 & kSuperIndexMask));  // entry 0 (a valid atom) when past the end of a row
-    l2 = __ldg(lpos + (c2 & kSuperIndexMask));
-    n1 = ent(d1, 0u);
-    n2 = ent(d1, 32u);
-    const unsigned r = wid + 8u * ((dc.y >> 16) & 15u);
-    if (r != cur_r) {
-      if (cur_r != 0xffffffffu) flush();
-      cur_r = r;
+  const uint32_t* __restrict__ blk = snbr + sb0;  // block-uniform; per-lane offsets stay 32-bit
+  struct Set {
+    uint32_t e1, e2;  // entries (lane, lane + 32) of the set's trip
+    uint32_t dy;      // its descriptor (.y)
+    float4 l1, l2;    // their records
+  };
+  unsigned it = 0u;  // next trip of the table
+  auto refill = [&](Set& s) {  // descriptor and entries of the table's next trip, L2 prefetch four trips down
+    const uint2 d = s_trip[wid][it];
+    const uint2 pd = s_trip[wid][it + 4];
+    ++it;
+    const unsigned rem = d.y & kRem;
+    s.dy = d.y;
+    s.e1 = (lane < rem) ? load_u32_idx(blk, d.x + lane) : 0u;  // 0 = sorted atom 0, home image: a valid record
+    s.e2 = (lane + 32u < rem) ? load_u32_idx(blk, d.x + 32u + lane) : 0u;
+    prefetch_l2_idx(blk, pd.x + 2u * lane);  // 8 bytes per lane cover the 256 bytes of a trip
+  };
+  auto request = [&](Set& s) {
+    s.l1 = load_f4_idx(lpos, s.e1 & kSuperIndexMask);
+    s.l2 = load_f4_idx(lpos, s.e2 & kSuperIndexMask);
+  };
+  // one trip: `cur` holds its entries and (arrived) records, `nxt` the entries of the next trip.  As in k_sweep_img,
+  // everything the trip waits for is consumed before it issues new loads (two register sets alternate, no copies).
+  auto step = [&](Set& cur, Set& nxt) {
+    const uint32_t a1 = cur.e1, a2 = cur.e2, dy = cur.dy;
+    if (dy & kNew) {  // a new row starts with this trip
+      if (have_row) flush();
+      have_row = true;
+      const unsigned r = wid + 8u * ((dy >> 16) & 15u);
       k = first + r;
-      li = s_li[r];
+      const float4 li = s_li[r];
+      lix = li.x;
+      liy = li.y;
+      liz = li.z;
       my_abs = __float_as_uint(li.w);
       grp_a = (k < n_a);
       alloc = s_alloc[r];
-      base = s_base[r];
+      if (FILL) rowp = nbr + s_base[r];
       total = total_far = 0u;
     }
-    const unsigned rem = dc.y & kRem;
-    const bool in1 = lane < rem, in2 = lane + 32u < rem;
-    const bool shifted = __any_sync(0xffffffffu, ((a1 | a2) & ~kSuperIndexMask) != 0u);
-    bool f1, f2;
-    const bool k1 = test(in1, a1, p1, shifted, f1);
-    const bool k2 = test(in2, a2, p2, shifted, f2);
-    emit(k1, f1, IMAGES ? a1 : (a1 & kSuperIndexMask));
-    if (rem > 32u) emit(k2, f2, IMAGES ? a2 : (a2 & kSuperIndexMask));
+    const unsigned rem = dy & kRem;
+    float dx1 = cur.l1.x - lix, dy1 = cur.l1.y - liy, dz1 = cur.l1.z - liz;
+    float dx2 = cur.l2.x - lix, dy2 = cur.l2.y - liy, dz2 = cur.l2.z - liz;
+    if (__any_sync(0xffffffffu, (a1 | a2) > kSuperIndexMask)) {  // some entry is seen through a periodic image
+      auto shifted = [&](uint32_t entry, const float4 lj, float& dx, float& dy_, float& dz) {
+        const uint32_t code = (entry >> 26) ^ kImageCentre;
+        const float wx = (float)((int)(code & 3u) - 1), wy = (float)((int)((code >> 2) & 3u) - 1),
+                    wz = (float)((int)((code >> 4) & 3u) - 1);
+        dx = lj.x - (lix - (wx * f.box[0] + wy * f.box[3] + wz * f.box[6]));
+        dy_ = lj.y - (liy - (wx * f.box[1] + wy * f.box[4] + wz * f.box[7]));
+        dz = lj.z - (liz - (wx * f.box[2] + wy * f.box[5] + wz * f.box[8]));
+      };
+      shifted(a1, cur.l1, dx1, dy1, dz1);
+      shifted(a2, cur.l2, dx2, dy2, dz2);
+    }
+    const bool ne1 = __float_as_uint(cur.l1.w) != my_abs, ne2 = __float_as_uint(cur.l2.w) != my_abs;
+    // issue side: records of the next trip, entries of the trip after next
+    request(nxt);
+    refill(cur);
+    const float r1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
+    const float r2 = fmaf(dz2, dz2, fmaf(dy2, dy2, dx2 * dx2));
+    batch((lane < rem) & ne1 & (r1 < c2_hi), r1, a1);  // j != k already holds in the super-list
+    if (rem > 32u) batch((lane + 32u < rem) & ne2 & (r2 < c2_hi), r2, a2);
+  };
+  Set A, B;
+  refill(A);
+  refill(B);
+  request(A);
+  for (;;) {
+    if (!(A.dy & kOk)) break;
+    step(A, B);
+    if (!(B.dy & kOk)) break;
+    step(B, A);
   }
-  if (cur_r != 0xffffffffu) flush();
+  if (have_row) flush();
 }
 
 __global__ void k_regular_offsets(unsigned rows, unsigned row_cap, unsigned long long* __restrict__ row_start) {
@@ -1184,7 +1232,7 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
                       const DevPbc& box, double cutoff2, double band_rel, unsigned n_a, int two_groups, unsigned row_begin,
                       unsigned row_end, uint32_t* row_count, unsigned long long* row_start, uint32_t* nbr, unsigned row_cap,
                       unsigned* cap_info, float far2, uint32_t* row_far_off, uint32_t* row_far_cnt, unsigned max_srow,
-                      cudaStream_t st) {
+                      int flat_minb, cudaStream_t st) {
   const unsigned rows = row_end - row_begin;
   if (!rows) return;
   const unsigned blocks = (unsigned)(((unsigned long long)rows * 32ull + 255ull) / 256ull);
@@ -1202,14 +1250,21 @@ void launch_nl_filter(int mode /*0 count, 1 fill, 2 capped single pass*/, bool i
 #define B200_FLAT_ARGS pos, perm, lpos, srow_start, srow_count, snbr, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                        row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt, rpb
     if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-    if (mode == 0) k_nl_filter_flat<false, false, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
-    else if (images) {
-      if (mode == 1) k_nl_filter_flat<true, false, true><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
-      else k_nl_filter_flat<true, true, true><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
-    } else {
-      if (mode == 1) k_nl_filter_flat<true, false, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
-      else k_nl_filter_flat<true, true, false><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);
-    }
+#define B200_FLAT_GO(MB)                                                                                     \
+    do {                                                                                                       \
+      if (mode == 0) k_nl_filter_flat<false, false, false, MB><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);            \
+      else if (images) {                                                                                       \
+        if (mode == 1) k_nl_filter_flat<true, false, true, MB><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);            \
+        else k_nl_filter_flat<true, true, true, MB><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);                       \
+      } else {                                                                                                 \
+        if (mode == 1) k_nl_filter_flat<true, false, false, MB><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);           \
+        else k_nl_filter_flat<true, true, false, MB><<<fb, 256, 0, st>>>(B200_FLAT_ARGS);                      \
+      }                                                                                                        \
+    } while (0)
+    // 2 resident blocks per SM: 122 registers, nothing spilled; 3: 80 registers, ~12 spill accesses per trip
+    if (flat_minb == 3) B200_FLAT_GO(3);
+    else B200_FLAT_GO(2);
+#undef B200_FLAT_GO
 #undef B200_FLAT_ARGS
     return;
   }
