@@ -475,6 +475,24 @@ struct SearchF32 {
 
 // SUPER: the rows of the super-list (cutoff + delta, kernels.cuh): entries carry the periodic image they were found
 // through in their top 6 bits, no near/far split.
+// float4 record `idx`: address = one IMAD.WIDE (index * 16 + base), one 128-bit load
+__device__ __forceinline__ float4 load_f4_idx(const float4* __restrict__ base, uint32_t idx) {
+  float4 v;
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %4, 16, %5;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [p];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(idx), "l"(base));
+  return v;
+}
+// 32-bit word `idx` of a block-uniform array: one IMAD.WIDE + load, no per-lane 64-bit pointer to keep alive
+__device__ __forceinline__ uint32_t load_u32_idx(const uint32_t* __restrict__ base, uint32_t idx) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %1, 4, %2;\n\tld.global.nc.u32 %0, [p];\n\t}" : "=r"(v) : "r"(idx), "l"(base));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_idx(const uint32_t* __restrict__ base, uint32_t idx) {
+  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %0, 4, %1;\n\tprefetch.global.L2 [p];\n\t}" ::"r"(idx), "l"(base));
+}
+
 template <bool FILL, bool CAPPED, bool SUPER, bool IMAGES>
 __global__ void __launch_bounds__(256, 4)
     k_nl_rows_f32(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
@@ -539,25 +557,28 @@ __global__ void __launch_bounds__(256, 4)
   // start, far ones backwards from its end (two-pass build: row_count still holds the total of the count pass)
   const unsigned alloc = CAPPED ? row_cap : (FILL ? ((row_count[k - row_begin] + 3u) & ~3u) : 0u);
 
-  // exact decision for a candidate inside the FP32 rounding band (NeighborList.cpp:246-259)
-  auto exact_keep = [&](uint32_t j) -> bool { return exact_within(pos, perm, pbc_g, k, j, two_groups, my_grp == 0u, cutoff2); };
-  auto test = [&](uint32_t j, const float4 lj, float ox, float oy, float oz, bool& far) -> bool {
-    const float dx = lj.x - ox, dy = lj.y - oy, dz = lj.z - oz;
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    bool keep = (j != k) && (__float_as_uint(lj.w) != my_abs) && (r2 < c2_hi);
-    if (keep && r2 > c2_lo) keep = exact_keep(j);
-    far = !SUPER && (r2 > far2);  // only orders the row: any classification gives the same results
-    return keep;
-  };
-  auto emit = [&](bool keep, bool far, uint32_t j, uint32_t img) {
-    const unsigned below = (1u << lane) - 1u;
-    const unsigned mn = __ballot_sync(0xffffffffu, keep && !far), mf = __ballot_sync(0xffffffffu, keep && far);
-    if (FILL && keep) {
-      const unsigned at = far ? total_far + __popc(mf & below) : total + __popc(mn & below);
-      if (at < alloc) nbr[base + (far ? alloc - 1u - at : at)] = j | img;
+  // One batch = 32 candidates, one per lane, without divergent branches (the kernel is bound by instruction issue):
+  // predicates, two ballots, one predicated store.  A candidate inside the FP32 rounding band of the cutoff takes the
+  // warp through the exact FP64 decision (NeighborList.cpp:246-259).
+  unsigned lt;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+  uint32_t* __restrict__ rowp = FILL ? nbr + base : nbr;
+  auto batch = [&](bool keep, float r2, uint32_t j, uint32_t img) {
+    const bool band = keep & (r2 > c2_lo);
+    if (__any_sync(0xffffffffu, band)) {
+      if (band) keep = exact_within(pos, perm, pbc_g, k, j, two_groups, my_grp == 0u, cutoff2);
+    }
+    const bool far = !SUPER && (r2 > far2);  // only orders the row: any classification gives the same results
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    const unsigned mf = SUPER ? 0u : __ballot_sync(0xffffffffu, keep & far);
+    const unsigned mn = mk & ~mf;
+    if (FILL) {
+      const unsigned at = (far ? total_far : total) + __popc((far ? mf : mn) & lt);
+      const unsigned idx = far ? alloc - 1u - at : at;
+      if (keep & (at < alloc)) rowp[idx] = j | img;
     }
     total += __popc(mn);
-    total_far += __popc(mf);
+    if (!SUPER) total_far += __popc(mf);
   };
   // one contiguous range: two 32-candidate batches per trip so that two loads are in flight per lane
   auto scan_range = [&](uint32_t s, uint32_t m, int wx, int wyy, int wzz) {
@@ -569,13 +590,14 @@ __global__ void __launch_bounds__(256, 4)
       const uint32_t e1 = e0 + lane, e2 = e1 + 32;
       const bool in1 = e1 < m, in2 = e2 < m;
       const uint32_t j1 = s + e1, j2 = s + e2;
-      const float4 l1 = __ldg(lpos + (in1 ? j1 : k));
-      const float4 l2 = __ldg(lpos + (in2 ? j2 : k));
-      bool f1, f2;
-      const bool k1 = in1 && test(j1, l1, ox, oy, oz, f1);
-      const bool k2 = in2 && test(j2, l2, ox, oy, oz, f2);
-      emit(k1, f1, j1, img);
-      if (e0 + 32 < m) emit(k2, f2, j2, img);
+      const float4 l1 = load_f4_idx(lpos, in1 ? j1 : k);
+      const float4 l2 = load_f4_idx(lpos, in2 ? j2 : k);
+      const float dx1 = l1.x - ox, dy1 = l1.y - oy, dz1 = l1.z - oz;
+      const float dx2 = l2.x - ox, dy2 = l2.y - oy, dz2 = l2.z - oz;
+      const float r1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
+      const float r2 = fmaf(dz2, dz2, fmaf(dy2, dy2, dx2 * dx2));
+      batch(in1 & (j1 != k) & (__float_as_uint(l1.w) != my_abs) & (r1 < c2_hi), r1, j1, img);
+      if (e0 + 32 < m) batch(in2 & (j2 != k) & (__float_as_uint(l2.w) != my_abs) & (r2 < c2_hi), r2, j2, img);
     }
   };
   for (int col = 0; col < ncol; ++col) {
@@ -716,24 +738,6 @@ __global__ void __launch_bounds__(256, 3)
 constexpr int kFltRowsPerWarp = 16;
 constexpr int kFltTripCap = 208;
 constexpr int kFltMinBlocks = 2;   // resident blocks per SM the register allocation is sized for  // trips per warp the table holds (launch_nl_filter sizes rows_per_block for it)
-
-// float4 record `idx`: address = one IMAD.WIDE (index * 16 + base), one 128-bit load
-__device__ __forceinline__ float4 load_f4_idx(const float4* __restrict__ base, uint32_t idx) {
-  float4 v;
-  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %4, 16, %5;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [p];\n\t}"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(idx), "l"(base));
-  return v;
-}
-// 32-bit word `idx` of a block-uniform array: one IMAD.WIDE + load, no per-lane 64-bit pointer to keep alive
-__device__ __forceinline__ uint32_t load_u32_idx(const uint32_t* __restrict__ base, uint32_t idx) {
-  uint32_t v;
-  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %1, 4, %2;\n\tld.global.nc.u32 %0, [p];\n\t}" : "=r"(v) : "r"(idx), "l"(base));
-  return v;
-}
-__device__ __forceinline__ void prefetch_l2_idx(const uint32_t* __restrict__ base, uint32_t idx) {
-  asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %0, 4, %1;\n\tprefetch.global.L2 [p];\n\t}" ::"r"(idx), "l"(base));
-}
 
 template <bool FILL, bool CAPPED, bool IMAGES, int MINB>
 __global__ void __launch_bounds__(256, MINB)
