@@ -246,6 +246,13 @@ int b200coord_group_set_charges(b200coord_group* g, const double* charges);
 int b200coord_group_set_types(b200coord_group* g, const unsigned* types, unsigned ntypes, const double* etas);
 int b200coord_group_calculate(b200coord_group* g, const double* pos, double* value, double* deriv, double* virial);
 
+/* ---- frames known in advance (trajectory post-processing; plumed driver, src/cltools/Driver.cpp): two steps in flight,
+   the upload of the next frame and the download of the previous result overlap the sweep of the current one.
+   b200coord_prepare(step) before every submit as before a calculate.  `deriv` (page-locked for a real overlap) is
+   complete, and *value / virial[9] are written, when the second submit after this one or b200coord_collect returns. */
+int b200coord_submit(b200coord_ctx* ctx, const double* pos, double* value, double* deriv, double* virial);
+int b200coord_collect(b200coord_ctx* ctx);
+
 /* ---- an MD engine that keeps positions and forces on the GPU. The reference's engines hand host
    pointers to plumed_cmd (patches/gromacs-2025.0.diff/src/gromacs/applied_forces/plumed/plumedforceprovider.cpp:171-204)
    and PLUMED copies them in and out (src/core/ActionAtomistic.cpp:444-537). Here the engine publishes its device

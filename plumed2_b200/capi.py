@@ -29,7 +29,7 @@ EXPORTED = ["b200coord_abi_version", "b200coord_switch_parse", "b200coord_switch
             "b200coord_comm_unique_id", "b200coord_comm_init", "b200coord_host_alloc", "b200coord_host_free",
             "b200coord_coupling_publish", "b200coord_coupling_withdraw", "b200coord_coupling_lookup",
             "b200coord_coupled_set_index", "b200coord_calculate_coupled", "b200coord_apply_coupled",
-            "b200coord_coupled_derivatives",
+            "b200coord_coupled_derivatives", "b200coord_submit", "b200coord_collect",
             "b200coord_device_alloc", "b200coord_device_free", "b200coord_memcpy_h2d", "b200coord_memcpy_d2h",
             "b200coord_device_synchronize", "b200coord_enqueue_device", "b200coord_stream_mark",
             "b200coord_stream_elapsed_ms", "b200coord_calculate_distributed", "b200coord_my_slice",
@@ -116,6 +116,8 @@ def lib():
     L.b200coord_calculate_coupled.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.b200coord_apply_coupled.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
     L.b200coord_coupled_derivatives.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200coord_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200coord_collect.argtypes = [C.c_void_p]
     L.b200coord_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.b200coord_host_free.argtypes = [C.c_void_p]
     L.b200coord_device_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]

@@ -206,6 +206,17 @@ struct b200coord_ctx {
   bool filter_flat = true;            // B200COORD_FILTER_FLAT=0: the per-row filter kernel
   int filter_minb = 2;                // B200COORD_FILTER_MINB=3: the 80-register build of the flat filter (3 blocks per SM)
   bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
+  // frames known in advance (b200coord_submit / _collect): two steps in flight, copies on their own streams
+  struct Pending {
+    bool busy = false;
+    double* value = nullptr;
+    double* virial = nullptr;
+  } pend[2];
+  cudaStream_t st_up = nullptr, st_down = nullptr;
+  cudaEvent_t q_up[2] = {nullptr, nullptr}, q_done[2] = {nullptr, nullptr}, q_down[2] = {nullptr, nullptr};
+  DevBuf<double> d_posq[2], d_outq[2];
+  double* h_tailq = nullptr;          // pinned: 2 x [virial 9 | value]
+  unsigned q_next = 0;
   // coupling with an engine whose arrays live on the device: where the action's atoms sit in the engine's arrays
   DevBuf<uint32_t> d_cidx;
   bool cidx_set = false;              // false: atom i of the action is atom i of the engine
@@ -1347,6 +1358,16 @@ void b200coord_destroy(b200coord_ctx* c) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2 * b200coord_ctx::kRing; ++i)
     if (c->sweep_ev[i]) cudaEventDestroy(c->sweep_ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    c->d_posq[i].release();
+    c->d_outq[i].release();
+    if (c->q_up[i]) cudaEventDestroy(c->q_up[i]);
+    if (c->q_done[i]) cudaEventDestroy(c->q_done[i]);
+    if (c->q_down[i]) cudaEventDestroy(c->q_down[i]);
+  }
+  if (c->h_tailq) cudaFreeHost(c->h_tailq);
+  if (c->st_up) cudaStreamDestroy(c->st_up);
+  if (c->st_down) cudaStreamDestroy(c->st_down);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -1446,6 +1467,72 @@ int b200coord_enqueue_device(b200coord_ctx* c, const double* d_pos, double* d_ou
     CU(c, cudaMemcpyAsync(d_out + 3 * (size_t)c->n, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToDevice, c->st));
   else
     CU(c, cudaMemcpyAsync(d_out, c->d_out.p, sizeof(double) * (3 * (size_t)c->n + 10), cudaMemcpyDeviceToDevice, c->st));
+  return B200COORD_OK;
+}
+
+// ---- frames known in advance (trajectory post-processing: plumed driver reads the next frame while this one is
+// computed, src/cltools/Driver.cpp).  Two steps are in flight: the upload of frame k+1 and the download of result k-1
+// run on their own streams under the sweep of frame k.  Results are the ones b200coord_calculate returns, bit for bit.
+namespace {
+int finish_pending(b200coord_ctx* c, int slot) {
+  b200coord_ctx::Pending& p = c->pend[slot];
+  if (!p.busy) return B200COORD_OK;
+  CU(c, cudaEventSynchronize(c->q_down[slot]));
+  const double* t = c->h_tailq + 10 * slot;
+  for (int i = 0; i < 9; ++i) p.virial[i] = t[i];
+  *p.value = t[9];
+  p.busy = false;
+  return B200COORD_OK;
+}
+}  // namespace
+
+int b200coord_submit(b200coord_ctx* c, const double* pos, double* value, double* deriv, double* virial) {
+  if (!c || !pos || !value || !deriv || !virial) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  if (c->cfg.nranks > 1) return fail(c, B200COORD_ERR_UNSUPPORTED, "b200coord_submit is a single-context call");
+  CU(c, cudaSetDevice(c->device));
+  const size_t n3 = 3 * (size_t)c->n;
+  if (!c->st_up) {
+    CU(c, cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->st_down, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(c, cudaEventCreateWithFlags(&c->q_up[i], cudaEventDisableTiming));
+      CU(c, cudaEventCreateWithFlags(&c->q_done[i], cudaEventDisableTiming));
+      CU(c, cudaEventCreateWithFlags(&c->q_down[i], cudaEventDisableTiming));
+      CU(c, c->d_posq[i].reserve(n3));
+      CU(c, c->d_outq[i].reserve(n3 + 10));
+    }
+    CU(c, cudaHostAlloc((void**)&c->h_tailq, 20 * sizeof(double), cudaHostAllocDefault));
+  }
+  const int slot = (int)(c->q_next & 1u);
+  int rc = finish_pending(c, slot);  // the step that used this slot two submits ago
+  if (rc) return rc;
+  maybe_pin(c, 0, pos, sizeof(double) * n3);
+  CU(c, cudaMemcpyAsync(c->d_posq[slot].p, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, c->st_up));
+  CU(c, cudaEventRecord(c->q_up[slot], c->st_up));
+  CU(c, cudaStreamWaitEvent(c->st, c->q_up[slot], 0));
+  rc = b200coord_enqueue_device(c, c->d_posq[slot].p, c->d_outq[slot].p);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->q_done[slot], c->st));
+  CU(c, cudaStreamWaitEvent(c->st_down, c->q_done[slot], 0));
+  CU(c, cudaMemcpyAsync(deriv, c->d_outq[slot].p, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->st_down));
+  CU(c, cudaMemcpyAsync(c->h_tailq + 10 * slot, c->d_outq[slot].p + n3, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st_down));
+  CU(c, cudaEventRecord(c->q_down[slot], c->st_down));
+  c->pend[slot].busy = true;
+  c->pend[slot].value = value;
+  c->pend[slot].virial = virial;
+  c->q_next++;
+  return B200COORD_OK;
+}
+
+int b200coord_collect(b200coord_ctx* c) {
+  if (!c) return fail(c, B200COORD_ERR_INVALID, "null argument");
+  CU(c, cudaSetDevice(c->device));
+  for (int i = 0; i < 2; ++i) {  // oldest first
+    const int rc = finish_pending(c, (int)((c->q_next + (unsigned)i) & 1u));
+    if (rc) return rc;
+  }
+  CU(c, cudaStreamSynchronize(c->st));
+  refresh_stats(c);
   return B200COORD_OK;
 }
 
