@@ -644,3 +644,48 @@ def test_neighbour_list_as_a_tool_device_pairs(groups):
     s = torch.where(r2 <= sw.dmax_2, (1.0 / (1.0 + y ** 3)) * sw.stretch + sw.shift, torch.zeros_like(r2))
     assert abs(float(s.sum().item()) - c.value) <= 1e-10 * abs(c.value)
     c.close()
+
+
+@pytest.mark.parametrize("line", [
+    "c: COORDINATION GROUPA=1-5000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=3",
+    "c: COORDINATION GROUPA=1-500 GROUPB=501-5000 SWITCH={EXP R_0=0.2 D_MAX=0.9} NLISTCELLS NL_CUTOFF=1.0 NL_STRIDE=2",
+    "c: COORDINATION GROUPA=1-2500 GROUPB=2501-5000 PAIR R_0=0.3",
+])
+def test_frames_submitted_ahead_give_the_synchronous_results(line):
+    """b200coord_submit / _collect (two steps in flight, copies on their own streams): every frame's value, derivatives
+    and virial are bit for bit what b200coord_calculate returns for the same sequence"""
+    import ctypes as C
+    n = 5000
+    pos0, box = water_box(n, 100.0, seed=77, triclinic=True)
+    rng = np.random.default_rng(5)
+    frames = []
+    p = pos0
+    for _ in range(11):
+        p = p + 0.004 * rng.standard_normal(p.shape)
+        frames.append(np.ascontiguousarray(p))
+    ref = []
+    c = P.Coordination.from_input(line)
+    for step, f in enumerate(frames):
+        c.prepare(step)
+        c.calculate(f, box)
+        ref.append((c.value, c.derivatives.copy(), c.virial.copy()))
+    c.close()
+    c = P.Coordination.from_input(line)
+    c._set_box(box)
+    L = c._L
+    vals = [C.c_double(0) for _ in frames]
+    ders = [np.full((c.n, 3), np.nan) for _ in frames]
+    virs = [np.full(9, np.nan) for _ in frames]
+    gathered = [c.gather(f).copy() for f in frames]
+    for step in range(len(frames)):
+        c.prepare(step)
+        capi.check(L.b200coord_submit(c._ctx, gathered[step].ctypes.data_as(C.c_void_p), C.byref(vals[step]),
+                                      ders[step].ctypes.data_as(C.c_void_p), virs[step].ctypes.data_as(C.c_void_p)), c._ctx)
+        if step >= 2:  # the step submitted two calls ago has been delivered
+            assert vals[step - 2].value == ref[step - 2][0]
+    capi.check(L.b200coord_collect(c._ctx), c._ctx)
+    for step in range(len(frames)):
+        assert vals[step].value == ref[step][0], step
+        np.testing.assert_array_equal(ders[step], ref[step][1], err_msg="step %d" % step)
+        np.testing.assert_array_equal(virs[step].reshape(3, 3), ref[step][2].reshape(3, 3), err_msg="step %d" % step)
+    c.close()
