@@ -682,10 +682,17 @@ def test_frames_submitted_ahead_give_the_synchronous_results(line):
         capi.check(L.b200coord_submit(c._ctx, gathered[step].ctypes.data_as(C.c_void_p), C.byref(vals[step]),
                                       ders[step].ctypes.data_as(C.c_void_p), virs[step].ctypes.data_as(C.c_void_p)), c._ctx)
         if step >= 2:  # the step submitted two calls ago has been delivered
-            assert vals[step - 2].value == ref[step - 2][0]
+            assert abs(vals[step - 2].value - ref[step - 2][0]) <= 1e-13 * abs(ref[step - 2][0])
     capi.check(L.b200coord_collect(c._ctx), c._ctx)
+    # few GROUPA atoms among many GROUPB atoms: the GROUPA rows add to their partners with atomics, whose
+    # order is not fixed from run to run; everything else is bit-reproducible
+    exact = "NLISTCELLS" not in line
     for step in range(len(frames)):
-        assert vals[step].value == ref[step][0], step
-        np.testing.assert_array_equal(ders[step], ref[step][1], err_msg="step %d" % step)
-        np.testing.assert_array_equal(virs[step].reshape(3, 3), ref[step][2].reshape(3, 3), err_msg="step %d" % step)
+        if exact:
+            assert vals[step].value == ref[step][0], step
+            np.testing.assert_array_equal(ders[step], ref[step][1], err_msg="step %d" % step)
+            np.testing.assert_array_equal(virs[step].reshape(3, 3), ref[step][2].reshape(3, 3), err_msg="step %d" % step)
+        else:
+            assert abs(vals[step].value - ref[step][0]) <= 1e-13 * abs(ref[step][0]), step
+            assert rel_err(ders[step], ref[step][1]) <= 1e-13 and rel_err(virs[step].reshape(3, 3), ref[step][2].reshape(3, 3)) <= 1e-13
     c.close()
