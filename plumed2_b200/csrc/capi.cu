@@ -206,6 +206,7 @@ struct b200coord_ctx {
   bool filter_flat = true;            // B200COORD_FILTER_FLAT=0: the per-row filter kernel
   int filter_minb = 2;                // B200COORD_FILTER_MINB=3: the 80-register build of the flat filter (3 blocks per SM)
   bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
+  bool in_process = false;            // one of several contexts of ONE process (b200coord_group_*), see collective_done
   // frames known in advance (b200coord_submit / _collect): two steps in flight, copies on their own streams
   struct Pending {
     bool busy = false;
@@ -386,6 +387,7 @@ int ensure_cell_arrays(b200coord_ctx* c) {
 }
 
 void needed_all(b200coord_ctx* c);
+int collective_done(b200coord_ctx* c);
 int build_tile_work(b200coord_ctx* c);
 
 // no neighbour list: one "cell" per group holding every atom in slot order (NeighborList.cpp:133-140 order)
@@ -665,6 +667,10 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
         NcclApi& api = nccl_api();
         ncclResult_t r = api.AllReduce(c->d_u64.p + 11, c->d_u64.p + 11, 1, ncclUint64, ncclMax, c->comm, c->st);
         if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce(displacement): ") + api.GetErrorString(r));
+        {
+          const int rcd = collective_done(c);
+          if (rcd) return rcd;
+        }
       }
       CU(c, cudaMemcpyAsync(c->h_u64 + 2, c->d_u64.p + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
@@ -812,20 +818,30 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   return B200COORD_OK;
 }
 
+// Several contexts in ONE process (b200coord_group_*, worker thread per device): a CUDA call that synchronises a device
+// -- the first launch of a kernel under lazy module loading, a growing local-memory pool, cudaFree -- can sit on a
+// driver lock while it waits for that device's NCCL kernel, which waits for a peer whose thread needs the same lock to
+// launch its part (seen as a hang of the 2-device group test).  So a thread of such a context does nothing else while
+// a collective of its context is in flight.  One process per device (MPI, torchrun) keeps the collectives asynchronous.
+int collective_done(b200coord_ctx* c) {
+  if (c->in_process) CU(c, cudaStreamSynchronize(c->st));
+  return B200COORD_OK;
+}
+
 int combine_ranks(b200coord_ctx* c) {
   NcclApi& api = nccl_api();
   ncclResult_t r;
   if (c->cfg.style == B200COORD_STYLE_PAIR) {
     r = api.AllReduce(c->d_out.p, c->d_out.p, (size_t)3 * c->n + 10, ncclDouble, ncclSum, c->comm, c->st);
     if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
-    return B200COORD_OK;
+    return collective_done(c);
   }
   // every rank owns complete derivatives for its rows: all-gather the row slices (sorted order), and
   // all-reduce the 10 scalars (virial + value) -- the Comm::Sum of CoordinationBase.cpp:218-224
   if (c->peer_mode) {  // rows were already stored into every peer by the sweep kernel; this all-reduce also orders the ranks
     r = api.AllReduce(c->d_out.p + (size_t)3 * c->n, c->d_out.p + (size_t)3 * c->n, 10, ncclDouble, ncclSum, c->comm, c->st);
     if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce: ") + api.GetErrorString(r));
-    return B200COORD_OK;
+    return collective_done(c);
   }
   api.GroupStart();
   r = api.AllGather(c->d_sderiv.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_sderiv.p, (size_t)3 * c->row_chunk,
@@ -836,7 +852,7 @@ int combine_ranks(b200coord_ctx* c) {
   if (r != ncclSuccess || r2 != ncclSuccess || r3 != ncclSuccess)
     return fail(c, B200COORD_ERR_NCCL, std::string("nccl combine: ") +
                                            api.GetErrorString(r != ncclSuccess ? r : (r2 != ncclSuccess ? r2 : r3)));
-  return B200COORD_OK;
+  return collective_done(c);
 }
 
 // the whole per-step device pipeline on c->st; d_pos device positions, result left in c->d_out
@@ -1569,7 +1585,7 @@ static int rank_barrier(b200coord_ctx* c) {
   NcclApi& api = nccl_api();
   ncclResult_t r = api.AllReduce(c->d_small.p + 24, c->d_small.p + 24, 1, ncclDouble, ncclSum, c->comm, c->st);
   if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce(barrier): ") + api.GetErrorString(r));
-  return B200COORD_OK;
+  return collective_done(c);
 }
 
 // does the coming step keep its list AND its continuous coordinates?  Then a rank only needs the positions of the
@@ -1609,6 +1625,8 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
       ncclResult_t r = api.AllGather(c->d_pos.p + (size_t)3 * c->row_chunk * c->cfg.rank, c->d_pos.p, (size_t)3 * c->row_chunk,
                                      ncclDouble, c->comm, c->st);
       if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
+      rc = collective_done(c);
+      if (rc) return rc;
     }
     rc = run_device(c, c->d_pos.p, nullptr, sliced ? c->slot_begin : 0u, sliced ? c->slot_count : 0xffffffffu);
   }
@@ -2009,6 +2027,7 @@ int b200coord_group_create(const b200coord_config* cfg, const b200coord_switch* 
       for (auto* x : g->ctx) b200coord_destroy(x);
       return rc;
     }
+    g->ctx[(size_t)r]->in_process = (ndevices > 1);
   }
   for (int r = 0; r < ndevices; ++r) g->workers.emplace_back(group_worker, g.get(), r);
   b200coord_group* gp = g.release();
