@@ -230,7 +230,23 @@ struct b200coord_ctx {
 
 namespace {
 
+// B200COORD_TRACE=1: one line on stderr at the main stations of a step (which rank is where when something waits)
+bool trace_on() {
+  static const bool on = [] { const char* e = std::getenv("B200COORD_TRACE"); return e && std::atoi(e) != 0; }();
+  return on;
+}
+#define B200_TRACE(c, ...)                                                              \
+  do {                                                                                  \
+    if (trace_on()) {                                                                   \
+      std::fprintf(stderr, "[b200coord r%d/%d dev%d] ", (c)->cfg.rank, (c)->cfg.nranks, (c)->device); \
+      std::fprintf(stderr, __VA_ARGS__);                                                \
+      std::fprintf(stderr, "\n");                                                       \
+      std::fflush(stderr);                                                              \
+    }                                                                                   \
+  } while (0)
+
 int fail(b200coord_ctx* c, int code, const std::string& msg) {
+  if (c) B200_TRACE(c, "FAIL %d: %s", code, msg.c_str());
   if (c) c->err = msg;
   g_last_error = msg;
   return code;
@@ -607,6 +623,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
   // the device and answered with the exact two-pass build), else count + scan + fill.
   auto build_rows = [&](auto&& launch, bool cappable) -> int {
     auto two_pass = [&]() -> int {
+      B200_TRACE(c, "rebuild: count pass");
       launch(0);
       launch_scan_rows(c->d_rowcount.p, rows, 3u, c->d_bsum.p, c->d_rowstart.p, c->d_u64.p, c->st);
       CU(c, cudaMemcpyAsync(c->h_u64, c->d_u64.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
@@ -621,6 +638,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
         if (cappable) need = std::max(need, (size_t)rows * next_row_cap(c->h_capinfo[0], 0u));
         CU(c, c->d_nbr.reserve(need + 4));
       }
+      B200_TRACE(c, "rebuild: fill pass, %llu entries", (unsigned long long)c->nbr_total);
       launch(1);
       c->stats.kernel_launches += 5;
       return B200COORD_OK;
@@ -630,9 +648,11 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
     if (cappable && c->row_cap > 0) {
       c->nbr_total = (unsigned long long)rows * c->row_cap;
       CU(c, c->d_nbr.reserve((size_t)c->nbr_total + 4));
+      B200_TRACE(c, "rebuild: single pass into rows of %u", c->row_cap);
       launch(2);
       CU(c, cudaMemcpyAsync(c->h_capinfo, c->d_capinfo.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
       CU(c, cudaStreamSynchronize(c->st));
+      B200_TRACE(c, "rebuild: single pass done, longest row %u overflow %u", c->h_capinfo[0], c->h_capinfo[1]);
       CU_LAST(c, "neighbour list single-pass build");
       c->stats.kernel_launches += 2;
       done = (c->h_capinfo[1] == 0);
@@ -666,6 +686,7 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
         // the largest displacement anywhere (non-negative doubles order like their bit patterns)
         NcclApi& api = nccl_api();
         ncclResult_t r = api.AllReduce(c->d_u64.p + 11, c->d_u64.p + 11, 1, ncclUint64, ncclMax, c->comm, c->st);
+        B200_TRACE(c, "rebuild: displacement all-reduce enqueued");
         if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllReduce(displacement): ") + api.GetErrorString(r));
         {
           const int rcd = collective_done(c);
@@ -873,8 +894,10 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
   if (!d_pos && (need_rebuild || c->cfg.style == B200COORD_STYLE_PAIR))
     return fail(c, B200COORD_ERR_STATE, "internal: a rebuild step needs the whole position array");
   if (need_rebuild) {
+    B200_TRACE(c, "rebuild starts");
     int rc = rebuild(c, d_pos);
     if (rc) return rc;
+    B200_TRACE(c, "rebuild done");
     c->invalidate = false;
   }
   {
@@ -1057,8 +1080,10 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
   launch_finalize(c->d_partials.p, nblocks, weight, c->d_out.p + (size_t)3 * c->n, c->d_fin.p, c->st);
   c->stats.kernel_launches += 2;
   if (c->comm) {
+    B200_TRACE(c, "sweep launched (%d blocks), combining", nblocks);
     int rc = combine_ranks(c);
     if (rc) return rc;
+    B200_TRACE(c, "combined");
   }
   if (c->cfg.style != B200COORD_STYLE_PAIR) {
     RowSrc rows;
@@ -1606,12 +1631,14 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   maybe_pin(c, 0, pos_slice, sizeof(double) * cnt);
   maybe_pin(c, 1, deriv_slice, sizeof(double) * cnt);
   int rc;
+  B200_TRACE(c, "calculate_distributed: pull=%d list_valid=%d invalidate=%d", (int)step_can_pull(c), (int)c->list_valid, (int)c->invalidate);
   CU(c, cudaEventRecord(c->ev[0], c->st));
   if (step_can_pull(c)) {
     c->pos_parity ^= 1u;
     if (cnt) CU(c, cudaMemcpyAsync(c->d_pslice[c->pos_parity].p, pos_slice, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->st));
     CU(c, cudaEventRecord(c->ev[1], c->st));
     rc = rank_barrier(c);  // every rank's slice is in place before anybody gathers from it
+    B200_TRACE(c, "barrier passed");
     if (rc) return rc;
     PosSrc src;
     for (int r = 0; r < 8; ++r) src.base[r] = c->peer_pos[c->pos_parity][r < c->cfg.nranks ? r : 0];
@@ -1627,6 +1654,7 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
       if (r != ncclSuccess) return fail(c, B200COORD_ERR_NCCL, std::string("ncclAllGather(positions): ") + api.GetErrorString(r));
       rc = collective_done(c);
       if (rc) return rc;
+      B200_TRACE(c, "positions all-gathered");
     }
     rc = run_device(c, c->d_pos.p, nullptr, sliced ? c->slot_begin : 0u, sliced ? c->slot_count : 0xffffffffu);
   }
@@ -1635,7 +1663,9 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   if (cnt) CU(c, cudaMemcpyAsync(deriv_slice, c->d_out.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaMemcpyAsync(c->h_small, c->d_out.p + 3 * (size_t)c->n, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st));
   CU(c, cudaEventRecord(c->ev[7], c->st));
+  B200_TRACE(c, "step enqueued, waiting for the stream");
   CU(c, cudaStreamSynchronize(c->st));
+  B200_TRACE(c, "step done");
   c->ev_valid[0] = c->ev_valid[3] = true;
   for (int i = 0; i < 9; ++i) virial[i] = c->h_small[i];
   *value = c->h_small[9];
