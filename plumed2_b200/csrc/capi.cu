@@ -247,6 +247,10 @@ bool trace_on() {
 
 int fail(b200coord_ctx* c, int code, const std::string& msg) {
   if (c) B200_TRACE(c, "FAIL %d: %s", code, msg.c_str());
+  // a context of an in-process group that fails leaves its peers waiting in their next collective: say why
+  if (c && c->in_process && !trace_on())
+    std::fprintf(stderr, "b200coord: device %d (rank %d of %d in this process) failed: %s\n", c->device, c->cfg.rank,
+                 c->cfg.nranks, msg.c_str());
   if (c) c->err = msg;
   g_last_error = msg;
   return code;

@@ -32,10 +32,14 @@ static void launch_one(const SweepArgs& a, const DevPbc& pbc, const DevSwitch& s
                        const unsigned long long* first_dev, const unsigned long long* end_dev, unsigned blocks, cudaStream_t st) {
   if (!blocks) return;
   constexpr size_t kDyn = (size_t)kTileCap * sizeof(SPos);
-  static bool configured = false;
-  if (!configured) {
+  // the attribute belongs to the function ON ONE DEVICE: several contexts of one process (b200coord_group_*) each
+  // need it (a per-process flag made the second device's launch fail with "invalid argument")
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(k_sweep_tile<K, PBC, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   k_sweep_tile<K, PBC, ACC><<<blocks, kSweepThreads, kDyn, st>>>(a, pbc, sw, work, first_dev, end_dev);
 }
