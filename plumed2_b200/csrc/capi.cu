@@ -846,8 +846,8 @@ int rebuild(b200coord_ctx* c, const double* d_pos) {
 // Several contexts in ONE process (b200coord_group_*, worker thread per device): a CUDA call that synchronises a device
 // -- the first launch of a kernel under lazy module loading, a growing local-memory pool, cudaFree -- can sit on a
 // driver lock while it waits for that device's NCCL kernel, which waits for a peer whose thread needs the same lock to
-// launch its part (seen as a hang of the 2-device group test).  So a thread of such a context does nothing else while
-// a collective of its context is in flight.  One process per device (MPI, torchrun) keeps the collectives asynchronous.
+// launch its part.  As a precaution a thread of such a context does nothing else while a collective of its context is
+// in flight.  One process per device (MPI, torchrun) keeps the collectives asynchronous.
 int collective_done(b200coord_ctx* c) {
   if (c->in_process) CU(c, cudaStreamSynchronize(c->st));
   return B200COORD_OK;
