@@ -35,6 +35,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;  // optional
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -55,6 +56,7 @@ NcclApi& nccl_api() {
   B200_SYM(GetUniqueId, "ncclGetUniqueId");
   B200_SYM(CommInitRank, "ncclCommInitRank");
   B200_SYM(CommDestroy, "ncclCommDestroy");
+  B200_SYM(CommAbort, "ncclCommAbort");
   B200_SYM(AllGather, "ncclAllGather");
   B200_SYM(AllReduce, "ncclAllReduce");
   B200_SYM(GroupStart, "ncclGroupStart");
@@ -207,6 +209,9 @@ struct b200coord_ctx {
   int filter_minb = 2;                // B200COORD_FILTER_MINB=3: the 80-register build of the flat filter (3 blocks per SM)
   bool tile_on = true;                // B200COORD_NO_TILE_SWEEP=1: the warp-per-row kernel instead
   bool in_process = false;            // one of several contexts of ONE process (b200coord_group_*), see collective_done
+  bool comm_aborted = false;          // the communicator was aborted after a failure of a group member: nothing to destroy
+  int test_fail_at = -1;              // B200COORD_TEST_FAIL=<rank>:<call>: the distributed call that fails on purpose (tests)
+  int dist_calls = 0;
   // frames known in advance (b200coord_submit / _collect): two steps in flight, copies on their own streams
   struct Pending {
     bool busy = false;
@@ -1328,6 +1333,10 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_PIN_HOST")) c->pin_host = (std::atoi(e) != 0);
   if (const char* e = std::getenv("B200COORD_FILTER_FLAT")) c->filter_flat = (std::atoi(e) != 0);
   if (const char* e = std::getenv("B200COORD_FILTER_MINB")) c->filter_minb = (std::atoi(e) == 3) ? 3 : 2;
+  if (const char* e = std::getenv("B200COORD_TEST_FAIL")) {  // "<rank>:<call>"
+    int rk = -1, call = -1;
+    if (std::sscanf(e, "%d:%d", &rk, &call) == 2 && rk == cfg->rank) c->test_fail_at = call;
+  }
   if (const char* e = std::getenv("B200COORD_NO_FAR_SPLIT")) c->far_split = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_SUPERLIST")) c->super_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_IMG_SWEEP")) c->img_on = (std::atoi(e) == 0);
@@ -1373,7 +1382,7 @@ void b200coord_destroy(b200coord_ctx* c) {
   for (auto& e : c->pinned)
     if (e.p) cudaHostUnregister(const_cast<void*>(e.p));
   cudaGetLastError();
-  if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+  if (c->comm && !c->comm_aborted && nccl_api().ok) nccl_api().CommDestroy(c->comm);
   c->d_pos.release(); c->d_out.release(); c->d_sderiv.release(); c->d_partials.release(); c->d_small.release();
   c->d_abs.release(); c->d_perm.release(); c->d_scell.release(); c->d_cell_of_slot.release(); c->d_tmp.release();
   c->d_ccount.release(); c->d_cstart.release(); c->d_cursor.release(); c->d_rowcount.release(); c->d_nbr.release();
@@ -1635,6 +1644,8 @@ int b200coord_calculate_distributed(b200coord_ctx* c, const double* pos_slice, d
   maybe_pin(c, 0, pos_slice, sizeof(double) * cnt);
   maybe_pin(c, 1, deriv_slice, sizeof(double) * cnt);
   int rc;
+  if (c->test_fail_at >= 0 && c->dist_calls++ == c->test_fail_at)
+    return fail(c, B200COORD_ERR_STATE, "failure injected by B200COORD_TEST_FAIL");
   B200_TRACE(c, "calculate_distributed: pull=%d list_valid=%d invalidate=%d", (int)step_can_pull(c), (int)c->list_valid, (int)c->invalidate);
   CU(c, cudaEventRecord(c->ev[0], c->st));
   if (step_can_pull(c)) {
@@ -1998,6 +2009,8 @@ struct b200coord_group {
   std::vector<int> rc;
   std::string err;
   unsigned n = 0;
+  bool broken = false;  // a member failed: its peers' communicators were aborted, the group only reports the error
+  int broken_rc = 0;
 };
 
 namespace {
@@ -2016,6 +2029,23 @@ void group_worker(b200coord_group* g, int r) {
     {
       std::lock_guard<std::mutex> lk(g->mu);
       g->rc[r] = rc;
+      if (rc && !g->broken && g->ctx.size() > 1) {
+        // The peers of a member that fails wait for it in their next collective, forever.  Abort their communicators
+        // (ncclCommAbort ends the operations in flight) so that every worker comes back; the group is unusable after.
+        g->broken = true;
+        g->broken_rc = rc;
+        g->err = "device " + std::to_string(g->ctx[(size_t)r] ? g->ctx[(size_t)r]->device : -1) + " (rank " + std::to_string(r) +
+                 "): " + (g->ctx[(size_t)r] ? g->ctx[(size_t)r]->err : g_last_error);
+        NcclApi& api = nccl_api();
+        if (api.CommAbort)
+          for (size_t o = 0; o < g->ctx.size(); ++o) {
+            b200coord_ctx* x = g->ctx[o];
+            if (x && x->comm && !x->comm_aborted) {
+              x->comm_aborted = true;
+              api.CommAbort(x->comm);
+            }
+          }
+      }
       if (--g->pending == 0) g->cv_done.notify_all();
     }
   }
@@ -2024,6 +2054,10 @@ void group_worker(b200coord_group* g, int r) {
 int group_run(b200coord_group* g, std::function<int(int)> fn) {
   {
     std::lock_guard<std::mutex> lk(g->mu);
+    if (g->broken) {
+      g_last_error = g->err;
+      return g->broken_rc ? g->broken_rc : B200COORD_ERR_STATE;
+    }
     g->task = std::move(fn);
     g->pending = (int)g->ctx.size();
     g->epoch++;
@@ -2031,6 +2065,10 @@ int group_run(b200coord_group* g, std::function<int(int)> fn) {
   g->cv_go.notify_all();
   std::unique_lock<std::mutex> lk(g->mu);
   g->cv_done.wait(lk, [&] { return g->pending == 0; });
+  if (g->broken) {
+    g_last_error = g->err;
+    return g->broken_rc;
+  }
   for (size_t r = 0; r < g->ctx.size(); ++r)
     if (g->rc[r]) {
       g->err = "rank " + std::to_string(r) + ": " + (g->ctx[r] ? g->ctx[r]->err : g_last_error);

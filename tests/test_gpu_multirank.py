@@ -151,3 +151,43 @@ def test_group_of_devices_in_one_process(ndev):
             assert rel_err(der, ref["deriv"]) <= 1e-10 and rel_err(vir.reshape(3, 3), ref["virial"]) <= 1e-10, (line, step)
         L.b200coord_group_destroy(g)
         single.close()
+
+
+def test_group_member_that_fails_does_not_leave_its_peers_waiting(monkeypatch):
+    """a device of an in-process group that fails before a collective (here on purpose: B200COORD_TEST_FAIL=<rank>:<call>)
+    used to leave the other workers in their all-reduce forever; now their communicators are aborted, the call returns
+    the member's error, and the group keeps reporting it"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import time
+    import plumed2_b200 as P
+    from plumed2_b200 import capi
+    L = capi.lib()
+    n = 4000
+    pos, box = water_box(n, 100.0, seed=53)
+    line = "c: COORDINATION GROUPA=1-4000 SWITCH={RATIONAL R_0=0.3 D_MAX=0.8} NLIST NL_CUTOFF=1.0 NL_STRIDE=5"
+    single = P.Coordination.from_input(line, device=0)
+    cfg = capi.Config.from_buffer_copy(single._cfg)
+    devs = (C.c_int * 2)(0, 1)
+    g = C.c_void_p()
+    absidx = np.ascontiguousarray(single.atoms)
+    monkeypatch.setenv("B200COORD_TEST_FAIL", "1:1")
+    capi.check(L.b200coord_group_create(C.byref(cfg), C.byref(single.switch), absidx.ctypes.data_as(C.POINTER(C.c_uint)),
+                                        devs, 2, C.byref(g)))
+    monkeypatch.delenv("B200COORD_TEST_FAIL")
+    b9 = np.ascontiguousarray(box.reshape(9))
+    der, vir, val = np.zeros((n, 3)), np.zeros(9), C.c_double(0)
+    rcs = []
+    t0 = time.time()
+    for step in range(3):
+        will = C.c_int(0)
+        L.b200coord_group_prepare(g, step, 0, C.byref(will))
+        L.b200coord_group_set_box(g, b9.ctypes.data_as(C.POINTER(C.c_double)))
+        p = np.ascontiguousarray(pos + 0.001 * step)
+        rcs.append(L.b200coord_group_calculate(g, p.ctypes.data_as(C.c_void_p), C.byref(val), der.ctypes.data_as(C.c_void_p),
+                                               vir.ctypes.data_as(C.POINTER(C.c_double))))
+    assert rcs[0] == 0 and rcs[1] != 0 and rcs[2] != 0, rcs
+    assert b"injected" in L.b200coord_group_last_error(g)
+    assert time.time() - t0 < 60
+    L.b200coord_group_destroy(g)
+    single.close()
