@@ -1412,6 +1412,9 @@ void b200coord_destroy(b200coord_ctx* c) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2 * b200coord_ctx::kRing; ++i)
     if (c->sweep_ev[i]) cudaEventDestroy(c->sweep_ev[i]);
+  // frames still in flight (b200coord_submit without a collect): their copies touch the caller's buffers
+  if (c->st_up) cudaStreamSynchronize(c->st_up);
+  if (c->st_down) cudaStreamSynchronize(c->st_down);
   for (int i = 0; i < 2; ++i) {
     c->d_posq[i].release();
     c->d_outq[i].release();
