@@ -493,8 +493,8 @@ __device__ __forceinline__ void prefetch_l2_idx(const uint32_t* __restrict__ bas
   asm volatile("{\n\t.reg .u64 p;\n\tmad.wide.u32 p, %0, 4, %1;\n\tprefetch.global.L2 [p];\n\t}" ::"r"(idx), "l"(base));
 }
 
-template <bool FILL, bool CAPPED, bool SUPER, bool IMAGES>
-__global__ void __launch_bounds__(256, 4)
+template <bool FILL, bool CAPPED, bool SUPER, bool IMAGES, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     k_nl_rows_f32(const double* __restrict__ pos, const uint32_t* __restrict__ perm, const float4* __restrict__ lpos,
                   const uint32_t* __restrict__ scell,
                   const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount, DevGrid g,
@@ -1215,18 +1215,26 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
 #define B200_F32_ARGS pos, perm, lpos, scell, cstart, ccount, g, pbc_g, f, cutoff2, n_a, two_groups, row_begin, row_end, \
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
-  if (super) {  // super-list rows: always with images
-    if (mode == 0) k_nl_rows_f32<false, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else if (mode == 1) k_nl_rows_f32<true, false, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, true, true, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  } else if (mode == 0) k_nl_rows_f32<false, false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  else if (images) {
-    if (mode == 1) k_nl_rows_f32<true, false, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, true, false, true><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  } else {
-    if (mode == 1) k_nl_rows_f32<true, false, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-    else k_nl_rows_f32<true, true, false, false><<<blocks, 256, 0, st>>>(B200_F32_ARGS);
-  }
+  // resident blocks per SM the register allocation is sized for: 4 -> 64 registers (spills ~120 bytes), 3 -> 80
+  static const int minb = [] { const char* e = std::getenv("B200COORD_ROWS_MINB"); return (e && std::atoi(e) == 3) ? 3 : 4; }();
+#define B200_F32_GO(MB)                                                                                          \
+  do {                                                                                                           \
+    if (super) { /* super-list rows: always with images */                                                       \
+      if (mode == 0) k_nl_rows_f32<false, false, true, true, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);          \
+      else if (mode == 1) k_nl_rows_f32<true, false, true, true, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);      \
+      else k_nl_rows_f32<true, true, true, true, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);                      \
+    } else if (mode == 0) k_nl_rows_f32<false, false, false, false, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);   \
+    else if (images) {                                                                                           \
+      if (mode == 1) k_nl_rows_f32<true, false, false, true, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);          \
+      else k_nl_rows_f32<true, true, false, true, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);                     \
+    } else {                                                                                                     \
+      if (mode == 1) k_nl_rows_f32<true, false, false, false, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);         \
+      else k_nl_rows_f32<true, true, false, false, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);                    \
+    }                                                                                                            \
+  } while (0)
+  if (minb == 3) B200_F32_GO(3);
+  else B200_F32_GO(4);
+#undef B200_F32_GO
 #undef B200_F32_ARGS
 }
 
