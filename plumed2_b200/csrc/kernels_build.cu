@@ -1216,7 +1216,12 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
                       row_count, row_start, nbr, row_cap, cap_info, far2, row_far_off, row_far_cnt
   if (mode == 2) k_regular_offsets<<<(rows + 255) / 256, 256, 0, st>>>(rows, row_cap, row_start);
   // resident blocks per SM the register allocation is sized for: 4 -> 64 registers (spills ~120 bytes), 3 -> 80
-  static const int minb = [] { const char* e = std::getenv("B200COORD_ROWS_MINB"); return (e && std::atoi(e) == 3) ? 3 : 4; }();
+  // (60 bytes), 2 -> no spills
+  static const int minb = [] {
+    const char* e = std::getenv("B200COORD_ROWS_MINB");
+    const int v = e ? std::atoi(e) : 3;
+    return (v == 2 || v == 4) ? v : 3;  // measured at 1 M atoms: 7.93 ms (4), 7.46 ms (3)
+  }();
 #define B200_F32_GO(MB)                                                                                          \
   do {                                                                                                           \
     if (super) { /* super-list rows: always with images */                                                       \
@@ -1232,8 +1237,9 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
       else k_nl_rows_f32<true, true, false, false, MB><<<blocks, 256, 0, st>>>(B200_F32_ARGS);                    \
     }                                                                                                            \
   } while (0)
-  if (minb == 3) B200_F32_GO(3);
-  else B200_F32_GO(4);
+  if (minb == 2) B200_F32_GO(2);
+  else if (minb == 4) B200_F32_GO(4);
+  else B200_F32_GO(3);
 #undef B200_F32_GO
 #undef B200_F32_ARGS
 }
