@@ -1220,7 +1220,7 @@ void launch_nl_rows_f32(int mode /*0 count, 1 fill, 2 capped single pass*/, bool
   static const int minb = [] {
     const char* e = std::getenv("B200COORD_ROWS_MINB");
     const int v = e ? std::atoi(e) : 3;
-    return (v == 2 || v == 4) ? v : 3;  // measured at 1 M atoms: 7.93 ms (4), 7.46 ms (3)
+    return (v == 2 || v == 4) ? v : 3;  // measured at 1 M atoms, whole rebuild: 7.93 ms (4), 7.46 ms (3), 9.03 ms (2)
   }();
 #define B200_F32_GO(MB)                                                                                          \
   do {                                                                                                           \
