@@ -165,7 +165,6 @@ struct b200coord_ctx {
   unsigned long sort_box_epoch = 0;   // box at the last re-sort (wpos / braw / images refer to it)
   DevBuf<uint4> d_meta;               // per row {start / 4, near count, far offset, far count}
   int img_variant = 2;                // resident blocks per SM the image sweep is compiled for (B200COORD_IMG_VARIANT)
-  unsigned img_prefetch = 2;          // B200COORD_IMG_PREFETCH: trips between the L2 prefetch of the entries and their use
   bool img_on = true;                 // B200COORD_NO_IMG_SWEEP=1: always the general kernel
   bool scatter_on = true;             // B200COORD_NO_SCATTER=1: sweep GROUPB rows even when they are short
   DevBuf<uint32_t> d_rowfar;   // [0,rows) offset of the far part inside the row's allocation, [rows, 2 rows) its length
@@ -1001,7 +1000,6 @@ int run_device(b200coord_ctx* c, const double* d_pos, double* out = nullptr, uns
     a.row_meta = c->d_meta.p;
     a.pos = src;
     a.executed = c->d_u64.p + 12;
-    a.pf_dist = c->img_prefetch;
     // image sweep: valid while a listed pair cannot have a second image as close as the stored one, i.e. while
     // NL_CUTOFF + 2 * displacement < half the smallest box height (any lattice vector is at least that long)
     a.img_disp2_max = 0.0;
@@ -1345,7 +1343,6 @@ int b200coord_create(const b200coord_config* cfg, const b200coord_switch* sw, co
   if (const char* e = std::getenv("B200COORD_NO_TILE_SWEEP")) c->tile_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_NO_SCATTER")) c->scatter_on = (std::atoi(e) == 0);
   if (const char* e = std::getenv("B200COORD_IMG_VARIANT")) c->img_variant = std::atoi(e);
-  if (const char* e = std::getenv("B200COORD_IMG_PREFETCH")) c->img_prefetch = (unsigned)std::min(5, std::max(1, std::atoi(e)));
   needed_all(c);
   *out = c;
   return B200COORD_OK;

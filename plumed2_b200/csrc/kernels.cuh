@@ -222,7 +222,6 @@ struct SweepArgs {
   double* partials;        // kPartialStride doubles per block
   unsigned long long* evals;  // list entries of the rows swept (both directions)
   unsigned long long* executed;  // entries actually evaluated (far parts that were skipped do not count)
-  unsigned pf_dist;              // image sweep: trips between the L2 prefetch of the entry stream and its use
   // box and switch parameters in global memory, for the out-of-line row patch (sweep_math.cuh: row_fixup_*)
   const DevPbc* pbc_g;
   const DevSwitch* sw_g;

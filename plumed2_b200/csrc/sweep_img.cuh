@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
   // warp's l-th row), so the hot loop's "iterator" is one 8-byte shared-memory load: no branches, no state.
   //   .x = first entry of the trip relative to the block's first row, .y = entries left in the part | row slot << 16 | flags
   constexpr unsigned kOk = 0x80000000u, kFar = 0x40000000u, kRem = 0xffffu;
-  __shared__ uint2 s_trip[kSweepWarps][kImgTripCap + 8];
+  __shared__ uint2 s_trip[kSweepWarps][kImgTripCap + 4];
   const uint32_t base4 = nrows ? s_meta[0].x : 0u;
   const uint32_t* __restrict__ blk = a.nbr + 4ull * base4 + lane;  // rows of a block are stored in order
   {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     for (unsigned t = 0; t < tn; ++t) s_trip[wid][at++] = make_uint2(off0 + 64u * t, (m.y - 64u * t) | (lane << 16) | kOk);
     for (unsigned t = 0; t < tf; ++t)
       s_trip[wid][at++] = make_uint2(off0 + m.z + 64u * t, (m.w - 64u * t) | (lane << 16) | kOk | kFar);
-    if (lane < 8u) s_trip[wid][total + lane] = make_uint2(0u, 0u);  // the pipeline reads up to eight trips past the end
+    if (lane < 4u) s_trip[wid][total + lane] = make_uint2(0u, 0u);  // the pipeline reads up to four trips past the end
     unsigned mine = m.y + (far_on ? m.w : 0u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     __syncwarp();
   }
   unsigned it = 0u;  // next trip of the table
-  const unsigned pf_dist = a.pf_dist;  // how far down the table the L2 prefetch looks (2; B200COORD_IMG_PREFETCH 1..5)
   uint2 it_d = s_trip[wid][0];
   // entries of the table's next trip (0 = sorted atom 0 through the home image: a valid record, masked out later)
   auto entry = [&](unsigned off) -> uint32_t { return (off + lane < (it_d.y & kRem)) ? __ldg(blk + it_d.x + off) : 0u; };
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2)
     // The entries stream from HBM, one 256-byte piece per warp and trip from ~2400 places at once; measured, a trip
     // (~1300 cycles) is not always enough for that round trip.  Ask L2 for the piece of the trip two further down
     // the table (8 bytes per lane cover its 256 bytes); the load above then finds its piece in L2.
-    const uint2 pd = s_trip[wid][it + pf_dist];
+    const uint2 pd = s_trip[wid][it + 2];
     asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + pd.x + lane));
   };
   Set A, B;
